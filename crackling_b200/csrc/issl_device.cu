@@ -1,0 +1,830 @@
+// issl_device.cu -- device-side half of libissl_cuda: index residency (re-layout from an .issl
+// image or on-device construction), and the scoring pipeline
+//     scan items -> K1 scan -> radix sort of survivor keys -> K2a contributions -> K2b ordered
+//     accumulation (with the reference's early exit) -> finalise.
+// "ref:" = /root/reference/src/ISSL/.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "issl_internal.h"
+#include "issl_kernels.cuh"
+
+using namespace issl;
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return issl_set_error(ISSL_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKR(call)                       \
+    do {                                \
+        int r_ = (call);                \
+        if (r_ != ISSL_OK) return r_;   \
+    } while (0)
+
+namespace {
+
+// growable device buffer
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return ISSL_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) { p = nullptr; return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+            cap = bytes;
+        } else cap = want;
+        return ISSL_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+struct issl_device {
+    int dev = -1;
+    issl_info info{};
+    IndexView iv{};
+    int layout = 0;
+    uint64_t nLists = 0;
+    uint64_t hbmBytes = 0;
+    int pbits = 0;
+
+    // index storage
+    DBuf sig, occ, ids, res32, sig64, listStart, listLen, filePrefix, mitMasks, mitScores;
+    uint32_t mitCount = 0;
+    std::vector<uint64_t> hMitMasks;   // as loaded/generated (for write_issl)
+    std::vector<double> hMitScores;
+    std::vector<uint64_t> hListLen, hListStart, hFilePrefix;
+
+    // scoring scratch
+    cudaStream_t stream = nullptr;
+    DBuf guides, totMit, totCfd, done, pairCounts, pairOffsets, items, keysA, keysB, sortTemp, scanTemp,
+        contribMit, contribCfd, counters, outMit, outCfd, hitId, hitDist, hitOcc, scoredEnd, segBegin;
+    unsigned long long *hCounters = nullptr;   // pinned: [0] total candidates, [1] hit count, [2] items, [3] done
+    uint64_t hitCap = 0;
+    std::vector<cudaEvent_t> evPool;
+    issl_stats stats{};
+    uint32_t maxBatch = 1u << 20;
+};
+
+// ---------------------------------------------------------------------------------------------
+// devices
+// ---------------------------------------------------------------------------------------------
+extern "C" int issl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int usable = 0;
+    for (int d = 0; d < n; d++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) usable++;
+    }
+    return usable;
+}
+
+static int select_device(int cuda_device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return issl_set_error(ISSL_ERR_NO_DEVICE, "no CUDA device available (%s); libissl_cuda has no CPU fallback",
+                              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (cuda_device < 0 || cuda_device >= n)
+        return issl_set_error(ISSL_ERR_NO_DEVICE, "CUDA device %d does not exist (%d present)", cuda_device, n);
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, cuda_device));
+    if (p.major != 10)
+        return issl_set_error(ISSL_ERR_NO_DEVICE, "CUDA device %d (%s, sm_%d%d) is not an sm_100 part; libissl_cuda is built for sm_100a only",
+                              cuda_device, p.name, p.major, p.minor);
+    CK(cudaSetDevice(cuda_device));
+    return ISSL_OK;
+}
+
+static int upload_constants()
+{
+    CK(cudaMemcpyToSymbol(c_cfdPos, ISSL_CFD_POS, sizeof(double) * 320));
+    CK(cudaMemcpyToSymbol(c_cfdPam, ISSL_CFD_PAM, sizeof(double) * 16));
+    return ISSL_OK;
+}
+
+static int choose_layout(const issl_info &f, int requested, int *out)
+{
+    const uint32_t w = (uint32_t)f.sliceWidth, kb = std::min<uint32_t>(w, 8);
+    const bool res32ok = (w % 2 == 0) && (2 * f.seqLength >= kb) && (2 * f.seqLength - kb <= 32);
+    if (requested == ISSL_LAYOUT_AUTO) requested = res32ok ? ISSL_LAYOUT_RES32 : ISSL_LAYOUT_SIG64;
+    if (requested == ISSL_LAYOUT_RES32 && !res32ok)
+        return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout RES32 needs an even slice width and 2*seqLength - min(width,8) <= 32");
+    if (requested != ISSL_LAYOUT_RES32 && requested != ISSL_LAYOUT_SIG64 && requested != ISSL_LAYOUT_GATHER)
+        return issl_set_error(ISSL_ERR_ARG, "unknown layout %d", requested);
+    *out = requested;
+    return ISSL_OK;
+}
+
+// common tail of both constructors: header-derived fields, list geometry, storage
+static int init_geometry(issl_device *d, const issl_info &f, int layout, const uint64_t *listLen /* host, nLists */)
+{
+    d->info = f;
+    d->layout = layout;
+    const uint64_t sliceLimit = 1ull << f.sliceWidth;
+    d->nLists = f.sliceCount * sliceLimit;
+    d->hListLen.assign(listLen, listLen + d->nLists);
+    d->hListStart.resize(d->nLists);
+    d->hFilePrefix.resize(d->nLists + 1);
+    uint64_t p = 0, q = 0;
+    for (uint64_t i = 0; i < d->nLists; i++) {
+        d->hListStart[i] = p;
+        d->hFilePrefix[i] = q;
+        q += listLen[i];
+        p += (listLen[i] + kListAlign - 1) / kListAlign * kListAlign;
+    }
+    d->hFilePrefix[d->nLists] = q;
+    const uint64_t P = p + kListAlign;   // slack so that no vector load can leave the allocation
+    d->pbits = 1;
+    while ((1ull << d->pbits) < P) d->pbits++;
+    if (d->pbits > 40) return issl_set_error(ISSL_ERR_UNSUPPORTED, "index too large: %llu list positions", (unsigned long long)P);
+
+    const uint64_t N = f.offtargetsCount;
+    CKR(d->sig.ensure(N * 8));
+    CKR(d->occ.ensure(N * 4));
+    CKR(d->ids.ensure(P * 4));
+    CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
+    if (layout == ISSL_LAYOUT_RES32) { CKR(d->res32.ensure(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
+    if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.ensure(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
+    CKR(d->listStart.ensure(d->nLists * 8));
+    CKR(d->listLen.ensure(d->nLists * 8));
+    CKR(d->filePrefix.ensure((d->nLists + 1) * 8));
+    CK(cudaMemcpyAsync(d->listStart.p, d->hListStart.data(), d->nLists * 8, cudaMemcpyHostToDevice, d->stream));
+    CK(cudaMemcpyAsync(d->listLen.p, d->hListLen.data(), d->nLists * 8, cudaMemcpyHostToDevice, d->stream));
+    CK(cudaMemcpyAsync(d->filePrefix.p, d->hFilePrefix.data(), (d->nLists + 1) * 8, cudaMemcpyHostToDevice, d->stream));
+
+    IndexView &v = d->iv;
+    v.sig = d->sig.as<uint64_t>();
+    v.occ = d->occ.as<uint32_t>();
+    v.ids = d->ids.as<uint32_t>();
+    v.res32 = d->res32.as<uint32_t>();
+    v.sig64 = d->sig64.as<uint64_t>();
+    v.listStart = d->listStart.as<uint64_t>();
+    v.listLen = d->listLen.as<uint64_t>();
+    v.N = N; v.P = P;
+    v.seqLength = (uint32_t)f.seqLength; v.sliceWidth = (uint32_t)f.sliceWidth;
+    v.sliceCount = (uint32_t)f.sliceCount; v.sliceLimit = (uint32_t)sliceLimit;
+    v.sliceMask = (uint32_t)(sliceLimit - 1);
+    v.knownBits = std::min<uint32_t>((uint32_t)f.sliceWidth, 8);
+    v.layout = layout;
+
+    d->hbmBytes = N * 12 + P * 4 + (layout == ISSL_LAYOUT_RES32 ? P * 4 : 0) + (layout == ISSL_LAYOUT_SIG64 ? P * 8 : 0) +
+                  d->nLists * 24;
+    return ISSL_OK;
+}
+
+static int upload_mit_table(issl_device *d)
+{
+    d->mitCount = (uint32_t)d->hMitMasks.size();
+    CKR(d->mitMasks.ensure(std::max<size_t>(1, d->mitCount) * 8));
+    CKR(d->mitScores.ensure(std::max<size_t>(1, d->mitCount) * 8));
+    if (d->mitCount) {
+        CK(cudaMemcpyAsync(d->mitMasks.p, d->hMitMasks.data(), d->mitCount * 8ull, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->mitScores.p, d->hMitScores.data(), d->mitCount * 8ull, cudaMemcpyHostToDevice, d->stream));
+    }
+    d->hbmBytes += d->mitCount * 16ull;
+    return ISSL_OK;
+}
+
+static int new_device(int cuda_device, issl_device **out)
+{
+    CKR(select_device(cuda_device));
+    issl_device *d = new issl_device();
+    d->dev = cuda_device;
+    if (const char *e = getenv("ISSL_BATCH")) {
+        const long v = atol(e);
+        if (v > 0 && v <= (1 << 24)) d->maxBatch = (uint32_t)v;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&d->hCounters, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        delete d;
+        return issl_set_error(ISSL_ERR_CUDA, "device %d setup: %s", cuda_device, cudaGetErrorString(e));
+    }
+    int rc = upload_constants();
+    if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
+    *out = d;
+    return ISSL_OK;
+}
+
+extern "C" void issl_device_destroy(issl_device *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->dev);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (DBuf *b : {&d->sig, &d->occ, &d->ids, &d->res32, &d->sig64, &d->listStart, &d->listLen, &d->filePrefix,
+                    &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairCounts,
+                    &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
+                    &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
+                    &d->scoredEnd, &d->segBegin})
+        b->release();
+    for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
+    if (d->hCounters) cudaFreeHost(d->hCounters);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// residency from an .issl image
+// ---------------------------------------------------------------------------------------------
+extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int layout, issl_device **out)
+{
+    if (!ix || !out) return issl_set_error(ISSL_ERR_ARG, "issl_device_create: null argument");
+    *out = nullptr;
+    int lay = 0;
+    CKR(choose_layout(ix->info, layout, &lay));
+    issl_device *d = nullptr;
+    CKR(new_device(cuda_device, &d));
+    auto fail = [&](int rc) { issl_device_destroy(d); return rc; };
+
+    int rc = init_geometry(d, ix->info, lay, ix->sizes);
+    if (rc != ISSL_OK) return fail(rc);
+    issl_sorted_score_table(ix->scorePairs, ix->scoresInFile, d->hMitMasks, d->hMitScores);
+    if ((rc = upload_mit_table(d)) != ISSL_OK) return fail(rc);
+
+    const uint64_t N = ix->info.offtargetsCount, S = ix->info.sliceCount;
+    // signatures first (the re-layout kernel gathers them)
+    constexpr size_t kStage = 64ull << 20;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t freeEv[2] = {nullptr, nullptr};
+    DBuf dstage[2];
+    unsigned long long *dErr = nullptr;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; b++) {
+            if (stage[b]) cudaFreeHost(stage[b]);
+            if (freeEv[b]) cudaEventDestroy(freeEv[b]);
+            dstage[b].release();
+        }
+        if (dErr) cudaFree(dErr);
+    };
+#define CKF(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            issl_set_error(ISSL_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            cleanup();                                                                                    \
+            return fail(ISSL_ERR_CUDA);                                                                   \
+        }                                                                                                 \
+    } while (0)
+    for (int b = 0; b < 2; b++) {
+        CKF(cudaMallocHost(&stage[b], kStage + 8));
+        CKF(cudaEventCreateWithFlags(&freeEv[b], cudaEventDisableTiming));
+        if (dstage[b].ensure(kStage + 8) != ISSL_OK) { cleanup(); return fail(ISSL_ERR_NOMEM); }
+    }
+    CKF(cudaMalloc(&dErr, 8));
+    CKF(cudaMemsetAsync(dErr, 0, 8, d->stream));
+
+    int buf = 0;
+    // 1) signatures: host image -> pinned -> device
+    for (uint64_t o = 0; o < N * 8; o += kStage) {
+        const size_t n = (size_t)std::min<uint64_t>(kStage, N * 8 - o);
+        CKF(cudaEventSynchronize(freeEv[buf]));
+        memcpy(stage[buf], reinterpret_cast<const uint8_t *>(ix->offtargets) + o, n);
+        CKF(cudaMemcpyAsync(d->sig.as<uint8_t>() + o, stage[buf], n, cudaMemcpyHostToDevice, d->stream));
+        CKF(cudaEventRecord(freeEv[buf], d->stream));
+        buf ^= 1;
+    }
+    // 2) lists, slice by slice, in chunks carrying one entry of overlap for the ascending-id check
+    const uint64_t chunkEntries = kStage / 8;
+    for (uint64_t s = 0; s < S; s++) {
+        for (uint64_t q0 = s * N; q0 < (s + 1) * N; q0 += chunkEntries) {
+            const uint64_t n = std::min<uint64_t>(chunkEntries, (s + 1) * N - q0);
+            const int hasPrev = q0 > s * N;
+            CKF(cudaEventSynchronize(freeEv[buf]));
+            memcpy(stage[buf], ix->entries + q0 - hasPrev, (n + hasPrev) * 8);
+            CKF(cudaMemcpyAsync(dstage[buf].p, stage[buf], (n + hasPrev) * 8, cudaMemcpyHostToDevice, d->stream));
+            RelayoutArgs a;
+            a.iv = d->iv; a.entries = dstage[buf].as<uint64_t>(); a.filePrefix = d->filePrefix.as<uint64_t>();
+            a.q0 = q0; a.n = n; a.slice = (uint32_t)s; a.hasPrev = hasPrev; a.errors = dErr;
+            k_relayout<<<blocks_for(n, 256), 256, 0, d->stream>>>(a);
+            CKF(cudaGetLastError());
+            CKF(cudaEventRecord(freeEv[buf], d->stream));
+            buf ^= 1;
+        }
+    }
+    CKF(cudaMemcpyAsync(d->hCounters, dErr, 8, cudaMemcpyDeviceToHost, d->stream));
+    CKF(cudaStreamSynchronize(d->stream));
+#undef CKF
+    const unsigned long long bad = d->hCounters[0];
+    cleanup();
+    if (bad)
+        return fail(issl_set_error(ISSL_ERR_UNSUPPORTED,
+                                   "Error reading index: %llu list entries violate the isslCreateIndex invariants "
+                                   "(id range, list membership, ascending ids or occurrence counts)", bad));
+    *out = d;
+    return ISSL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// on-device construction from sorted keys (synthetic indexes)
+// ---------------------------------------------------------------------------------------------
+static int build_from_sites(issl_device *d, int layout, uint64_t *dKeys, uint64_t nRaw, uint32_t L, uint32_t w,
+                            DBuf &keysAlt)
+{
+    cudaStream_t st = d->stream;
+    // sort raw keys (lexicographic site order)
+    {
+        cub::DoubleBuffer<uint64_t> db(dKeys, keysAlt.as<uint64_t>());
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, nRaw, 0, (int)(2 * L), st));
+        DBuf tmp; CKR(tmp.ensure(tb));
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, nRaw, 0, (int)(2 * L), st));
+        CK(cudaStreamSynchronize(st));
+        tmp.release();
+        if (db.Current() != dKeys) CK(cudaMemcpyAsync(dKeys, db.Current(), nRaw * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    // run-length collapse (ref isslCreateIndex.cpp:184-207)
+    DBuf flags, ranks, runStart;
+    CKR(flags.ensure(nRaw * 4));
+    CKR(ranks.ensure(nRaw * 8));
+    k_run_flags<<<blocks_for(nRaw, 256), 256, 0, st>>>(dKeys, nRaw, flags.as<uint32_t>());
+    {
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tb, flags.as<uint32_t>(), ranks.as<uint64_t>(), nRaw, st));
+        DBuf tmp; CKR(tmp.ensure(tb));
+        CK(cub::DeviceScan::InclusiveSum(tmp.p, tb, flags.as<uint32_t>(), ranks.as<uint64_t>(), nRaw, st));
+        CK(cudaMemcpyAsync(d->hCounters, ranks.as<uint64_t>() + (nRaw - 1), 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        tmp.release();
+    }
+    const uint64_t N = d->hCounters[0];
+    if (N >= (1ull << 32)) return issl_set_error(ISSL_ERR_UNSUPPORTED, "synthetic index: more than 2^32 distinct sites");
+
+    issl_info f{};
+    f.offtargetsCount = N; f.seqLength = L; f.seqCount = nRaw; f.sliceWidth = w; f.sliceCount = (2 * L) / w;
+    // score table exactly as the reference builder would store it (ref isslCreateIndex.cpp:239-252)
+    {
+        uint64_t sc = 0;
+        issl_mit_table(L, w, nullptr, nullptr, 0, &sc);
+        d->hMitMasks.resize(sc); d->hMitScores.resize(sc);
+        issl_mit_table(L, w, d->hMitMasks.data(), d->hMitScores.data(), sc, &sc);
+        f.scoresCount = sc;
+    }
+
+    // signatures + occurrences into temporaries (init_geometry needs the list lengths first)
+    DBuf sigTmp, occTmp;
+    CKR(sigTmp.ensure(N * 8)); CKR(occTmp.ensure(N * 4)); CKR(runStart.ensure(N * 8));
+    k_run_scatter<<<blocks_for(nRaw, 256), 256, 0, st>>>(dKeys, flags.as<uint32_t>(), ranks.as<uint64_t>(), nRaw, L,
+                                                        sigTmp.as<uint64_t>(), runStart.as<uint64_t>());
+    k_run_lengths<<<blocks_for(N, 256), 256, 0, st>>>(runStart.as<uint64_t>(), N, nRaw, occTmp.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    flags.release(); ranks.release(); runStart.release();
+
+    // per-slice values, histograms
+    const uint64_t S = f.sliceCount, sliceLimit = 1ull << w;
+    const uint32_t smask = (uint32_t)(sliceLimit - 1);
+    DBuf values, valuesSorted, idsTmp, idsSorted, hist, valueStart;
+    CKR(values.ensure(N)); CKR(valuesSorted.ensure(N)); CKR(idsTmp.ensure(N * 4)); CKR(idsSorted.ensure(N * 4));
+    CKR(hist.ensure(S * 256 * 8)); CKR(valueStart.ensure(256 * 8));
+    CK(cudaMemsetAsync(hist.p, 0, S * 256 * 8, st));
+    // pass A: histograms of all slices (list lengths), so that geometry can be fixed
+    for (uint64_t s = 0; s < S; s++)
+        k_slice_values<<<148 * 8, 256, 0, st>>>(sigTmp.as<uint64_t>(), N, w, smask, (uint32_t)s, values.as<uint8_t>(),
+                                               idsTmp.as<uint32_t>(), hist.as<unsigned long long>() + s * 256);
+    std::vector<unsigned long long> hHist(S * 256);
+    CK(cudaMemcpyAsync(hHist.data(), hist.p, S * 256 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<uint64_t> listLen(S * sliceLimit, 0);
+    for (uint64_t s = 0; s < S; s++)
+        for (uint64_t v = 0; v < 256 && v < sliceLimit; v++) listLen[s * sliceLimit + v] = hHist[s * 256 + v];
+
+    CKR(init_geometry(d, f, layout, listLen.data()));
+    CKR(upload_mit_table(d));
+    CK(cudaMemcpyAsync(d->sig.p, sigTmp.p, N * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(d->occ.p, occTmp.p, N * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    sigTmp.release(); occTmp.release();
+
+    // pass B: per slice, stable 8-bit radix sort of (value, id) and placement (ref :216-234)
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, values.as<uint8_t>(), valuesSorted.as<uint8_t>(), idsTmp.as<uint32_t>(),
+                                       idsSorted.as<uint32_t>(), N, 0, 8, st));
+    DBuf tmp; CKR(tmp.ensure(tb));
+    for (uint64_t s = 0; s < S; s++) {
+        k_slice_values<<<148 * 8, 256, 0, st>>>(d->sig.as<uint64_t>(), N, w, smask, (uint32_t)s, values.as<uint8_t>(),
+                                               idsTmp.as<uint32_t>(), hist.as<unsigned long long>() + s * 256);
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, values.as<uint8_t>(), valuesSorted.as<uint8_t>(), idsTmp.as<uint32_t>(),
+                                           idsSorted.as<uint32_t>(), N, 0, 8, st));
+        uint64_t vs[256], acc = 0;
+        for (int v = 0; v < 256; v++) { vs[v] = acc; acc += hHist[s * 256 + v]; }
+        CK(cudaMemcpyAsync(valueStart.p, vs, sizeof vs, cudaMemcpyHostToDevice, st));
+        k_place_slice<<<blocks_for(N, 256), 256, 0, st>>>(d->iv, valuesSorted.as<uint8_t>(), idsSorted.as<uint32_t>(), N,
+                                                         (uint32_t)s, valueStart.as<uint64_t>());
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));   // vs[] is a stack buffer
+    }
+    for (DBuf *b : {&values, &valuesSorted, &idsTmp, &idsSorted, &hist, &valueStart, &tmp}) b->release();
+    return ISSL_OK;
+}
+
+extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uint64_t uniform_sites,
+                                            uint32_t families, uint32_t family_size, double max_sub_rate,
+                                            uint32_t seqLength, uint32_t sliceWidth, issl_device **out)
+{
+    if (!out) return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: null argument");
+    *out = nullptr;
+    if (seqLength == 0 || seqLength > 32 || sliceWidth < 2 || sliceWidth > 24 || (2 * seqLength) / sliceWidth == 0)
+        return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: bad sequence length / slice width");
+    const uint64_t nRaw = uniform_sites + (uint64_t)families * family_size;
+    if (nRaw == 0) return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: no sites");
+    issl_info f{};
+    f.seqLength = seqLength; f.sliceWidth = sliceWidth; f.sliceCount = (2 * seqLength) / sliceWidth;
+    int lay = 0;
+    CKR(choose_layout(f, layout, &lay));
+    issl_device *d = nullptr;
+    CKR(new_device(cuda_device, &d));
+    DBuf keys, keysAlt;
+    int rc = keys.ensure(nRaw * 8);
+    if (rc == ISSL_OK) rc = keysAlt.ensure(nRaw * 8);
+    if (rc == ISSL_OK) {
+        k_synth_sites<<<blocks_for(nRaw, 256), 256, 0, d->stream>>>(seed, uniform_sites, families, family_size, max_sub_rate,
+                                                                   seqLength, keys.as<uint64_t>());
+        rc = build_from_sites(d, lay, keys.as<uint64_t>(), nRaw, seqLength, sliceWidth, keysAlt);
+    }
+    keys.release(); keysAlt.release();
+    if (rc == ISSL_OK) {
+        cudaError_t e = cudaStreamSynchronize(d->stream);
+        if (e != cudaSuccess) rc = issl_set_error(ISSL_ERR_CUDA, "synthetic build: %s", cudaGetErrorString(e));
+    }
+    if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
+    *out = d;
+    return ISSL_OK;
+}
+
+extern "C" int issl_device_get_info(const issl_device *d, issl_device_info *out)
+{
+    if (!d || !out) return issl_set_error(ISSL_ERR_ARG, "issl_device_get_info: null argument");
+    out->cuda_device = d->dev;
+    out->layout = d->layout;
+    out->bytes_per_candidate = d->layout == ISSL_LAYOUT_RES32 ? 4 : (d->layout == ISSL_LAYOUT_SIG64 ? 8 : 12);
+    out->hbm_bytes = d->hbmBytes;
+    out->list_entries = d->info.sliceCount * d->info.offtargetsCount;
+    out->info = d->info;
+    return ISSL_OK;
+}
+
+extern "C" int issl_device_read_sites(issl_device *d, const uint64_t *site_ids, uint64_t n, uint64_t *out)
+{
+    if (!d || (n && (!site_ids || !out))) return issl_set_error(ISSL_ERR_ARG, "issl_device_read_sites: null argument");
+    if (n == 0) return ISSL_OK;
+    CK(cudaSetDevice(d->dev));
+    DBuf in, o;
+    CKR(in.ensure(n * 8)); CKR(o.ensure(n * 8));
+    CK(cudaMemcpyAsync(in.p, site_ids, n * 8, cudaMemcpyHostToDevice, d->stream));
+    k_gather_sites<<<blocks_for(n, 256), 256, 0, d->stream>>>(d->iv.sig, d->iv.N, in.as<uint64_t>(), n, o.as<uint64_t>());
+    CK(cudaMemcpyAsync(out, o.p, n * 8, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    in.release(); o.release();
+    return ISSL_OK;
+}
+
+extern "C" int issl_device_write_issl(issl_device *d, const char *path)
+{
+    if (!d || !path) return issl_set_error(ISSL_ERR_ARG, "issl_device_write_issl: null argument");
+    CK(cudaSetDevice(d->dev));
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return issl_set_error(ISSL_ERR_IO, "cannot create %s", path);
+    auto put = [&](const void *p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, fp) == bytes; };
+    bool ok = true;
+    const uint64_t header[6] = {d->info.offtargetsCount, d->info.seqLength, d->info.seqCount,
+                                d->info.sliceWidth, d->info.sliceCount, d->info.scoresCount};
+    ok &= put(header, sizeof header);
+    for (size_t k = 0; k < d->hMitMasks.size() && ok; k++) { ok &= put(&d->hMitMasks[k], 8); ok &= put(&d->hMitScores[k], 8); }
+    constexpr size_t kStage = 64ull << 20;
+    uint8_t *stage = nullptr;
+    DBuf dbuf;
+    int rc = ISSL_OK;
+    if (cudaMallocHost(&stage, kStage) != cudaSuccess) { fclose(fp); return issl_set_error(ISSL_ERR_NOMEM, "pinned staging buffer"); }
+    const uint64_t N = d->info.offtargetsCount;
+    for (uint64_t o = 0; o < N * 8 && ok; o += kStage) {
+        const size_t n = (size_t)std::min<uint64_t>(kStage, N * 8 - o);
+        if (cudaMemcpyAsync(stage, d->sig.as<uint8_t>() + o, n, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
+            cudaStreamSynchronize(d->stream) != cudaSuccess) { rc = issl_set_error(ISSL_ERR_CUDA, "D2H of signatures failed"); ok = false; break; }
+        ok &= put(stage, n);
+    }
+    ok = ok && put(d->hListLen.data(), d->nLists * 8);
+    if (ok && (rc = dbuf.ensure(kStage)) == ISSL_OK) {
+        const uint64_t total = d->hFilePrefix[d->nLists], per = kStage / 8;
+        for (uint64_t q0 = 0; q0 < total && ok; q0 += per) {
+            const uint64_t n = std::min<uint64_t>(per, total - q0);
+            k_export_entries<<<blocks_for(n, 256), 256, 0, d->stream>>>(d->iv, d->filePrefix.as<uint64_t>(), d->nLists, q0, n,
+                                                                       dbuf.as<uint64_t>());
+            if (cudaMemcpyAsync(stage, dbuf.p, n * 8, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
+                cudaStreamSynchronize(d->stream) != cudaSuccess) { rc = issl_set_error(ISSL_ERR_CUDA, "D2H of list entries failed"); ok = false; break; }
+            ok &= put(stage, n * 8);
+        }
+    }
+    cudaFreeHost(stage);
+    dbuf.release();
+    if (fclose(fp) != 0) ok = false;
+    if (rc != ISSL_OK) return rc;
+    if (!ok) return issl_set_error(ISSL_ERR_IO, "short write to %s", path);
+    return ISSL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct HitSink {     // host-side collection for issl_score_hits
+    std::vector<uint64_t> guide;
+    std::vector<uint32_t> id, occ;
+    std::vector<int32_t> dist;
+};
+
+struct EventTimer {
+    issl_device *d;
+    size_t used = 0;
+    std::vector<std::pair<size_t, size_t>> scanPairs;
+    int get(cudaEvent_t *ev)
+    {
+        if (used == d->evPool.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            d->evPool.push_back(e);
+        }
+        *ev = d->evPool[used++];
+        return ISSL_OK;
+    }
+};
+
+}  // namespace
+
+// one batch of <= maxBatch guides, already resident at dGuides
+static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint64_t guideBase, int maxDist,
+                       double threshold, int method, double *dMit, double *dCfd, HitSink *sink, EventTimer &timer)
+{
+    const bool calcMit = method == ISSL_METHOD_MIT || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
+    const bool calcCfd = method == ISSL_METHOD_CFD || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
+    if (!calcMit && !calcCfd) return ISSL_OK;   // unknown method: nothing is scored, both columns print as -1
+
+    const double maximumSum = (10000.0 - threshold * 100) / threshold;   // ref :326
+    const bool checkExit = !(std::isnan(maximumSum) || (std::isinf(maximumSum) && maximumSum > 0));
+    const uint32_t S = d->iv.sliceCount;
+
+    CKR(d->totMit.ensure(n * 8ull)); CKR(d->totCfd.ensure(n * 8ull)); CKR(d->done.ensure(n));
+    CKR(d->counters.ensure(8 * 8));
+    CK(cudaMemsetAsync(d->totMit.p, 0, n * 8ull, st));
+    CK(cudaMemsetAsync(d->totCfd.p, 0, n * 8ull, st));
+    CK(cudaMemsetAsync(d->done.p, 0, n, st));
+    if (sink) { CKR(d->scoredEnd.ensure(n * 8ull)); CKR(d->segBegin.ensure(n * 8ull)); }
+    unsigned long long *dc = d->counters.as<unsigned long long>();
+    std::vector<uint64_t> hEnd, hBegin, hKeys;
+    std::vector<uint32_t> hId, hOcc;
+    std::vector<int32_t> hDist;
+
+    // without early exit all slices go in one wave; with it, one wave per slice so that guides
+    // which exited stop generating work (ref :501-502)
+    const uint32_t wave = checkExit ? 1 : S;
+    for (uint32_t s0 = 0; s0 < S; s0 += wave) {
+        const uint32_t ns = std::min(wave, S - s0);
+        const uint64_t pairs = (uint64_t)n * ns;
+        const uint8_t *doneMask = checkExit ? d->done.as<uint8_t>() : nullptr;
+
+        CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
+        k_wave_total<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
+        CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        d->stats.launches += 1;
+        const uint64_t candidates = d->hCounters[0];
+        d->stats.candidates += candidates;
+        if (candidates == 0) continue;
+
+        // chunk: aim at >= ~64k items for balance, never below one quantum
+        uint64_t chunk64 = (candidates / 65536 + kChunkQuantum - 1) / kChunkQuantum * kChunkQuantum;
+        chunk64 = std::max<uint64_t>(chunk64, 2 * kChunkQuantum);
+        chunk64 = std::min<uint64_t>(chunk64, 1ull << 30);
+        const uint32_t chunk = (uint32_t)chunk64;
+
+        CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
+        k_wave_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, chunk, d->pairCounts.as<uint32_t>());
+        CK(cudaMemsetAsync(d->pairCounts.as<uint32_t>() + pairs, 0, 4, st));
+        size_t tb = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
+        CKR(d->scanTemp.ensure(tb));
+        CK(cub::DeviceScan::ExclusiveSum(d->scanTemp.p, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
+        CK(cudaMemcpyAsync(d->hCounters + 2, d->pairOffsets.as<uint32_t>() + pairs, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t nItems = *reinterpret_cast<uint32_t *>(d->hCounters + 2);
+        CKR(d->items.ensure((size_t)nItems * sizeof(ScanItem)));
+        k_wave_fill<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, chunk,
+                                                           d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
+        d->stats.launches += 4;
+
+        // K1 (re-run with a larger survivor buffer if it overflowed)
+        uint64_t nHits = 0;
+        for (;;) {
+            if (d->hitCap == 0) {
+                d->hitCap = 1ull << 22;
+                CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+            }
+            CK(cudaMemsetAsync(dc + 1, 0, 8, st));
+            ScanArgs a;
+            a.iv = d->iv; a.items = d->items.as<ScanItem>(); a.guides = dGuides; a.hitKeys = d->keysA.as<uint64_t>();
+            a.hitCount = dc + 1; a.hitCap = d->hitCap; a.maxDist = maxDist; a.pbits = d->pbits;
+            cudaEvent_t e0, e1;
+            CKR(timer.get(&e0)); CKR(timer.get(&e1));
+            timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
+            CK(cudaEventRecord(e0, st));
+            if (d->layout == ISSL_LAYOUT_RES32) k_scan<kRes32><<<nItems, kScanThreads, 0, st>>>(a);
+            else if (d->layout == ISSL_LAYOUT_SIG64) k_scan<kSig64><<<nItems, kScanThreads, 0, st>>>(a);
+            else k_scan<kGather><<<nItems, kScanThreads, 0, st>>>(a);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1, st));
+            CK(cudaMemcpyAsync(d->hCounters + 1, dc + 1, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            d->stats.scan_launches += 1;
+            d->stats.launches += 1;
+            nHits = d->hCounters[1];
+            if (nHits <= d->hitCap) break;
+            d->hitCap = nHits + nHits / 4;
+            CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+        }
+        if (nHits == 0) continue;
+
+        // canonical order: sort keys (guide, position)
+        int gbits = 1;
+        while ((1ull << gbits) < n) gbits++;
+        cub::DoubleBuffer<uint64_t> db(d->keysA.as<uint64_t>(), d->keysB.as<uint64_t>());
+        tb = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, nHits, 0, d->pbits + gbits, st));
+        CKR(d->sortTemp.ensure(tb));
+        CK(cub::DeviceRadixSort::SortKeys(d->sortTemp.p, tb, db, nHits, 0, d->pbits + gbits, st));
+        const uint64_t *sorted = db.Current();
+        d->stats.launches += (uint64_t)((d->pbits + gbits + 7) / 8) * 2 + 1;   // histogram + onesweep passes (approximate)
+
+        CKR(d->contribMit.ensure(nHits * 8)); CKR(d->contribCfd.ensure(nHits * 8));
+        if (sink) { CKR(d->hitId.ensure(nHits * 4)); CKR(d->hitDist.ensure(nHits * 4)); CKR(d->hitOcc.ensure(nHits * 4)); }
+        ContribArgs c;
+        c.iv = d->iv; c.keys = sorted; c.nHits = nHits; c.guides = dGuides;
+        c.mitMasks = d->mitMasks.as<uint64_t>(); c.mitScores = d->mitScores.as<double>(); c.mitCount = d->mitCount;
+        c.pbits = d->pbits; c.calcMit = calcMit; c.calcCfd = calcCfd;
+        c.contribMit = d->contribMit.as<double>(); c.contribCfd = d->contribCfd.as<double>();
+        c.hitId = sink ? d->hitId.as<uint32_t>() : nullptr;
+        c.hitDist = sink ? d->hitDist.as<int32_t>() : nullptr;
+        c.hitOcc = sink ? d->hitOcc.as<uint32_t>() : nullptr;
+        k_contrib<<<blocks_for(nHits, 256), 256, 0, st>>>(c);
+
+        AccumArgs ac;
+        ac.keys = sorted; ac.nHits = nHits; ac.contribMit = c.contribMit; ac.contribCfd = c.contribCfd;
+        ac.nGuides = n; ac.pbits = d->pbits; ac.method = method; ac.checkExit = checkExit; ac.maximumSum = maximumSum;
+        ac.totMit = d->totMit.as<double>(); ac.totCfd = d->totCfd.as<double>(); ac.done = d->done.as<uint8_t>();
+        ac.scoredEnd = sink ? d->scoredEnd.as<uint64_t>() : nullptr;
+        ac.segBegin = sink ? d->segBegin.as<uint64_t>() : nullptr;
+        k_accumulate<<<blocks_for(n, 128), 128, 0, st>>>(ac);
+        CK(cudaGetLastError());
+        d->stats.launches += 2;
+
+        if (sink) {
+            hEnd.resize(n); hBegin.resize(n); hKeys.resize(nHits); hId.resize(nHits); hOcc.resize(nHits); hDist.resize(nHits);
+            CK(cudaMemcpyAsync(hEnd.data(), d->scoredEnd.p, n * 8ull, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hBegin.data(), d->segBegin.p, n * 8ull, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hId.data(), d->hitId.p, nHits * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hOcc.data(), d->hitOcc.p, nHits * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hDist.data(), d->hitDist.p, nHits * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (uint32_t g = 0; g < n; g++)
+                for (uint64_t j = hBegin[g]; j < hEnd[g]; j++) {
+                    sink->guide.push_back(guideBase + g);
+                    sink->id.push_back(hId[j]); sink->dist.push_back(hDist[j]); sink->occ.push_back(hOcc[j]);
+                }
+            d->stats.hits += 0;
+        }
+        d->stats.hits += nHits;
+    }
+
+    if (checkExit) {
+        CK(cudaMemsetAsync(dc + 3, 0, 8, st));
+        k_count_done<<<blocks_for(n, 256), 256, 0, st>>>(d->done.as<uint8_t>(), n, dc + 3);
+        CK(cudaMemcpyAsync(d->hCounters + 3, dc + 3, 8, cudaMemcpyDeviceToHost, st));
+        d->stats.launches += 1;
+    }
+    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(d->totMit.as<double>(), d->totCfd.as<double>(), n, calcMit ? dMit : nullptr,
+                                                  calcCfd ? dCfd : nullptr);
+    CK(cudaGetLastError());
+    d->stats.launches += 1;
+    CK(cudaStreamSynchronize(st));
+    if (checkExit) d->stats.early_exits += d->hCounters[3];
+    return ISSL_OK;
+}
+
+static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDevice, size_t n, int maxDist, double threshold,
+                        int method, double *mitOut, double *cfdOut, bool outOnDevice, cudaStream_t st, HitSink *sink)
+{
+    if (!d) return issl_set_error(ISSL_ERR_ARG, "issl_score: null device handle");
+    if (n && !guides) return issl_set_error(ISSL_ERR_ARG, "issl_score: null guide array");
+    CK(cudaSetDevice(d->dev));
+    if (!st) st = d->stream;
+    d->stats = issl_stats{};
+    d->stats.guides = n;
+    EventTimer timer{d};
+    cudaEvent_t t0, t1;
+    CKR(timer.get(&t0)); CKR(timer.get(&t1));
+    CK(cudaEventRecord(t0, st));
+
+    const bool calcMit = method == ISSL_METHOD_MIT || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
+    const bool calcCfd = method == ISSL_METHOD_CFD || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
+    if ((calcMit && !mitOut) || (calcCfd && !cfdOut))
+        return issl_set_error(ISSL_ERR_ARG, "issl_score: output array missing for a column the method computes");
+
+    for (size_t b0 = 0; b0 < n; b0 += d->maxBatch) {
+        const uint32_t nb = (uint32_t)std::min<size_t>(d->maxBatch, n - b0);
+        const uint64_t *dG = guides + b0;
+        if (!guidesOnDevice) {
+            CKR(d->guides.ensure(nb * 8ull));
+            CK(cudaMemcpyAsync(d->guides.p, guides + b0, nb * 8ull, cudaMemcpyHostToDevice, st));
+            dG = d->guides.as<uint64_t>();
+        }
+        double *dM = mitOut ? mitOut + b0 : nullptr, *dC = cfdOut ? cfdOut + b0 : nullptr;
+        if (!outOnDevice) {
+            CKR(d->outMit.ensure(nb * 8ull)); CKR(d->outCfd.ensure(nb * 8ull));
+            dM = d->outMit.as<double>(); dC = d->outCfd.as<double>();
+        }
+        CKR(score_batch(d, st, dG, nb, b0, maxDist, threshold, method, dM, dC, sink, timer));
+        if (!outOnDevice) {
+            if (calcMit) CK(cudaMemcpyAsync(mitOut + b0, dM, nb * 8ull, cudaMemcpyDeviceToHost, st));
+            if (calcCfd) CK(cudaMemcpyAsync(cfdOut + b0, dC, nb * 8ull, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    CK(cudaEventRecord(t1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    d->stats.total_ms = ms;
+    for (auto &pr : timer.scanPairs) {
+        CK(cudaEventElapsedTime(&ms, d->evPool[pr.first], d->evPool[pr.second]));
+        d->stats.scan_ms += ms;
+    }
+    return ISSL_OK;
+}
+
+extern "C" int issl_score(issl_device *d, const uint64_t *guides, size_t n, int maxDist, double threshold, int method,
+                          double *mit_out, double *cfd_out)
+{
+    return score_common(d, guides, false, n, maxDist, threshold, method, mit_out, cfd_out, false, nullptr, nullptr);
+}
+
+extern "C" int issl_score_device(issl_device *d, const uint64_t *d_guides, size_t n, int maxDist, double threshold,
+                                 int method, double *d_mit_out, double *d_cfd_out, void *stream)
+{
+    return score_common(d, d_guides, true, n, maxDist, threshold, method, d_mit_out, d_cfd_out, true,
+                        static_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int issl_score_hits(issl_device *d, const uint64_t *guides, size_t n, int maxDist, double threshold, int method,
+                               double *mit_out, double *cfd_out, uint64_t *hit_guide, uint32_t *hit_id, int32_t *hit_dist,
+                               uint32_t *hit_occ, size_t cap, size_t *count)
+{
+    HitSink sink;
+    CKR(score_common(d, guides, false, n, maxDist, threshold, method, mit_out, cfd_out, false, nullptr, &sink));
+    // waves append per slice; the reference's order is per guide, then slice, then list position
+    std::vector<size_t> order(sink.guide.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return sink.guide[a] < sink.guide[b]; });
+    if (count) *count = order.size();
+    for (size_t i = 0; i < order.size() && i < cap; i++) {
+        const size_t k = order[i];
+        if (hit_guide) hit_guide[i] = sink.guide[k];
+        if (hit_id) hit_id[i] = sink.id[k];
+        if (hit_dist) hit_dist[i] = sink.dist[k];
+        if (hit_occ) hit_occ[i] = sink.occ[k];
+    }
+    return ISSL_OK;
+}
+
+extern "C" int issl_last_stats(const issl_device *d, issl_stats *out)
+{
+    if (!d || !out) return issl_set_error(ISSL_ERR_ARG, "issl_last_stats: null argument");
+    *out = d->stats;
+    return ISSL_OK;
+}

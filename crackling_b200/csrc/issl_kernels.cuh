@@ -1,0 +1,633 @@
+// issl_kernels.cuh -- hand-written sm_100a kernels of libissl_cuda.
+//
+// "ref:" = /root/reference/src/ISSL/.  See DESIGN.md for the data layout and the roofline of
+// each kernel.  Everything here is integer/bitwise work except the survivor scoring
+// (k_contrib / k_accumulate), which is fp64 with explicitly unfused multiply/add so the sums
+// come out bit-identical to the reference's x86-64 build (no FMA, Makefile:5 of the reference).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "cfd_tables.h"
+
+namespace issl {
+
+constexpr int kScanThreads = 256;      // threads per scan CTA
+constexpr int kScanUnroll = 4;         // 16-byte loads in flight per thread
+constexpr uint32_t kListAlign = 32;    // list starts are padded to 32 entries (128 B of residuals)
+constexpr uint32_t kChunkQuantum = 4096;   // scan-item sizes are multiples of this many entries
+
+enum Layout : int { kRes32 = 1, kSig64 = 2, kGather = 3 };
+
+// The index as it lies in HBM.  Position space: p in [0, P) enumerates the entries of all slice
+// lists, slice-major then list value then ascending site id -- the order in which the reference
+// walks them for one guide (ref isslScoreOfftargets.cpp:330-344) -- with every list start rounded
+// up to kListAlign entries.
+struct IndexView {
+    const uint64_t *sig;        // [N]  packed site signatures (ref offtargets[], :200-204)
+    const uint32_t *occ;        // [N]  occurrences per site (ref: high half of every list entry, :348)
+    const uint32_t *ids;        // [P]  site id per list position (ref: low half of the entry, :347)
+    const uint32_t *res32;      // [P]  kRes32: signature with the slice's known bits removed
+    const uint64_t *sig64;      // [P]  kSig64: signature inline
+    const uint64_t *listStart;  // [nLists] first position of list (slice * sliceLimit + value)
+    const uint64_t *listLen;    // [nLists] ref allSlicelistSizes, :221-226
+    uint64_t N, P;
+    uint32_t seqLength, sliceWidth, sliceCount, sliceLimit;
+    uint32_t sliceMask;         // 2^sliceWidth - 1
+    uint32_t knownBits;         // min(sliceWidth, 8): bits every member of a list shares with the list value
+    int layout;
+};
+
+// One unit of scan work: `count` consecutive list positions starting at p0, tested against guide g.
+struct ScanItem {
+    uint64_t p0Slice;   // bits 0..55 position, bits 56..63 slice index
+    uint32_t count;
+    uint32_t guide;     // index into the batch's guide array
+};
+
+__constant__ double c_cfdPos[320];
+__constant__ double c_cfdPam[16];
+
+// ------------------------------------------------------------------------------------------------
+// bit helpers
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t remove_bits(uint64_t x, uint32_t off, uint32_t nbits)
+{
+    const uint64_t low = x & ((1ull << off) - 1ull);
+    const uint64_t high = (off + nbits >= 64) ? 0ull : (x >> (off + nbits));
+    return low | (high << off);
+}
+
+__host__ __device__ __forceinline__ uint64_t insert_bits(uint64_t x, uint32_t off, uint32_t nbits, uint64_t v)
+{
+    const uint64_t low = x & ((1ull << off) - 1ull);
+    const uint64_t high = x >> off;
+    return low | (v << off) | ((off + nbits >= 64) ? 0ull : (high << (off + nbits)));
+}
+
+// per-base mismatch flags, ref :376-379: ((x & 0xAAAA..) >> 1) | (x & 0x5555..)
+__device__ __forceinline__ uint64_t mismatch_mask64(uint64_t x)
+{
+    return (x | (x >> 1)) & 0x5555555555555555ull;
+}
+__device__ __forceinline__ int distance32(uint32_t x)
+{
+    return __popc((x | (x >> 1)) & 0x55555555u);
+}
+__device__ __forceinline__ int distance64(uint64_t x)
+{
+    return __popcll(mismatch_mask64(x));
+}
+
+// Does list (slice k, value of the guide at slice k) contain this site?  The builder files a site
+// under `uint8_t sliceVal` (ref isslCreateIndex.cpp:228), i.e. under the LOW 8 BITS of its slice
+// value; the scorer looks a guide up under its full slice value (ref isslScoreOfftargets.cpp:336-341).
+__device__ __forceinline__ bool in_list(uint64_t siteSig, uint64_t guideSig, uint32_t k, uint32_t w, uint32_t smask)
+{
+    const uint32_t sv = (uint32_t)(siteSig >> (w * k)) & smask & 0xFFu;
+    const uint32_t gv = (uint32_t)(guideSig >> (w * k)) & smask;
+    return sv == gv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: candidate scan.  ref isslScoreOfftargets.cpp:344-390 (the inner hot loop) for one
+// (guide, slice, chunk of the selected list).
+//
+// Streams the chunk with coalesced 16-byte loads (4 residuals / 2 signatures / 4 ids per load,
+// kScanUnroll loads in flight per thread), XOR + fold + popcount, keeps dist <= maxDist.
+// De-duplication is stateless: a site reached through several slices is counted only in the
+// lowest slice whose looked-up list contains it (in_list), which is where the reference's toggle
+// bitset (:385-390, :463) lets it through, because every list holds each site at most once and
+// the distance does not depend on the slice.  Survivors (~4e-5 of candidates on a uniform
+// genome) are appended to a key buffer: key = guide << pbits | position.  Sorting the keys
+// restores the reference's visiting order for every guide.
+// ------------------------------------------------------------------------------------------------
+struct ScanArgs {
+    IndexView iv;
+    const ScanItem *items;
+    const uint64_t *guides;
+    uint64_t *hitKeys;
+    unsigned long long *hitCount;
+    uint64_t hitCap;
+    int maxDist;
+    int pbits;
+};
+
+__device__ __forceinline__ void emit_hit(const ScanArgs &a, uint64_t guideSig, uint64_t siteSig, uint32_t slice,
+                                         uint32_t guide, uint64_t pos)
+{
+    for (uint32_t k = 0; k < slice; k++)
+        if (in_list(siteSig, guideSig, k, a.iv.sliceWidth, a.iv.sliceMask)) return;
+    const unsigned long long slot = atomicAdd(a.hitCount, 1ull);
+    if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << a.pbits) | pos;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kScanThreads) k_scan(const ScanArgs a)
+{
+    const ScanItem it = a.items[blockIdx.x];
+    const uint32_t slice = (uint32_t)(it.p0Slice >> 56);
+    const uint64_t p0 = it.p0Slice & ((1ull << 56) - 1ull);
+    const uint32_t n = it.count;
+    const uint64_t g = a.guides[it.guide];
+    const int maxDist = a.maxDist;
+    const uint32_t tid = threadIdx.x;
+
+    if (LAYOUT == kRes32) {
+        const uint32_t off = a.iv.sliceWidth * slice, kb = a.iv.knownBits;
+        const uint32_t gres = (uint32_t)remove_bits(g, off, kb);
+        const uint64_t known = (g >> off) & ((1ull << kb) - 1ull);
+        const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.res32 + p0);
+        const uint32_t nvec = n >> 2;
+        auto test = [&](uint32_t r, uint64_t pos) {
+            if (distance32(r ^ gres) <= maxDist)
+                emit_hit(a, g, insert_bits(r, off, kb, known), slice, it.guide, pos);
+        };
+        uint32_t i = tid;
+        for (; i + (kScanUnroll - 1) * kScanThreads < nvec; i += kScanUnroll * kScanThreads) {
+            uint4 r[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) r[u] = __ldcs(v4 + i + u * kScanThreads);
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                const uint64_t pos = p0 + 4ull * (i + u * kScanThreads);
+                test(r[u].x, pos); test(r[u].y, pos + 1); test(r[u].z, pos + 2); test(r[u].w, pos + 3);
+            }
+        }
+        for (; i < nvec; i += kScanThreads) {
+            const uint4 r = __ldcs(v4 + i);
+            const uint64_t pos = p0 + 4ull * i;
+            test(r.x, pos); test(r.y, pos + 1); test(r.z, pos + 2); test(r.w, pos + 3);
+        }
+        if (tid < (n & 3u)) {
+            const uint64_t pos = p0 + 4ull * nvec + tid;
+            test(a.iv.res32[pos], pos);
+        }
+    } else if (LAYOUT == kSig64) {
+        const ulonglong2 *__restrict__ v2 = reinterpret_cast<const ulonglong2 *>(a.iv.sig64 + p0);
+        const uint32_t nvec = n >> 1;
+        auto test = [&](uint64_t s, uint64_t pos) {
+            if (distance64(s ^ g) <= maxDist) emit_hit(a, g, s, slice, it.guide, pos);
+        };
+        uint32_t i = tid;
+        for (; i + (kScanUnroll - 1) * kScanThreads < nvec; i += kScanUnroll * kScanThreads) {
+            ulonglong2 r[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) r[u] = __ldcs(v2 + i + u * kScanThreads);
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                const uint64_t pos = p0 + 2ull * (i + u * kScanThreads);
+                test(r[u].x, pos); test(r[u].y, pos + 1);
+            }
+        }
+        for (; i < nvec; i += kScanThreads) {
+            const ulonglong2 r = __ldcs(v2 + i);
+            const uint64_t pos = p0 + 2ull * i;
+            test(r.x, pos); test(r.y, pos + 1);
+        }
+        if (tid < (n & 1u)) {
+            const uint64_t pos = p0 + 2ull * nvec + tid;
+            test(a.iv.sig64[pos], pos);
+        }
+    } else {   // kGather: ids streamed, signatures gathered (the reference's own access pattern, :346-376)
+        const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.ids + p0);
+        const uint64_t *__restrict__ sig = a.iv.sig;
+        const uint32_t nvec = n >> 2;
+        auto test = [&](uint64_t s, uint64_t pos) {
+            if (distance64(s ^ g) <= maxDist) emit_hit(a, g, s, slice, it.guide, pos);
+        };
+        uint32_t i = tid;
+        for (; i + (kScanUnroll - 1) * kScanThreads < nvec; i += kScanUnroll * kScanThreads) {
+            uint4 r[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) r[u] = __ldcs(v4 + i + u * kScanThreads);
+            uint64_t s[kScanUnroll][4];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                s[u][0] = __ldg(sig + r[u].x); s[u][1] = __ldg(sig + r[u].y);
+                s[u][2] = __ldg(sig + r[u].z); s[u][3] = __ldg(sig + r[u].w);
+            }
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                const uint64_t pos = p0 + 4ull * (i + u * kScanThreads);
+#pragma unroll
+                for (int c = 0; c < 4; c++) test(s[u][c], pos + c);
+            }
+        }
+        for (; i < nvec; i += kScanThreads) {
+            const uint4 r = __ldcs(v4 + i);
+            const uint64_t pos = p0 + 4ull * i;
+            test(__ldg(sig + r.x), pos); test(__ldg(sig + r.y), pos + 1);
+            test(__ldg(sig + r.z), pos + 2); test(__ldg(sig + r.w), pos + 3);
+        }
+        if (tid < (n & 3u)) {
+            const uint64_t pos = p0 + 4ull * nvec + tid;
+            test(__ldg(sig + a.iv.ids[pos]), pos);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scan-item construction (ref :330-341: slice value -> list -> length).
+// One "pair" = (guide, slice) for slices in [slice0, slice0 + nSlices).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pair_list(const IndexView &iv, uint64_t g, uint32_t slice)
+{
+    const uint32_t v = (uint32_t)(g >> (iv.sliceWidth * slice)) & iv.sliceMask;
+    return (uint64_t)slice * iv.sliceLimit + v;
+}
+
+// pass 1: total candidates of the wave (decides the chunk size; also the reported unit count)
+__global__ void k_wave_total(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
+                             uint32_t slice0, uint32_t nSlices, unsigned long long *total)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long len = 0;
+    if (t < (uint64_t)nGuides * nSlices) {
+        const uint32_t gi = (uint32_t)(t / nSlices), s = slice0 + (uint32_t)(t % nSlices);
+        if (!done || !done[gi]) len = iv.listLen[pair_list(iv, guides[gi], s)];
+    }
+    // warp-reduce before the atomic
+    for (int o = 16; o > 0; o >>= 1) len += __shfl_down_sync(0xffffffffu, len, o);
+    if ((threadIdx.x & 31) == 0 && len) atomicAdd(total, len);
+}
+
+// pass 2: chunks per pair
+__global__ void k_wave_count(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
+                             uint32_t slice0, uint32_t nSlices, uint32_t chunk, uint32_t *counts)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)nGuides * nSlices) return;
+    const uint32_t gi = (uint32_t)(t / nSlices), s = slice0 + (uint32_t)(t % nSlices);
+    uint32_t c = 0;
+    if (!done || !done[gi]) {
+        const uint64_t len = iv.listLen[pair_list(iv, guides[gi], s)];
+        c = (uint32_t)((len + chunk - 1) / chunk);
+    }
+    counts[t] = c;
+}
+
+// pass 3: write the items of every pair at its scanned offset
+__global__ void k_wave_fill(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
+                            uint32_t slice0, uint32_t nSlices, uint32_t chunk, const uint32_t *offsets,
+                            ScanItem *items)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)nGuides * nSlices) return;
+    const uint32_t gi = (uint32_t)(t / nSlices), s = slice0 + (uint32_t)(t % nSlices);
+    if (done && done[gi]) return;
+    const uint64_t list = pair_list(iv, guides[gi], s);
+    const uint64_t len = iv.listLen[list], start = iv.listStart[list];
+    uint32_t o = offsets[t];
+    for (uint64_t c0 = 0; c0 < len; c0 += chunk, o++) {
+        ScanItem it;
+        it.p0Slice = (start + c0) | ((uint64_t)s << 56);
+        it.count = (uint32_t)((len - c0 < chunk) ? (len - c0) : chunk);
+        it.guide = gi;
+        items[o] = it;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: score every survivor.  ref :392-461.
+// MIT: table[mismatch mask] * occ when dist > 0 (missing mask -> 0.0, the inserting operator[] at :394).
+// CFD: 1 when dist == 0, else PAM(GG) * prod over mismatching positions < 20, ascending (:411-458); * occ.
+// ------------------------------------------------------------------------------------------------
+struct ContribArgs {
+    IndexView iv;
+    const uint64_t *keys;     // sorted
+    uint64_t nHits;
+    const uint64_t *guides;
+    const uint64_t *mitMasks; // sorted ascending
+    const double *mitScores;
+    uint32_t mitCount;
+    int pbits;
+    int calcMit, calcCfd;
+    double *contribMit;       // [nHits]
+    double *contribCfd;       // [nHits]
+    uint32_t *hitId;          // optional dump
+    int32_t *hitDist;
+    uint32_t *hitOcc;
+};
+
+__global__ void __launch_bounds__(256) k_contrib(const ContribArgs a)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.nHits) return;
+    const uint64_t key = a.keys[j];
+    const uint64_t pos = key & ((1ull << a.pbits) - 1ull);
+    const uint64_t g = a.guides[key >> a.pbits];
+    const uint32_t id = a.iv.ids[pos];
+    const uint64_t site = a.iv.sig[id];
+    const uint32_t occ = a.iv.occ[id];
+    const uint64_t mm = mismatch_mask64(g ^ site);
+    const int dist = __popcll(mm);
+    const double docc = (double)occ;
+
+    double cm = 0.0, cc = 0.0;
+    if (a.calcMit && dist > 0) {
+        uint32_t lo = 0, hi = a.mitCount;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.mitMasks[mid] < mm) lo = mid + 1; else hi = mid;
+        }
+        const double s = (lo < a.mitCount && a.mitMasks[lo] == mm) ? a.mitScores[lo] : 0.0;
+        cm = __dmul_rn(s, docc);
+    }
+    if (a.calcCfd) {
+        double cfd = 1.0;
+        if (dist > 0) {
+            cfd = c_cfdPam[10];   // 0b1010 = GG, ref :411
+            uint32_t m20 = 0;     // mismatch flags of positions 0..19, one bit each (ref loop :413)
+            for (int p = 0; p < 20; p++) m20 |= (uint32_t)((mm >> (2 * p)) & 1ull) << p;
+            while (m20) {
+                const int p = __ffs(m20) - 1;
+                m20 &= m20 - 1;
+                const uint32_t gb = (uint32_t)(g >> (2 * p)) & 3u, ob = (uint32_t)(site >> (2 * p)) & 3u;
+                cfd = __dmul_rn(cfd, c_cfdPos[(p << 4) | (gb << 2) | (ob ^ 3u)]);
+            }
+        }
+        cc = __dmul_rn(cfd, docc);
+    }
+    a.contribMit[j] = cm;
+    a.contribCfd[j] = cc;
+    if (a.hitId) { a.hitId[j] = id; a.hitDist[j] = dist; a.hitOcc[j] = occ; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: per-guide ordered accumulation with the reference's early exit.  ref :322-327, :394, :460,
+// :466-502.  One thread per guide walks its survivors in (slice, list position) order -- the
+// sorted key order -- adding one rounded product at a time, exactly as the CPU does, and stops at
+// the first survivor after which the method's predicate exceeds maximum_sum.
+// ------------------------------------------------------------------------------------------------
+struct AccumArgs {
+    const uint64_t *keys;
+    uint64_t nHits;
+    const double *contribMit, *contribCfd;
+    uint32_t nGuides;
+    int pbits;
+    int method;
+    int checkExit;          // 0: maximum_sum is +inf/NaN or the method is unknown
+    double maximumSum;
+    double *totMit, *totCfd;   // [nGuides] running sums, carried across slice waves
+    uint8_t *done;             // [nGuides] set when the guide exited early
+    uint64_t *scoredEnd;       // optional [nGuides]: index one past the guide's last scored survivor
+    uint64_t *segBegin;        // optional [nGuides]: index of the guide's first survivor of this wave
+};
+
+__device__ __forceinline__ uint64_t lower_bound_key(const uint64_t *keys, uint64_t n, uint64_t key)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) k_accumulate(const AccumArgs a)
+{
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= a.nGuides) return;
+    const uint64_t lo = lower_bound_key(a.keys, a.nHits, (uint64_t)gi << a.pbits);
+    if (a.segBegin) a.segBegin[gi] = lo;
+    if (a.done[gi]) { if (a.scoredEnd) a.scoredEnd[gi] = lo; return; }
+    const uint64_t hi = lower_bound_key(a.keys, a.nHits, ((uint64_t)gi + 1) << a.pbits);
+    double mit = a.totMit[gi], cfd = a.totCfd[gi];
+    const double mx = a.maximumSum;
+    uint64_t j = lo;
+    bool stop = false;
+    for (; j < hi && !stop; j++) {
+        mit = __dadd_rn(mit, a.contribMit[j]);
+        cfd = __dadd_rn(cfd, a.contribCfd[j]);
+        if (a.checkExit) {
+            switch (a.method) {
+            case ISSL_METHOD_AND: stop = (mit > mx && cfd > mx); break;
+            case ISSL_METHOD_OR:  stop = (mit > mx || cfd > mx); break;
+            case ISSL_METHOD_AVG: stop = (__ddiv_rn(__dadd_rn(mit, cfd), 2.0) > mx); break;
+            case ISSL_METHOD_MIT: stop = (mit > mx); break;
+            case ISSL_METHOD_CFD: stop = (cfd > mx); break;
+            default: break;
+            }
+        }
+    }
+    a.totMit[gi] = mit;
+    a.totCfd[gi] = cfd;
+    if (stop) a.done[gi] = 1;
+    if (a.scoredEnd) a.scoredEnd[gi] = j;
+}
+
+// ref :505-506
+__global__ void k_finalize(const double *totMit, const double *totCfd, uint32_t n, double *mitOut, double *cfdOut)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mitOut) mitOut[i] = __ddiv_rn(10000.0, __dadd_rn(100.0, totMit[i]));
+    if (cfdOut) cfdOut[i] = __ddiv_rn(10000.0, __dadd_rn(100.0, totCfd[i]));
+}
+
+__global__ void k_count_done(const uint8_t *done, uint32_t n, unsigned long long *count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = __ballot_sync(0xffffffffu, i < n && done[i]);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one-time re-layout of the file's list section into position space, with validation of
+// the builder's invariants (ref isslCreateIndex.cpp:216-234).
+// entries[] holds file entries [q0, q0 + n) of ONE slice, preceded by entry q0-1 when hasPrev.
+// errors[0] counts violations (id range, membership, ascending ids, occurrence mismatch).
+// ------------------------------------------------------------------------------------------------
+struct RelayoutArgs {
+    IndexView iv;             // ids/res32/sig64/occ are written through const_cast'ed pointers
+    const uint64_t *entries;
+    const uint64_t *filePrefix;   // [nLists + 1] exclusive prefix of listLen in file order
+    uint64_t q0, n;
+    uint32_t slice;
+    int hasPrev;
+    unsigned long long *errors;
+};
+
+__global__ void __launch_bounds__(256) k_relayout(const RelayoutArgs a)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const uint64_t q = a.q0 + t;
+    const uint64_t e = a.entries[t + (a.hasPrev ? 1 : 0)];
+    const uint32_t id = (uint32_t)(e & 0xFFFFFFFFull), occ = (uint32_t)(e >> 32);
+    // list of this file position: last list whose prefix <= q
+    uint64_t lo = (uint64_t)a.slice * a.iv.sliceLimit, hi = lo + a.iv.sliceLimit;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (a.filePrefix[mid] <= q) lo = mid; else hi = mid;
+    }
+    const uint64_t list = lo, j = q - a.filePrefix[list];
+    const uint32_t value = (uint32_t)(list - (uint64_t)a.slice * a.iv.sliceLimit);
+    bool bad = id >= a.iv.N;
+    if (!bad) {
+        const uint64_t s = a.iv.sig[id];
+        const uint32_t off = a.iv.sliceWidth * a.slice;
+        const uint32_t sv = (uint32_t)(s >> off) & a.iv.sliceMask & 0xFFu;
+        bad |= (sv != value);
+        if (j > 0) {
+            const uint64_t prev = a.entries[t + (a.hasPrev ? 1 : 0) - 1];
+            bad |= ((uint32_t)(prev & 0xFFFFFFFFull) >= id);
+        }
+        uint32_t *occOut = const_cast<uint32_t *>(a.iv.occ);
+        if (a.slice == 0) occOut[id] = occ; else bad |= (occOut[id] != occ);
+        const uint64_t p = a.iv.listStart[list] + j;
+        const_cast<uint32_t *>(a.iv.ids)[p] = id;
+        if (a.iv.layout == kRes32)
+            const_cast<uint32_t *>(a.iv.res32)[p] = (uint32_t)remove_bits(s, off, a.iv.knownBits);
+        else if (a.iv.layout == kSig64)
+            const_cast<uint64_t *>(a.iv.sig64)[p] = s;
+    }
+    if (bad) atomicAdd(a.errors, 1ull);
+}
+
+// Inverse of K3: file-order entries (occ << 32 | id) of positions [q0, q0 + n), for
+// issl_device_write_issl (ref isslCreateIndex.cpp:285-289).
+__global__ void k_export_entries(IndexView iv, const uint64_t *filePrefix, uint64_t nLists, uint64_t q0, uint64_t n,
+                                 uint64_t *out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t q = q0 + t;
+    uint64_t lo = 0, hi = nLists;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (filePrefix[mid] <= q) lo = mid; else hi = mid;
+    }
+    const uint64_t p = iv.listStart[lo] + (q - filePrefix[lo]);
+    const uint32_t id = iv.ids[p];
+    out[t] = ((uint64_t)iv.occ[id] << 32) | id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Index construction on the device (synthetic indexes; ref isslCreateIndex.cpp:184-234).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
+{   // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t rng3(uint64_t seed, uint64_t a, uint64_t b)
+{
+    return mix64(mix64(mix64(seed) ^ a) ^ (b * 0xD6E8FEB86659FD93ull));
+}
+
+// Sort key of a site: base 0 most significant, so that ascending keys = the lexicographic order of
+// the text file the reference builder expects (extractOfftargets.py sorts strings).
+__host__ __device__ __forceinline__ uint64_t sig_to_sortkey(uint64_t sig, uint32_t L)
+{
+    uint64_t k = 0;
+    for (uint32_t j = 0; j < L; j++) k |= ((sig >> (2 * j)) & 3ull) << (2 * (L - 1 - j));
+    return k;
+}
+
+// uniform sites: i.i.d. bases, first base in {A,C,G}; family members: a per-family random root,
+// each base substituted with the family's rate.
+__global__ void k_synth_sites(uint64_t seed, uint64_t nUniform, uint32_t families, uint32_t familySize,
+                              double maxSubRate, uint32_t L, uint64_t *keys)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = nUniform + (uint64_t)families * familySize;
+    if (t >= total) return;
+    const uint64_t lmask = (L >= 32) ? ~0ull : ((1ull << (2 * L)) - 1ull);
+    uint64_t sig;
+    if (t < nUniform) {
+        const uint64_t r = rng3(seed, 1, t);
+        sig = r & lmask & ~3ull;
+        sig |= (rng3(seed, 2, t) % 3ull);
+    } else {
+        const uint64_t m = t - nUniform, f = m / familySize;
+        const uint64_t root = (rng3(seed, 3, f) & lmask & ~3ull) | (rng3(seed, 4, f) % 3ull);
+        const double rate = maxSubRate * (double)(rng3(seed, 5, f) >> 11) * (1.0 / 9007199254740992.0);
+        sig = root;
+        for (uint32_t j = 0; j < L; j++) {
+            const uint64_t r = rng3(seed, 6 + j, m);
+            const double u = (double)(r >> 11) * (1.0 / 9007199254740992.0);
+            if (u < rate) {
+                const uint64_t b = ((sig >> (2 * j)) & 3ull), nb = (b + 1 + (r % 3ull)) & 3ull;
+                sig = (sig & ~(3ull << (2 * j))) | (nb << (2 * j));
+            }
+        }
+    }
+    keys[t] = sig_to_sortkey(sig, L);
+}
+
+// run heads of the sorted key array
+__global__ void k_run_flags(const uint64_t *keys, uint64_t n, uint32_t *flags)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    flags[t] = (t == 0 || keys[t] != keys[t - 1]) ? 1u : 0u;
+}
+
+// scatter run heads: runStart[rank] = t, sig[rank] = signature (rank = inclusive scan of flags - 1)
+__global__ void k_run_scatter(const uint64_t *keys, const uint32_t *flags, const uint64_t *rankIncl, uint64_t n,
+                              uint32_t L, uint64_t *sig, uint64_t *runStart)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n || !flags[t]) return;
+    const uint64_t r = rankIncl[t] - 1;
+    runStart[r] = t;
+    sig[r] = sig_to_sortkey(keys[t], L);   // the key transform is an involution (base order reversal)
+}
+
+__global__ void k_run_lengths(const uint64_t *runStart, uint64_t nRuns, uint64_t n, uint32_t *occ)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRuns) return;
+    const uint64_t end = (r + 1 < nRuns) ? runStart[r + 1] : n;
+    occ[r] = (uint32_t)(end - runStart[r]);
+}
+
+// per-slice list value of every site: (sig >> w*slice) & mask, truncated to 8 bits (ref :228)
+__global__ void k_slice_values(const uint64_t *sig, uint64_t n, uint32_t w, uint32_t smask, uint32_t slice,
+                               uint8_t *values, uint32_t *ids, unsigned long long *hist)
+{
+    __shared__ unsigned int h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const uint8_t v = (uint8_t)((uint32_t)(sig[t] >> (w * slice)) & smask);
+        values[t] = v;
+        ids[t] = (uint32_t)t;
+        atomicAdd(&h[v], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
+}
+
+// place the stably sorted ids of one slice into position space
+__global__ void k_place_slice(IndexView iv, const uint8_t *sortedValues, const uint32_t *sortedIds, uint64_t n,
+                              uint32_t slice, const uint64_t *valueStart /* [256] rank of first id per value */)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t v = sortedValues[t], id = sortedIds[t];
+    const uint64_t list = (uint64_t)slice * iv.sliceLimit + v;
+    const uint64_t p = iv.listStart[list] + (t - valueStart[v]);
+    const uint64_t s = iv.sig[id];
+    const_cast<uint32_t *>(iv.ids)[p] = id;
+    if (iv.layout == kRes32)
+        const_cast<uint32_t *>(iv.res32)[p] = (uint32_t)remove_bits(s, iv.sliceWidth * slice, iv.knownBits);
+    else if (iv.layout == kSig64)
+        const_cast<uint64_t *>(iv.sig64)[p] = s;
+}
+
+__global__ void k_gather_sites(const uint64_t *sig, uint64_t N, const uint64_t *siteIds, uint64_t n, uint64_t *out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    out[t] = sig[siteIds[t] % N];
+}
+
+}  // namespace issl

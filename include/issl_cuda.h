@@ -1,0 +1,200 @@
+/*
+ * issl_cuda.h -- C ABI of libissl_cuda, the B200 (sm_100a) implementation of Crackling's
+ * ISSL off-target scorer.
+ *
+ * The reference has no plugin/operator API for this path: the seam is the process boundary of
+ * the `isslScoreOfftargets` executable (argv in, stdout out), whose main() is
+ * /root/reference/src/ISSL/isslScoreOfftargets.cpp:91-530.  This header splits that main()
+ * into the phases a host program (ours: crackling_b200/csrc/isslScoreOfftargets.cpp; a
+ * maintainer's: see INTEGRATION.md) calls in order.  Each entry point cites the reference
+ * region it replaces; "ref:" paths are relative to /root/reference/src/ISSL/.
+ *
+ * Conventions: plain C types only; every function returns ISSL_OK (0) or an issl_status
+ * error code and records a message retrievable with issl_last_error() (thread-local);
+ * no exceptions cross the boundary; there is NO CPU fallback -- without an sm_100 device
+ * issl_device_create* fails with ISSL_ERR_NO_DEVICE.
+ *
+ * Threading: an issl_index is immutable after open and may be shared.  An issl_device may be
+ * used by one host thread at a time; different issl_device handles (one per GPU) may be driven
+ * concurrently from different host threads (guides partitioned, index replicated, no collective:
+ * ref guides are independent, isslScoreOfftargets.cpp:316-317).
+ */
+#ifndef ISSL_CUDA_H
+#define ISSL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISSL_CUDA_ABI_VERSION 1
+
+typedef enum issl_status {
+    ISSL_OK = 0,
+    ISSL_ERR_IO = 1,          /* file cannot be opened / read                              */
+    ISSL_ERR_FORMAT = 2,      /* not a valid .issl image (ref error exits :164-167, :201-204, :223-226, :237-240) */
+    ISSL_ERR_CUDA = 3,        /* a CUDA call failed                                        */
+    ISSL_ERR_NO_DEVICE = 4,   /* no usable sm_100 device -- the product never falls back to the CPU */
+    ISSL_ERR_ARG = 5,         /* bad argument                                              */
+    ISSL_ERR_UNSUPPORTED = 6, /* a valid file this implementation refuses (e.g. lists that violate
+                                 the invariants of isslCreateIndex.cpp:216-234)            */
+    ISSL_ERR_NOMEM = 7
+} issl_status;
+
+/* ref enum ScoreMethod, isslScoreOfftargets.cpp:44 and :121-143 */
+typedef enum issl_method {
+    ISSL_METHOD_UNKNOWN = 0,  /* any other string: both columns print as -1, nothing is scored */
+    ISSL_METHOD_MIT = 1,
+    ISSL_METHOD_CFD = 2,
+    ISSL_METHOD_AND = 3,
+    ISSL_METHOD_OR = 4,
+    ISSL_METHOD_AVG = 5
+} issl_method;
+
+/* The six header words of an .issl file, ref isslScoreOfftargets.cpp:162-174
+ * (written by isslCreateIndex.cpp:257-267). */
+typedef struct issl_info {
+    uint64_t offtargetsCount; /* distinct off-target sites                                 */
+    uint64_t seqLength;       /* bases per site (20)                                       */
+    uint64_t seqCount;        /* sites before duplicate collapsing                         */
+    uint64_t sliceWidth;      /* bits per slice                                            */
+    uint64_t sliceCount;      /* slices per site = 2*seqLength / sliceWidth                */
+    uint64_t scoresCount;     /* header count of precomputed local MIT scores              */
+} issl_info;
+
+/* How the index lies in HBM (DESIGN.md "Data layout"). */
+typedef enum issl_layout {
+    ISSL_LAYOUT_AUTO = 0,     /* RES32 when the file allows it, else SIG64                  */
+    ISSL_LAYOUT_RES32 = 1,    /* slice lists hold 32-bit residual signatures inline: 4 B / candidate */
+    ISSL_LAYOUT_SIG64 = 2,    /* slice lists hold the 64-bit signature inline: 8 B / candidate      */
+    ISSL_LAYOUT_GATHER = 3    /* slice lists hold 32-bit ids, signatures gathered: 4 + 8 B / candidate
+                                 (the layout BASELINE.json's north_star describes; kept for comparison) */
+} issl_layout;
+
+typedef struct issl_device_info {
+    int cuda_device;
+    int layout;                    /* issl_layout actually in use                          */
+    uint32_t bytes_per_candidate;  /* algorithmic bytes streamed per list entry visited    */
+    uint64_t hbm_bytes;            /* bytes of HBM held by the index                       */
+    uint64_t list_entries;         /* sliceCount * offtargetsCount                          */
+    issl_info info;
+} issl_device_info;
+
+/* Counters of the last issl_score* call on a device handle. */
+typedef struct issl_stats {
+    uint64_t guides;
+    uint64_t candidates;       /* list entries visited = the unit of work (ref loop at :344)       */
+    uint64_t hits;             /* entries with dist <= maxDist that survived de-duplication        */
+    uint64_t scan_launches;    /* launches of the candidate-scan kernel                            */
+    uint64_t launches;         /* all kernel launches of ours                                      */
+    double scan_ms;            /* device time of the scan kernel(s), CUDA events on the call's stream */
+    double total_ms;           /* device time of the whole call (setup + scan + sort + score)      */
+    uint64_t early_exits;      /* guides that stopped before the last slice (threshold > 0)        */
+} issl_stats;
+
+typedef struct issl_index issl_index;     /* a parsed .issl image in host memory          */
+typedef struct issl_device issl_device;   /* an index resident in one GPU's HBM           */
+
+/* ---- host side: the .issl file ------------------------------------------------------------ */
+
+/* Maps and validates an .issl file.  Replaces the sequential fread of
+ * isslScoreOfftargets.cpp:152-243 (header, score table, signatures, list sizes, lists). */
+int issl_index_open(const char *path, issl_index **out);
+
+/* Same, over an image already in memory (not copied; must outlive the handle). */
+int issl_index_from_memory(const void *image, size_t bytes, issl_index **out);
+
+int issl_index_info(const issl_index *index, issl_info *out);
+void issl_index_close(issl_index *index);
+
+/* 2-bit packs a guide file (fixed-width lines of seqLength bases + LF) into out[bytes/(seqLength+1)].
+ * Replaces sequenceToSignature, isslScoreOfftargets.cpp:63-71 with the table of :99-102
+ * (A=0 C=1 G=2 T=3, anything else 0), applied as in :297-305.  Fails with ISSL_ERR_ARG when
+ * bytes is not a multiple of seqLength+1 (ref :277-282). */
+int issl_pack_guides(const char *text, size_t bytes, size_t seqLength, uint64_t *out);
+
+/* Inverse, ref signatureToSequence :82-89; out receives seqLength chars (no terminator). */
+void issl_unpack_guide(uint64_t signature, size_t seqLength, char *out);
+
+/* ref :121-143 */
+int issl_method_from_string(const char *name);
+
+/* ---- device side -------------------------------------------------------------------------- */
+
+/* Number of usable sm_100 devices (0 when there is none; never an error). */
+int issl_device_count(void);
+
+/* One-time re-layout of the index into the HBM of `cuda_device` (call once per GPU).
+ * Replaces the in-memory structures built at isslScoreOfftargets.cpp:200-270 (offtargets[],
+ * allSlicelistSizes, allSignatures, sliceLists pointer table).  Validates the builder's
+ * invariants (isslCreateIndex.cpp:216-234) on the device while copying. */
+int issl_device_create(const issl_index *index, int cuda_device, int layout, issl_device **out);
+
+/* Builds a synthetic index directly in HBM (benchmarks: a human-scale .issl is ~28 GB and cannot
+ * be shipped to the GPU box).  Sites are drawn from a counter-based RNG: `uniform_sites` i.i.d.
+ * uniform 20-mers whose first base is A/C/G (the extractor's regex, extractOfftargets.py:23),
+ * plus `families` near-repeat families of `family_size` copies with per-base substitution
+ * rate <= max_sub_rate; then sorted, run-length collapsed into occurrence counts and turned into
+ * slice lists exactly as isslCreateIndex.cpp:184-252 does (including its 8-bit slice truncation). */
+int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uint64_t uniform_sites,
+                                 uint32_t families, uint32_t family_size, double max_sub_rate,
+                                 uint32_t seqLength, uint32_t sliceWidth, issl_device **out);
+
+int issl_device_get_info(const issl_device *dev, issl_device_info *out);
+void issl_device_destroy(issl_device *dev);
+
+/* Serialises the device-resident index back into the reference's .issl byte format
+ * (isslCreateIndex.cpp:256-289) -- used to hand a synthetic index to the reference binary. */
+int issl_device_write_issl(issl_device *dev, const char *path);
+
+/* Copies the signatures of the sites site_ids[0..n) (taken modulo offtargetsCount) to host --
+ * used to draw benchmark guides from a synthetic index. */
+int issl_device_read_sites(issl_device *dev, const uint64_t *site_ids, uint64_t n, uint64_t *out);
+
+/* Scores n packed guides.  Replaces the parallel region isslScoreOfftargets.cpp:308-511:
+ * mit_out[i] = 10000/(100 + sum of local MIT scores * occurrences), cfd_out[i] likewise for CFD
+ * (:505-506), with the reference's order-dependent early exit (:326, :466-496) reproduced exactly.
+ * Host buffers; H2D of guides and D2H of scores happen inside the call; blocking.
+ * A column the method does not compute is left untouched (the reference prints -1 for it);
+ * its pointer may be NULL. */
+int issl_score(issl_device *dev, const uint64_t *guides, size_t n, int maxDist, double threshold,
+               int method, double *mit_out, double *cfd_out);
+
+/* Same with DEVICE pointers and a caller stream (cudaStream_t passed as void*, NULL = the
+ * handle's own stream).  Work is enqueued on that stream; the call returns after the stream
+ * has drained (the pipeline reads survivor counts back between phases). */
+int issl_score_device(issl_device *dev, const uint64_t *d_guides, size_t n, int maxDist,
+                      double threshold, int method, double *d_mit_out, double *d_cfd_out,
+                      void *stream);
+
+/* Debug / parity export: scores like issl_score and also returns every scored hit as
+ * (guide index, site id, distance, occurrences), sorted by (guide, slice, list position) -- the
+ * order in which the reference meets them (hits after a guide's early exit are not reported).
+ * *count receives the total; at most cap tuples are stored. */
+int issl_score_hits(issl_device *dev, const uint64_t *guides, size_t n, int maxDist, double threshold,
+                    int method, double *mit_out, double *cfd_out,
+                    uint64_t *hit_guide, uint32_t *hit_id, int32_t *hit_dist, uint32_t *hit_occ,
+                    size_t cap, size_t *count);
+
+int issl_last_stats(const issl_device *dev, issl_stats *out);
+
+/* ---- builder-side arithmetic (used by the synthetic builder; exposed for parity tests) ---- */
+
+/* Local MIT score of a mismatch mask (bit 2*pos set per mismatching position).
+ * ref isslCreateIndex.cpp:93-130 (single_score / sscore). */
+double issl_local_mit_score(uint64_t mask, size_t seqLength);
+
+/* The score table isslCreateIndex.cpp:239-252 writes: masks ascending; returns the number of
+ * entries written (<= cap) and the header's scoresCount through *scoresCount. */
+size_t issl_mit_table(size_t seqLength, size_t sliceWidth, uint64_t *masks, double *scores, size_t cap,
+                      uint64_t *scoresCount);
+
+const char *issl_last_error(void);
+int issl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISSL_CUDA_H */

@@ -1,0 +1,130 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, host-side logic (guide packing, method names, builder arithmetic, .issl
+validation) agrees with the oracle, and the host program keeps the reference's CLI contract.
+No compute call is made (there is no GPU here and the product has no CPU path)."""
+import pathlib
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import crackling_b200 as cb
+import issl_testdata as td
+from conftest import golden_case
+from oracle import oracle
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def declared_functions():
+    text = (ROOT / "include" / "issl_cuda.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(issl_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = cb.lib()
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"libissl_cuda.so does not export {n}"
+    assert set(L._issl_symbols) == set(names), "binding.py and issl_cuda.h disagree"
+    assert L.issl_abi_version() == 1
+
+
+def test_pack_unpack_and_methods():
+    g = td.make_guides(7, td.make_offtargets(7, n_random=50, n_families=1, family_size=5), n=33)
+    got = cb.pack_guides(g)
+    assert np.array_equal(got, td.pack_guides(g))
+    assert [int(x) for x in got] == [oracle.encode(g[i * 21:i * 21 + 20]) for i in range(33)]
+    assert cb.unpack_guide(got[0]) == g[:20].decode()
+    assert cb.pack_guides(b"NNNNACGTACGTACGTACGT\n")[0] == cb.pack_guides(b"AAAAACGTACGTACGTACGT\n")[0]
+    with pytest.raises(cb.IsslError):
+        cb.pack_guides(b"ACGT\n" * 3 + b"A", 4)
+    for name, code in cb.METHODS.items():
+        assert cb.method_code(name) == code
+    assert cb.method_code("MIT") == 0 and cb.method_code("") == 0
+
+
+@pytest.mark.parametrize("w", [4, 5, 8, 10])
+def test_mit_table_is_bit_identical_to_reference_builder(w):
+    # the oracle image is itself pinned to the reference isslCreateIndex (test_oracle_golden.py)
+    img = oracle.create_index(b"ACGTACGTACGTACGTACGT\n", 20, w)
+    masks, scores, header_count = cb.mit_table(20, w)
+    assert header_count == oracle.header(img)["scoresCount"]
+    pairs = np.frombuffer(img[48:48 + 16 * header_count], dtype=np.uint64).reshape(-1, 2)
+    assert np.array_equal(pairs[:, 0], masks)
+    assert np.array_equal(pairs[:, 1], scores.view(np.uint64))
+    assert cb.local_mit_score(0x1) == 100.0 and cb.local_mit_score(0x5) == 5.219780219780221
+
+
+def test_index_validation():
+    case = golden_case("w8_families")
+    img = case.issl
+    ix = cb.Index(img)
+    assert ix.info == {k: v for k, v in case.expected["header"].items() if k != "rc"}
+    for cut, text in [(40, "header invalid"), (48 + 100, "header invalid"), (len(img) - 8, "slice contents"),
+                      (48 + 16 * 6195 + 64, "off-target sequences")]:
+        with pytest.raises(cb.IsslError) as e:
+            cb.Index(img[:cut])
+        assert e.value.code == 2 and text in e.value.message
+    # a list-size table that does not sum to one entry per site per slice is refused
+    bad = bytearray(img)
+    off = 48 + 16 * 6195 + 8 * ix.info["offtargetsCount"]
+    bad[off:off + 8] = (int.from_bytes(bad[off:off + 8], "little") + 1).to_bytes(8, "little")
+    with pytest.raises(cb.IsslError) as e:
+        cb.Index(bytes(bad))
+    assert e.value.code == 6
+
+
+def run_cli(*args):
+    return subprocess.run([str(cb.cli_path()), *map(str, args)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+
+
+def test_cli_contract_without_scoring(tmp_path):
+    case = golden_case("tiny")
+    (tmp_path / "i.issl").write_bytes(case.issl)
+    (tmp_path / "g.txt").write_bytes(case.guides)
+    p = run_cli()
+    assert p.returncode == 1 and p.stdout == b"" and b"Usage:" in p.stderr and b"[issltable] [query file] [max distance]" in p.stderr
+    p = run_cli(tmp_path / "i.issl", tmp_path / "g.txt", 4, 0)          # the reference would crash; we refuse
+    assert p.returncode == 1 and p.stdout == b""
+    # unknown method: every line SEQ\t-1\t-1 (isslScoreOfftargets.cpp:122-143, :517-525) -- nothing is scored
+    p = run_cli(tmp_path / "i.issl", tmp_path / "g.txt", 4, 0, "bogus")
+    want = [r for r in case.expected["runs"] if r["method"] == "bogus"][0]
+    assert p.returncode == 0 and p.stdout.decode() == want["stdout"]
+    # guide file not a multiple of the line length: same three stderr lines, exit 1
+    (tmp_path / "bad.txt").write_bytes(case.guides[:-3])
+    p = run_cli(tmp_path / "i.issl", tmp_path / "bad.txt", 4, 0, "mit")
+    assert p.returncode == 1 and p.stdout == b""
+    assert p.stderr.decode().splitlines()[0] == "Error: query file is not a multiple of the expected line length (21)"
+    (tmp_path / "empty.txt").write_bytes(b"")
+    p = run_cli(tmp_path / "i.issl", tmp_path / "empty.txt", 4, 0, "mit")
+    assert p.returncode == 1 and b"Failed to read in query file." in p.stderr
+    (tmp_path / "trunc.issl").write_bytes(case.issl[:30])
+    p = run_cli(tmp_path / "trunc.issl", tmp_path / "g.txt", 4, 0, "mit")
+    assert p.returncode == 1 and b"Error reading index: header invalid" in p.stderr and p.stdout == b""
+
+
+def test_no_gpu_means_loud_failure_not_fallback(tmp_path):
+    if cb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    case = golden_case("tiny")
+    with pytest.raises(cb.IsslError) as e:
+        cb.Device.from_index(cb.Index(case.issl))
+    assert e.value.code == 4
+    (tmp_path / "i.issl").write_bytes(case.issl)
+    (tmp_path / "g.txt").write_bytes(case.guides)
+    p = run_cli(tmp_path / "i.issl", tmp_path / "g.txt", 4, 0, "mit")
+    assert p.returncode == 1 and p.stdout == b"" and b"no CPU fallback" in p.stderr
+
+
+def test_product_never_touches_the_oracle():
+    for path in list((ROOT / "crackling_b200").rglob("*.py")) + list((ROOT / "crackling_b200" / "csrc").glob("*")) + \
+            [ROOT / "include" / "issl_cuda.h"]:
+        if path.is_file() and path.suffix in (".py", ".h", ".cpp", ".cu", ".cuh"):
+            text = path.read_text(errors="replace")
+            assert "issl_oracle" not in text and "from oracle" not in text and "import oracle" not in text, path
+    out = subprocess.run(["ldd", str(cb.lib_path())], stdout=subprocess.PIPE).stdout.decode()
+    assert "oracle" not in out
