@@ -35,7 +35,7 @@ class _DeviceInfo(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("guides", C.c_uint64), ("candidates", C.c_uint64), ("hits", C.c_uint64),
                 ("scan_launches", C.c_uint64), ("launches", C.c_uint64), ("scan_ms", C.c_double),
-                ("total_ms", C.c_double), ("early_exits", C.c_uint64)]
+                ("total_ms", C.c_double), ("early_exits", C.c_uint64), ("streamed", C.c_uint64)]
 
 
 _lib = None

@@ -79,7 +79,7 @@ struct issl_device {
 
     // scoring scratch
     cudaStream_t stream = nullptr;
-    DBuf guides, totMit, totCfd, done, pairCounts, pairOffsets, items, keysA, keysB, sortTemp, scanTemp,
+    DBuf guides, totMit, totCfd, done, pairKeys, pairVals, pairKeysSorted, pairValsSorted, pairCounts, pairOffsets, items, keysA, keysB, sortTemp, scanTemp,
         contribMit, contribCfd, counters, outMit, outCfd, hitId, hitDist, hitOcc, scoredEnd, segBegin;
     unsigned long long *hCounters = nullptr;   // pinned: [0] total candidates, [1] hit count, [2] items, [3] done
     uint64_t hitCap = 0;
@@ -240,7 +240,7 @@ extern "C" void issl_device_destroy(issl_device *d)
     cudaSetDevice(d->dev);
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (DBuf *b : {&d->sig, &d->occ, &d->ids, &d->res32, &d->sig64, &d->listStart, &d->listLen, &d->filePrefix,
-                    &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairCounts,
+                    &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
                     &d->scoredEnd, &d->segBegin})
@@ -610,34 +610,50 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         const uint64_t pairs = (uint64_t)n * ns;
         const uint8_t *doneMask = checkExit ? d->done.as<uint8_t>() : nullptr;
 
+        // group the (guide, slice) pairs by the list they select: radix sort of (list id, guide index)
+        const uint32_t nLists = (uint32_t)d->nLists;
+        CKR(d->pairKeys.ensure(pairs * 4)); CKR(d->pairVals.ensure(pairs * 4));
+        CKR(d->pairKeysSorted.ensure(pairs * 4)); CKR(d->pairValsSorted.ensure(pairs * 4));
         CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
-        k_wave_total<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
+        k_pair_keys<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, nLists,
+                                                           d->pairKeys.as<uint32_t>(), d->pairVals.as<uint32_t>(), dc + 0);
+        int keyBits = 1;
+        while ((1ull << keyBits) <= nLists) keyBits++;
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, d->pairKeys.as<uint32_t>(), d->pairKeysSorted.as<uint32_t>(),
+                                           d->pairVals.as<uint32_t>(), d->pairValsSorted.as<uint32_t>(), pairs, 0, keyBits, st));
+        CKR(d->sortTemp.ensure(tb));
+        CK(cub::DeviceRadixSort::SortPairs(d->sortTemp.p, tb, d->pairKeys.as<uint32_t>(), d->pairKeysSorted.as<uint32_t>(),
+                                           d->pairVals.as<uint32_t>(), d->pairValsSorted.as<uint32_t>(), pairs, 0, keyBits, st));
         CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        d->stats.launches += 1;
+        d->stats.launches += 1 + (uint64_t)((keyBits + 7) / 8) + 2;
         const uint64_t candidates = d->hCounters[0];
         d->stats.candidates += candidates;
         if (candidates == 0) continue;
 
-        // chunk: aim at >= ~64k items for balance, never below one quantum
-        uint64_t chunk64 = (candidates / 65536 + kChunkQuantum - 1) / kChunkQuantum * kChunkQuantum;
+        // chunk: aim at a few hundred thousand items at most, never below two quanta
+        uint64_t chunk64 = (candidates / (1ull << 19) + kChunkQuantum - 1) / kChunkQuantum * kChunkQuantum;
         chunk64 = std::max<uint64_t>(chunk64, 2 * kChunkQuantum);
         chunk64 = std::min<uint64_t>(chunk64, 1ull << 30);
         const uint32_t chunk = (uint32_t)chunk64;
 
         CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
-        k_wave_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, chunk, d->pairCounts.as<uint32_t>());
+        k_group_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
+                                                             d->pairCounts.as<uint32_t>(), dc + 4);
         CK(cudaMemsetAsync(d->pairCounts.as<uint32_t>() + pairs, 0, 4, st));
-        size_t tb = 0;
+        tb = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
         CKR(d->scanTemp.ensure(tb));
         CK(cub::DeviceScan::ExclusiveSum(d->scanTemp.p, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
         CK(cudaMemcpyAsync(d->hCounters + 2, d->pairOffsets.as<uint32_t>() + pairs, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(d->hCounters + 4, dc + 4, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const uint32_t nItems = *reinterpret_cast<uint32_t *>(d->hCounters + 2);
+        d->stats.streamed += d->hCounters[4];
         CKR(d->items.ensure((size_t)nItems * sizeof(ScanItem)));
-        k_wave_fill<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, chunk,
-                                                           d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
+        k_group_fill<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
+                                                            d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
         d->stats.launches += 4;
 
         // K1 (re-run with a larger survivor buffer if it overflowed)
@@ -649,7 +665,8 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
             ScanArgs a;
-            a.iv = d->iv; a.items = d->items.as<ScanItem>(); a.guides = dGuides; a.hitKeys = d->keysA.as<uint64_t>();
+            a.iv = d->iv; a.items = d->items.as<ScanItem>(); a.guides = dGuides;
+            a.sortedGuide = d->pairValsSorted.as<uint32_t>(); a.hitKeys = d->keysA.as<uint64_t>();
             a.hitCount = dc + 1; a.hitCap = d->hitCap; a.maxDist = maxDist; a.pbits = d->pbits;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));

@@ -14,7 +14,6 @@
 namespace issl {
 
 constexpr int kScanThreads = 256;      // threads per scan CTA
-constexpr int kScanUnroll = 4;         // 16-byte loads in flight per thread
 constexpr uint32_t kListAlign = 32;    // list starts are padded to 32 entries (128 B of residuals)
 constexpr uint32_t kChunkQuantum = 4096;   // scan-item sizes are multiples of this many entries
 
@@ -39,12 +38,15 @@ struct IndexView {
     int layout;
 };
 
-// One unit of scan work: `count` consecutive list positions starting at p0, tested against guide g.
+// One unit of scan work: `count` consecutive list positions starting at p0, tested against a GROUP
+// of up to kMaxGroup guides that all selected this list (same slice, same slice value).  The chunk
+// is streamed from HBM once and every guide of the group is tested against it from registers.
 struct ScanItem {
-    uint64_t p0Slice;   // bits 0..55 position, bits 56..63 slice index
+    uint64_t p0Slice;     // bits 0..39 position p0, bits 40..47 group size (1..8), bits 56..63 slice index
     uint32_t count;
-    uint32_t guide;     // index into the batch's guide array
+    uint32_t groupStart;  // index of the group's first member in the list-sorted guide index array
 };
+constexpr int kMaxGroup = 8;
 
 __constant__ double c_cfdPos[320];
 __constant__ double c_cfdPam[16];
@@ -92,10 +94,11 @@ __device__ __forceinline__ bool in_list(uint64_t siteSig, uint64_t guideSig, uin
 
 // ------------------------------------------------------------------------------------------------
 // K1: candidate scan.  ref isslScoreOfftargets.cpp:344-390 (the inner hot loop) for one
-// (guide, slice, chunk of the selected list).
+// (group of guides, slice, chunk of the list they all selected).
 //
 // Streams the chunk with coalesced 16-byte loads (4 residuals / 2 signatures / 4 ids per load,
-// kScanUnroll loads in flight per thread), XOR + fold + popcount, keeps dist <= maxDist.
+// 2-4 loads in flight per thread), XOR + fold + popcount against every guide of the group held in
+// registers, keeps dist <= maxDist.
 // De-duplication is stateless: a site reached through several slices is counted only in the
 // lowest slice whose looked-up list contains it (in_list), which is where the reference's toggle
 // bitset (:385-390, :463) lets it through, because every list holds each site at most once and
@@ -106,7 +109,8 @@ __device__ __forceinline__ bool in_list(uint64_t siteSig, uint64_t guideSig, uin
 struct ScanArgs {
     IndexView iv;
     const ScanItem *items;
-    const uint64_t *guides;
+    const uint64_t *guides;        // the batch's packed guides
+    const uint32_t *sortedGuide;   // guide indices sorted by the list they select
     uint64_t *hitKeys;
     unsigned long long *hitCount;
     uint64_t hitCap;
@@ -123,113 +127,183 @@ __device__ __forceinline__ void emit_hit(const ScanArgs &a, uint64_t guideSig, u
     if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << a.pbits) | pos;
 }
 
+// Rare path (about one 16-byte vector in 800 per guide on a uniform genome): some candidate of a
+// vector is within maxDist of some guide of the group.  Re-tests every (candidate, guide) pair of
+// the vector exactly and emits the survivors.  Kept out of line so that the streaming loop stays
+// small; everything it needs is re-read from global memory.
 template <int LAYOUT>
-__global__ void __launch_bounds__(kScanThreads) k_scan(const ScanArgs a)
+__device__ __noinline__ void scan_slow(const ScanArgs &a, uint32_t slice, uint32_t groupStart, uint32_t groupSize,
+                                       uint64_t pos0, int nCand, uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3)
 {
-    const ScanItem it = a.items[blockIdx.x];
-    const uint32_t slice = (uint32_t)(it.p0Slice >> 56);
-    const uint64_t p0 = it.p0Slice & ((1ull << 56) - 1ull);
-    const uint32_t n = it.count;
-    const uint64_t g = a.guides[it.guide];
-    const int maxDist = a.maxDist;
-    const uint32_t tid = threadIdx.x;
-
-    if (LAYOUT == kRes32) {
-        const uint32_t off = a.iv.sliceWidth * slice, kb = a.iv.knownBits;
-        const uint32_t gres = (uint32_t)remove_bits(g, off, kb);
-        const uint64_t known = (g >> off) & ((1ull << kb) - 1ull);
-        const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.res32 + p0);
-        const uint32_t nvec = n >> 2;
-        auto test = [&](uint32_t r, uint64_t pos) {
-            if (distance32(r ^ gres) <= maxDist)
-                emit_hit(a, g, insert_bits(r, off, kb, known), slice, it.guide, pos);
-        };
-        uint32_t i = tid;
-        for (; i + (kScanUnroll - 1) * kScanThreads < nvec; i += kScanUnroll * kScanThreads) {
-            uint4 r[kScanUnroll];
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) r[u] = __ldcs(v4 + i + u * kScanThreads);
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) {
-                const uint64_t pos = p0 + 4ull * (i + u * kScanThreads);
-                test(r[u].x, pos); test(r[u].y, pos + 1); test(r[u].z, pos + 2); test(r[u].w, pos + 3);
-            }
-        }
-        for (; i < nvec; i += kScanThreads) {
-            const uint4 r = __ldcs(v4 + i);
-            const uint64_t pos = p0 + 4ull * i;
-            test(r.x, pos); test(r.y, pos + 1); test(r.z, pos + 2); test(r.w, pos + 3);
-        }
-        if (tid < (n & 3u)) {
-            const uint64_t pos = p0 + 4ull * nvec + tid;
-            test(a.iv.res32[pos], pos);
-        }
-    } else if (LAYOUT == kSig64) {
-        const ulonglong2 *__restrict__ v2 = reinterpret_cast<const ulonglong2 *>(a.iv.sig64 + p0);
-        const uint32_t nvec = n >> 1;
-        auto test = [&](uint64_t s, uint64_t pos) {
-            if (distance64(s ^ g) <= maxDist) emit_hit(a, g, s, slice, it.guide, pos);
-        };
-        uint32_t i = tid;
-        for (; i + (kScanUnroll - 1) * kScanThreads < nvec; i += kScanUnroll * kScanThreads) {
-            ulonglong2 r[kScanUnroll];
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) r[u] = __ldcs(v2 + i + u * kScanThreads);
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) {
-                const uint64_t pos = p0 + 2ull * (i + u * kScanThreads);
-                test(r[u].x, pos); test(r[u].y, pos + 1);
-            }
-        }
-        for (; i < nvec; i += kScanThreads) {
-            const ulonglong2 r = __ldcs(v2 + i);
-            const uint64_t pos = p0 + 2ull * i;
-            test(r.x, pos); test(r.y, pos + 1);
-        }
-        if (tid < (n & 1u)) {
-            const uint64_t pos = p0 + 2ull * nvec + tid;
-            test(a.iv.sig64[pos], pos);
-        }
-    } else {   // kGather: ids streamed, signatures gathered (the reference's own access pattern, :346-376)
-        const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.ids + p0);
-        const uint64_t *__restrict__ sig = a.iv.sig;
-        const uint32_t nvec = n >> 2;
-        auto test = [&](uint64_t s, uint64_t pos) {
-            if (distance64(s ^ g) <= maxDist) emit_hit(a, g, s, slice, it.guide, pos);
-        };
-        uint32_t i = tid;
-        for (; i + (kScanUnroll - 1) * kScanThreads < nvec; i += kScanUnroll * kScanThreads) {
-            uint4 r[kScanUnroll];
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) r[u] = __ldcs(v4 + i + u * kScanThreads);
-            uint64_t s[kScanUnroll][4];
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) {
-                s[u][0] = __ldg(sig + r[u].x); s[u][1] = __ldg(sig + r[u].y);
-                s[u][2] = __ldg(sig + r[u].z); s[u][3] = __ldg(sig + r[u].w);
-            }
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; u++) {
-                const uint64_t pos = p0 + 4ull * (i + u * kScanThreads);
-#pragma unroll
-                for (int c = 0; c < 4; c++) test(s[u][c], pos + c);
-            }
-        }
-        for (; i < nvec; i += kScanThreads) {
-            const uint4 r = __ldcs(v4 + i);
-            const uint64_t pos = p0 + 4ull * i;
-            test(__ldg(sig + r.x), pos); test(__ldg(sig + r.y), pos + 1);
-            test(__ldg(sig + r.z), pos + 2); test(__ldg(sig + r.w), pos + 3);
-        }
-        if (tid < (n & 3u)) {
-            const uint64_t pos = p0 + 4ull * nvec + tid;
-            test(__ldg(sig + a.iv.ids[pos]), pos);
+    const uint32_t off = a.iv.sliceWidth * slice, kb = a.iv.knownBits;
+    const uint64_t cand[4] = {c0, c1, c2, c3};
+    for (uint32_t j = 0; j < groupSize; j++) {
+        const uint32_t guide = a.sortedGuide[groupStart + j];
+        const uint64_t g = a.guides[guide];
+        for (int c = 0; c < nCand; c++) {
+            uint64_t site = cand[c];
+            if (LAYOUT == kRes32) site = insert_bits(site, off, kb, (g >> off) & ((1ull << kb) - 1ull));
+            if (distance64(site ^ g) <= a.maxDist) emit_hit(a, g, site, slice, guide, pos0 + c);
         }
     }
 }
 
+// Streaming loop for one group class (G = 1, 2, 4, 8 guides held in registers).
+//
+// kRes32: 4 candidates per 16-byte load.  G <= 2 uses x = c ^ g; popc((x | x >> 1) & 0x5555..);
+// G >= 4 pre-splits candidate and guides into their even-bit and odd-bit planes once
+// (cE = c & M, cO = (c >> 1) & M), so that one pair costs two LOP3 and one POPC:
+// popc((cE ^ gE) | (cO ^ gO)).  The minimum distance of all pairs of a vector is reduced with
+// integer min and tested with a single branch.
+template <int LAYOUT, int G>
+__device__ __forceinline__ void scan_body(const ScanArgs &a, const ScanItem &it)
+{
+    constexpr uint32_t M32 = 0x55555555u;
+    constexpr uint64_t M64 = 0x5555555555555555ull;
+    constexpr int U = (G >= 4) ? 2 : 4;          // 16-byte loads in flight per thread
+    const uint32_t slice = (uint32_t)(it.p0Slice >> 56);
+    const uint32_t groupSize = (uint32_t)(it.p0Slice >> 40) & 0xFFu;
+    const uint64_t p0 = it.p0Slice & ((1ull << 40) - 1ull);
+    const uint32_t n = it.count, tid = threadIdx.x;
+    const int maxDist = a.maxDist;
+    const uint32_t off = a.iv.sliceWidth * slice, kb = a.iv.knownBits;
+
+    if (LAYOUT == kRes32) {
+        uint32_t gE[G], gO[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const uint32_t member = (uint32_t)j < groupSize ? (uint32_t)j : 0u;   // padding slots repeat member 0
+            const uint32_t r = (uint32_t)remove_bits(a.guides[a.sortedGuide[it.groupStart + member]], off, kb);
+            if (G >= 4) { gE[j] = r & M32; gO[j] = (r >> 1) & M32; } else { gE[j] = r; gO[j] = 0; }
+        }
+        auto vec_min = [&](const uint4 &r) {
+            const uint32_t c[4] = {r.x, r.y, r.z, r.w};
+            int m = 64;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (G >= 4) {
+                    const uint32_t cE = c[k] & M32, cO = (c[k] >> 1) & M32;
+#pragma unroll
+                    for (int j = 0; j < G; j++) m = min(m, __popc((cE ^ gE[j]) | (cO ^ gO[j])));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; j++) { const uint32_t x = c[k] ^ gE[j]; m = min(m, __popc((x | (x >> 1)) & M32)); }
+                }
+            }
+            return m;
+        };
+        const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.res32 + p0);
+        const uint32_t nvec = n >> 2;
+        uint32_t i = tid;
+        for (; i + (U - 1) * kScanThreads < nvec; i += U * kScanThreads) {
+            uint4 r[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) r[u] = __ldcs(v4 + i + u * kScanThreads);
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (vec_min(r[u]) <= maxDist)
+                    scan_slow<kRes32>(a, slice, it.groupStart, groupSize, p0 + 4ull * (i + u * kScanThreads), 4,
+                                      r[u].x, r[u].y, r[u].z, r[u].w);
+        }
+        for (; i < nvec; i += kScanThreads) {
+            const uint4 r = __ldcs(v4 + i);
+            if (vec_min(r) <= maxDist)
+                scan_slow<kRes32>(a, slice, it.groupStart, groupSize, p0 + 4ull * i, 4, r.x, r.y, r.z, r.w);
+        }
+        if (tid == 0 && (n & 3u)) {
+            const uint64_t pos = p0 + 4ull * nvec;
+            uint64_t c[4] = {0, 0, 0, 0};
+            for (uint32_t k = 0; k < (n & 3u); k++) c[k] = a.iv.res32[pos + k];
+            scan_slow<kRes32>(a, slice, it.groupStart, groupSize, pos, (int)(n & 3u), c[0], c[1], c[2], c[3]);
+        }
+    } else {
+        // 64-bit signatures: inline (kSig64, 2 per 16-byte load) or gathered through ids (kGather, the
+        // reference's own access pattern, isslScoreOfftargets.cpp:346-376).  Two POPC per pair.
+        uint64_t gE[G], gO[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const uint32_t member = (uint32_t)j < groupSize ? (uint32_t)j : 0u;
+            const uint64_t g = a.guides[a.sortedGuide[it.groupStart + member]];
+            gE[j] = g & M64; gO[j] = (g >> 1) & M64;
+        }
+        auto pair_min = [&](uint64_t s, int m) {
+            const uint64_t cE = s & M64, cO = (s >> 1) & M64;
+#pragma unroll
+            for (int j = 0; j < G; j++) m = min(m, __popcll((cE ^ gE[j]) | (cO ^ gO[j])));
+            return m;
+        };
+        if (LAYOUT == kSig64) {
+            const ulonglong2 *__restrict__ v2 = reinterpret_cast<const ulonglong2 *>(a.iv.sig64 + p0);
+            const uint32_t nvec = n >> 1;
+            uint32_t i = tid;
+            for (; i + (U - 1) * kScanThreads < nvec; i += U * kScanThreads) {
+                ulonglong2 r[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) r[u] = __ldcs(v2 + i + u * kScanThreads);
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (pair_min(r[u].y, pair_min(r[u].x, 64)) <= maxDist)
+                        scan_slow<kSig64>(a, slice, it.groupStart, groupSize, p0 + 2ull * (i + u * kScanThreads), 2,
+                                          r[u].x, r[u].y, 0, 0);
+            }
+            for (; i < nvec; i += kScanThreads) {
+                const ulonglong2 r = __ldcs(v2 + i);
+                if (pair_min(r.y, pair_min(r.x, 64)) <= maxDist)
+                    scan_slow<kSig64>(a, slice, it.groupStart, groupSize, p0 + 2ull * i, 2, r.x, r.y, 0, 0);
+            }
+            if (tid == 0 && (n & 1u))
+                scan_slow<kSig64>(a, slice, it.groupStart, groupSize, p0 + 2ull * nvec, 1, a.iv.sig64[p0 + 2ull * nvec], 0, 0, 0);
+        } else {
+            const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.ids + p0);
+            const uint64_t *__restrict__ sig = a.iv.sig;
+            const uint32_t nvec = n >> 2;
+            uint32_t i = tid;
+            for (; i + (U - 1) * kScanThreads < nvec; i += U * kScanThreads) {
+                uint4 r[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) r[u] = __ldcs(v4 + i + u * kScanThreads);
+                uint64_t s[U][4];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    s[u][0] = __ldg(sig + r[u].x); s[u][1] = __ldg(sig + r[u].y);
+                    s[u][2] = __ldg(sig + r[u].z); s[u][3] = __ldg(sig + r[u].w);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (pair_min(s[u][3], pair_min(s[u][2], pair_min(s[u][1], pair_min(s[u][0], 64)))) <= maxDist)
+                        scan_slow<kGather>(a, slice, it.groupStart, groupSize, p0 + 4ull * (i + u * kScanThreads), 4,
+                                           s[u][0], s[u][1], s[u][2], s[u][3]);
+            }
+            for (; i < nvec; i += kScanThreads) {
+                const uint4 r = __ldcs(v4 + i);
+                const uint64_t s0 = __ldg(sig + r.x), s1 = __ldg(sig + r.y), s2 = __ldg(sig + r.z), s3 = __ldg(sig + r.w);
+                if (pair_min(s3, pair_min(s2, pair_min(s1, pair_min(s0, 64)))) <= maxDist)
+                    scan_slow<kGather>(a, slice, it.groupStart, groupSize, p0 + 4ull * i, 4, s0, s1, s2, s3);
+            }
+            if (tid == 0 && (n & 3u)) {
+                const uint64_t pos = p0 + 4ull * nvec;
+                uint64_t c[4] = {0, 0, 0, 0};
+                for (uint32_t k = 0; k < (n & 3u); k++) c[k] = sig[a.iv.ids[pos + k]];
+                scan_slow<kGather>(a, slice, it.groupStart, groupSize, pos, (int)(n & 3u), c[0], c[1], c[2], c[3]);
+            }
+        }
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kScanThreads) k_scan(const ScanArgs a)
+{
+    const ScanItem it = a.items[blockIdx.x];
+    const uint32_t groupSize = (uint32_t)(it.p0Slice >> 40) & 0xFFu;
+    if (groupSize > 4) scan_body<LAYOUT, 8>(a, it);
+    else if (groupSize > 2) scan_body<LAYOUT, 4>(a, it);
+    else if (groupSize == 2) scan_body<LAYOUT, 2>(a, it);
+    else scan_body<LAYOUT, 1>(a, it);
+}
+
 // ------------------------------------------------------------------------------------------------
-// Scan-item construction (ref :330-341: slice value -> list -> length).
+// Scan-item construction (ref :330-341: slice value -> list -> length), with guides grouped by
+// the list they select so that a list chunk is streamed once per group instead of once per guide.
 // One "pair" = (guide, slice) for slices in [slice0, slice0 + nSlices).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t pair_list(const IndexView &iv, uint64_t g, uint32_t slice)
@@ -238,53 +312,90 @@ __device__ __forceinline__ uint64_t pair_list(const IndexView &iv, uint64_t g, u
     return (uint64_t)slice * iv.sliceLimit + v;
 }
 
-// pass 1: total candidates of the wave (decides the chunk size; also the reported unit count)
-__global__ void k_wave_total(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
-                             uint32_t slice0, uint32_t nSlices, unsigned long long *total)
+// pass 1: sort key (list id; nLists = "no work") and value (guide index) of every pair, plus the
+// total number of candidates of the wave = the reported unit count (entries the reference visits).
+__global__ void k_pair_keys(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
+                            uint32_t slice0, uint32_t nSlices, uint32_t nLists, uint32_t *keys, uint32_t *vals,
+                            unsigned long long *total)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long len = 0;
     if (t < (uint64_t)nGuides * nSlices) {
         const uint32_t gi = (uint32_t)(t / nSlices), s = slice0 + (uint32_t)(t % nSlices);
-        if (!done || !done[gi]) len = iv.listLen[pair_list(iv, guides[gi], s)];
+        uint32_t key = nLists;
+        if (!done || !done[gi]) {
+            const uint64_t list = pair_list(iv, guides[gi], s);
+            len = iv.listLen[list];
+            if (len) key = (uint32_t)list;
+        }
+        keys[t] = key;
+        vals[t] = gi;
     }
-    // warp-reduce before the atomic
     for (int o = 16; o > 0; o >>= 1) len += __shfl_down_sync(0xffffffffu, len, o);
     if ((threadIdx.x & 31) == 0 && len) atomicAdd(total, len);
 }
 
-// pass 2: chunks per pair
-__global__ void k_wave_count(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
-                             uint32_t slice0, uint32_t nSlices, uint32_t chunk, uint32_t *counts)
+// Group shape of sorted pair i: runs of equal list id are cut into groups of 8; a remainder r is
+// cut as 7..8 -> one group, 5..6 -> 4 + (r - 4), 1..4 -> one group.  Returns the group size when i
+// is the first member of a group, else 0.
+__device__ __forceinline__ uint32_t group_head_size(uint32_t rank, uint32_t runLen)
 {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)nGuides * nSlices) return;
-    const uint32_t gi = (uint32_t)(t / nSlices), s = slice0 + (uint32_t)(t % nSlices);
-    uint32_t c = 0;
-    if (!done || !done[gi]) {
-        const uint64_t len = iv.listLen[pair_list(iv, guides[gi], s)];
-        c = (uint32_t)((len + chunk - 1) / chunk);
-    }
-    counts[t] = c;
+    const uint32_t base = runLen & ~7u, r = runLen - base;
+    if (rank < base) return (rank & 7u) == 0 ? 8u : 0u;
+    const uint32_t q = rank - base;
+    if (q == 0) return (r == 5 || r == 6) ? 4u : r;
+    if (q == 4 && (r == 5 || r == 6)) return r - 4;
+    return 0u;
 }
 
-// pass 3: write the items of every pair at its scanned offset
-__global__ void k_wave_fill(IndexView iv, const uint64_t *guides, const uint8_t *done, uint32_t nGuides,
-                            uint32_t slice0, uint32_t nSlices, uint32_t chunk, const uint32_t *offsets,
-                            ScanItem *items)
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *keys, uint32_t n, uint32_t key)
 {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)nGuides * nSlices) return;
-    const uint32_t gi = (uint32_t)(t / nSlices), s = slice0 + (uint32_t)(t % nSlices);
-    if (done && done[gi]) return;
-    const uint64_t list = pair_list(iv, guides[gi], s);
-    const uint64_t len = iv.listLen[list], start = iv.listStart[list];
-    uint32_t o = offsets[t];
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// pass 2: items per sorted pair (non-zero only at group heads)
+__global__ void k_group_count(IndexView iv, const uint32_t *sortedKeys, uint32_t nPairs, uint32_t nLists, uint32_t chunk,
+                              uint32_t *counts, unsigned long long *streamed)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nPairs) return;
+    uint32_t c = 0;
+    const uint32_t key = sortedKeys[i];
+    if (key < nLists) {
+        const uint32_t lb = lower_bound_u32(sortedKeys, nPairs, key), ub = lower_bound_u32(sortedKeys, nPairs, key + 1);
+        if (group_head_size(i - lb, ub - lb)) {
+            const uint64_t len = iv.listLen[key];
+            c = (uint32_t)((len + chunk - 1) / chunk);
+            atomicAdd(streamed, (unsigned long long)len);
+        }
+    }
+    counts[i] = c;
+}
+
+// pass 3: write the items of every group at its scanned offset
+__global__ void k_group_fill(IndexView iv, const uint32_t *sortedKeys, uint32_t nPairs, uint32_t nLists, uint32_t chunk,
+                             const uint32_t *offsets, ScanItem *items)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nPairs) return;
+    const uint32_t key = sortedKeys[i];
+    if (key >= nLists) return;
+    const uint32_t lb = lower_bound_u32(sortedKeys, nPairs, key), ub = lower_bound_u32(sortedKeys, nPairs, key + 1);
+    const uint32_t size = group_head_size(i - lb, ub - lb);
+    if (!size) return;
+    const uint64_t len = iv.listLen[key], start = iv.listStart[key];
+    const uint64_t slice = key / iv.sliceLimit;
+    uint32_t o = offsets[i];
     for (uint64_t c0 = 0; c0 < len; c0 += chunk, o++) {
         ScanItem it;
-        it.p0Slice = (start + c0) | ((uint64_t)s << 56);
+        it.p0Slice = (start + c0) | ((uint64_t)size << 40) | (slice << 56);
         it.count = (uint32_t)((len - c0 < chunk) ? (len - c0) : chunk);
-        it.guide = gi;
+        it.groupStart = i;
         items[o] = it;
     }
 }

@@ -92,6 +92,7 @@ typedef struct issl_stats {
     double scan_ms;            /* device time of the scan kernel(s), CUDA events on the call's stream */
     double total_ms;           /* device time of the whole call (setup + scan + sort + score)      */
     uint64_t early_exits;      /* guides that stopped before the last slice (threshold > 0)        */
+    uint64_t streamed;         /* list entries actually read from HBM (each chunk once per guide GROUP) */
 } issl_stats;
 
 typedef struct issl_index issl_index;     /* a parsed .issl image in host memory          */
