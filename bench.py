@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--family-size", type=int, default=0)
     ap.add_argument("--cpu-guides", type=int, default=0, help="guides in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-group", type=int, default=32, choices=[1, 2, 4, 8, 32],
+                    help="guides sharing one streamed list chunk (1 = pure HBM streaming, one guide per scan item)")
     ap.add_argument("--scratch", default=None, help="directory for the .issl handed to the reference (default /dev/shm)")
     return ap.parse_args()
 
@@ -143,7 +145,7 @@ def hbm_peak() -> tuple[float, str]:
 
 
 def ncu_traffic_per_candidate(layout_name: str):
-    """dram bytes per candidate of k_scan from the committed ncu --set full capture, if any."""
+    """dram bytes per streamed list entry of k_scan from the committed ncu --set full capture, if any."""
     p = ROOT / "profiles" / "scan_traffic.json"
     if p.exists():
         try:
@@ -192,16 +194,29 @@ def time_port(issl_path: str, guides: np.ndarray, max_dist: int, threshold: floa
     return time.perf_counter() - t0
 
 
-def cpu_baseline(dev, guides: np.ndarray, args, n_sample: int) -> dict:
+def fmt_lines(guides: np.ndarray, mit: np.ndarray, cfd: np.ndarray) -> bytes:
+    """The reference's output lines (isslScoreOfftargets.cpp:514-527) for method and/or/avg."""
+    import crackling_b200 as cb
+    return b"".join(b"%s\t%s\t%s\n" % (cb.unpack_guide(int(s)).encode(), b"%f" % m, b"%f" % c)
+                    for s, m, c in zip(guides, mit, cfd))
+
+
+def cpu_baseline(dev, guides: np.ndarray, args, n_sample: int, gpu_mit=None, gpu_cfd=None) -> dict:
     cores = os.cpu_count() or 1
+    parity = None
     scratch = args.scratch or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
     with tempfile.TemporaryDirectory(dir=scratch) as tmp:
         issl_path = os.path.join(tmp, "index.issl")
         dev.write_issl(issl_path)
         sample = guides[:n_sample]
         if reference_exe():
-            t, t_load, _ = time_reference(issl_path, sample, args.max_dist, args.threshold, args.method, tmp)
+            t, t_load, ref_stdout = time_reference(issl_path, sample, args.max_dist, args.threshold, args.method, tmp)
             kind = "reference"
+            if gpu_mit is not None and args.method in ("and", "or", "avg"):
+                ours = fmt_lines(sample, gpu_mit[:n_sample], gpu_cfd[:n_sample]).splitlines()
+                theirs = ref_stdout.splitlines()
+                same = sum(a == b for a, b in zip(ours, theirs))
+                parity = f"{same}/{len(theirs)} output lines byte-identical to the reference's stdout at full index size"
             note = (f"oracle/_ref/isslScoreOfftargets (unmodified reference, g++ -O3 -fopenmp -mpopcnt) on the same index "
                     f"written as a {os.path.getsize(issl_path) / 1e9:.1f} GB .issl, first {n_sample} guides of the batch, "
                     f"OpenMP default threads = {cores} cores; scoring {t:.1f} s = wall minus {t_load:.1f} s index load")
@@ -209,7 +224,10 @@ def cpu_baseline(dev, guides: np.ndarray, args, n_sample: int) -> dict:
             t = time_port(issl_path, sample, args.max_dist, args.threshold, args.method)
             kind = "port"
             note = f"oracle C port (oracle/issl_oracle.c), first {n_sample} guides, {cores} OpenMP threads, {t:.1f} s"
-    return {"value": n_sample / t, "unit": "guides/s", "cores": cores, "kind": kind, "sample": note}
+    out = {"value": n_sample / t, "unit": "guides/s", "cores": cores, "kind": kind, "sample": note}
+    if parity:
+        out["parity"] = parity
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -234,6 +252,7 @@ def main() -> int:
         import torch.distributed as dist
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
+    os.environ["ISSL_MAX_GROUP"] = str(args.max_group)
     t_build = time.perf_counter()
     dev = cb.Device.synthetic(local_rank, args.layout, seed=1, uniform_sites=args.sites, families=args.families,
                               family_size=args.family_size, max_sub_rate=0.15, seq_length=20, slice_width=args.slice_width)
@@ -247,6 +266,7 @@ def main() -> int:
     config = {"workload": workload, "sites": info["offtargetsCount"], "guides_per_gpu": args.guides,
               "global_guides": args.guides * world, "method": args.method, "max_dist": args.max_dist,
               "threshold": args.threshold, "slice_width": args.slice_width, "hbm_layout": layout_name,
+              "max_group": args.max_group,
               "index_hbm_gb": round(info["hbm_bytes"] / 1e9, 2), "index_build_s": round(t_build, 2),
               "parallelism": f"replicated index, guides partitioned x{world}, no collective",
               "l2": "inputs larger than L2 (each step streams ~45 MB of slice lists per guide)"}
@@ -301,7 +321,7 @@ def main() -> int:
 
     for _ in range(args.warmup):
         step_device()
-    scan_ms, scan_launches, launches, candidates, hits = 0.0, 0, 0, 0, 0
+    scan_ms, scan_launches, launches, candidates, hits, streamed = 0.0, 0, 0, 0, 0, 0
     barrier()
     with ClockSampler(local_rank) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,7 +330,7 @@ def main() -> int:
             step_device()
             st = dev.stats
             scan_ms += st["scan_ms"]; scan_launches += st["scan_launches"]; launches += st["launches"]
-            candidates += st["candidates"]; hits += st["hits"]
+            candidates += st["candidates"]; hits += st["hits"]; streamed += st["streamed"]
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -356,9 +376,23 @@ def main() -> int:
                 "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_candidate": bpc, "candidates_per_launch": candidates / max(scan_launches, 1),
                 "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": scan_ms / ms_total,
-                "traffic": (tpc * candidates / max(scan_launches, 1)) if tpc else None,
-                "traffic_source": "profiles/scan_traffic.json (ncu --set full dram bytes per candidate x candidates)" if tpc else None,
+                "traffic": (tpc * streamed / max(scan_launches, 1)) if tpc else None,
+                "traffic_source": ("profiles/scan_traffic.json: ncu --set full dram bytes per list entry streamed x entries "
+                                   "streamed per launch (each chunk is read once per guide group)") if tpc else None,
                 "frac_of_nominal_8TBps": achieved / 8000.0}
+    # With list reuse (max_group > 1) a chunk read from HBM once serves up to 8 guides, so the figure above --
+    # algorithmic bytes of the reference's per-guide walk over time -- legitimately exceeds the HBM peak
+    # (SURVEY.md 8d).  What then bounds the kernel is the XU pipe: one POPC per (guide, candidate) pair at
+    # 16 lanes/clk/SM (measured: profiles/).  Both views are reported.
+    clk = clocks.summary()
+    sm_hz = (clk["sm_mhz"] or 1965.0) * 1e6
+    pairs_per_s = candidates / max(scan_launches, 1) / (per_launch_ms / 1e3)
+    streamed_gbs = bpc * streamed / max(scan_launches, 1) / (per_launch_ms / 1e3) / 1e9
+    roofline.update({"reuse": candidates / max(streamed, 1), "streamed_gbs": streamed_gbs,
+                     "streamed_frac_of_hbm_peak": streamed_gbs / peak,
+                     "pipe_bound": {"pipe": "xu (POPC, 16 lanes/clk/SM x 148 SMs)", "achieved_pairs_per_s": pairs_per_s,
+                                    "peak_pairs_per_s": 148 * 16 * sm_hz, "frac": pairs_per_s / (148 * 16 * sm_hz),
+                                    "sm_mhz_used": sm_hz / 1e6}})
 
     result = {"metric": "guides scored/sec (MIT+CFD, <=4 mm)", "value": value, "unit": "guides/s", "n_gpus": world,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -374,7 +408,7 @@ def main() -> int:
             n_sample = args.cpu_guides or min(n, 100 * (os.cpu_count() or 1))
             for t in (d_guides, d_mit, d_cfd):
                 del t
-            result["cpu_baseline"] = cpu_baseline(dev, guides, args, n_sample)
+            result["cpu_baseline"] = cpu_baseline(dev, guides, args, n_sample, hm, hc)
         except Exception as e:   # the baseline must not take the GPU number down with it
             result["cpu_baseline"] = {"value": None, "unit": "guides/s", "cores": os.cpu_count(), "kind": "reference",
                                       "sample": f"failed: {e}"}

@@ -86,6 +86,7 @@ struct issl_device {
     std::vector<cudaEvent_t> evPool;
     issl_stats stats{};
     uint32_t maxBatch = 1u << 20;
+    uint32_t maxGroup = kBigGroup;   // ISSL_MAX_GROUP: 32 bit-sliced blocks + register groups (default), 8/4/2 register groups only, 1 no list reuse
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -221,6 +222,10 @@ static int new_device(int cuda_device, issl_device **out)
     if (const char *e = getenv("ISSL_BATCH")) {
         const long v = atol(e);
         if (v > 0 && v <= (1 << 24)) d->maxBatch = (uint32_t)v;
+    }
+    if (const char *e = getenv("ISSL_MAX_GROUP")) {
+        const long v = atol(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&d->hCounters, 8 * sizeof(unsigned long long));
@@ -638,9 +643,11 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         chunk64 = std::min<uint64_t>(chunk64, 1ull << 30);
         const uint32_t chunk = (uint32_t)chunk64;
 
+        uint32_t maxGroup = d->maxGroup;
+        if (maxGroup > kMaxGroup && !(d->layout == ISSL_LAYOUT_RES32 && maxDist <= 4)) maxGroup = kMaxGroup;
         CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
         k_group_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
-                                                             d->pairCounts.as<uint32_t>(), dc + 4);
+                                                             maxGroup, d->pairCounts.as<uint32_t>(), dc + 4);
         CK(cudaMemsetAsync(d->pairCounts.as<uint32_t>() + pairs, 0, 4, st));
         tb = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
@@ -653,7 +660,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         d->stats.streamed += d->hCounters[4];
         CKR(d->items.ensure((size_t)nItems * sizeof(ScanItem)));
         k_group_fill<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
-                                                            d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
+                                                            maxGroup, d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
         d->stats.launches += 4;
 
         // K1 (re-run with a larger survivor buffer if it overflowed)

@@ -46,7 +46,9 @@ struct ScanItem {
     uint32_t count;
     uint32_t groupStart;  // index of the group's first member in the list-sorted guide index array
 };
-constexpr int kMaxGroup = 8;
+constexpr int kMaxGroup = 8;       // largest group of the POPC path (guides held in registers)
+constexpr int kBigGroup = 32;      // group of the bit-sliced path (one bit per guide in every word)
+constexpr int kBigGroupMin = 14;   // a remainder of at least this many guides still gets a bit-sliced block
 
 __constant__ double c_cfdPos[320];
 __constant__ double c_cfdPam[16];
@@ -290,11 +292,125 @@ __device__ __forceinline__ void scan_body(const ScanArgs &a, const ScanItem &it)
     }
 }
 
+// Bit-sliced path (kRes32, maxDist <= 4, groups of 9..32 guides): no POPC at all.
+//
+// Every 32-bit word holds one bit per GUIDE of the group.  For each pair of adjacent residual
+// bases (a nibble of the candidate, 8 nibbles) a 16-entry shared-memory table gives, for the 16
+// possible nibble values, the two words "guide j differs from this base" -- 1 KB per group, built
+// once per scan item.  A thread handles one candidate at a time: 8 conflict-free LDS.64 (16
+// entries x 8 B = one bank row, equal entries broadcast) yield the 16 per-base mismatch words, a
+// carry-save adder tree (11 full adders = 22 LOP3) counts them per bit lane, and 4 more LOP3
+// give the lanes whose count is <= 4.  24 + 16 ALU-pipe instructions test 32 (guide, candidate)
+// pairs, against 32 POPC (XU pipe, 16 lanes/clk) + 80 ALU for the same pairs on the register path.
+// The accept word is exact for maxDist = 4 and a superset for maxDist < 4; survivors are re-tested.
+struct BitSliceTable { uint2 e[8][16]; };
+
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
+{
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
+}
+
+__device__ __forceinline__ uint32_t accept_le4(const BitSliceTable &tb, uint32_t c)
+{
+    uint32_t f[16];
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const uint2 e = tb.e[p][(c >> (4 * p)) & 15u];
+        f[2 * p] = e.x; f[2 * p + 1] = e.y;
+    }
+    uint32_t s0, s1, s2, s3, s4, k0, k1, k2, k3, k4, k5, k6, t0, t1, u0, u1, q0, q1, q2, m;
+    full_add(f[0], f[1], f[2], s0, k0);
+    full_add(f[3], f[4], f[5], s1, k1);
+    full_add(f[6], f[7], f[8], s2, k2);
+    full_add(f[9], f[10], f[11], s3, k3);
+    full_add(f[12], f[13], f[14], s4, k4);
+    full_add(s0, s1, s2, t0, k5);          // weight-1 bits left: t0, t1
+    full_add(s3, s4, f[15], t1, k6);
+    full_add(k0, k1, k2, u0, q0);          // weight 2
+    full_add(k3, k4, k5, u1, q1);
+    full_add(u0, u1, k6, m, q2);           // weight-2 bit left: m; weight-4 bits: q0, q1, q2
+    // count = t0 + t1 + 2 m + 4 (q0 + q1 + q2) >= 5  <=>  two of q set, or one q set and any of t0, t1, m
+    const uint32_t reject = ((q0 & q1) | (q2 & (q0 ^ q1))) | ((q0 | q1 | q2) & (t0 | t1 | m));
+    return ~reject;
+}
+
+__device__ __noinline__ void scan_emit32(const ScanArgs &a, uint32_t slice, uint32_t groupStart, uint32_t accept,
+                                         uint32_t residual, uint64_t pos)
+{
+    const uint32_t off = a.iv.sliceWidth * slice, kb = a.iv.knownBits;
+    while (accept) {
+        const uint32_t j = __ffs(accept) - 1;
+        accept &= accept - 1;
+        const uint32_t guide = a.sortedGuide[groupStart + j];
+        const uint64_t g = a.guides[guide];
+        const uint64_t site = insert_bits(residual, off, kb, (g >> off) & ((1ull << kb) - 1ull));
+        if (distance64(site ^ g) <= a.maxDist) emit_hit(a, g, site, slice, guide, pos);
+    }
+}
+
+__device__ __forceinline__ void scan_body_bitsliced(const ScanArgs &a, const ScanItem &it, BitSliceTable &tb, uint32_t *gres)
+{
+    const uint32_t slice = (uint32_t)(it.p0Slice >> 56);
+    const uint32_t groupSize = (uint32_t)(it.p0Slice >> 40) & 0xFFu;
+    const uint64_t p0 = it.p0Slice & ((1ull << 40) - 1ull);
+    const uint32_t n = it.count, tid = threadIdx.x;
+    const uint32_t off = a.iv.sliceWidth * slice, kb = a.iv.knownBits;
+
+    if (tid < 32) gres[tid] = tid < groupSize ? (uint32_t)remove_bits(a.guides[a.sortedGuide[it.groupStart + tid]], off, kb) : 0u;
+    __syncthreads();
+    if (tid < 128) {
+        const uint32_t p = tid >> 4, nib = tid & 15u;
+        uint32_t w0 = 0, w1 = 0;
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint32_t gn = (gres[j] >> (4 * p)) & 15u;
+            const bool unused = j >= groupSize;            // unused lanes always mismatch, so they never accept
+            w0 |= (uint32_t)(unused || ((gn & 3u) != (nib & 3u))) << j;
+            w1 |= (uint32_t)(unused || ((gn >> 2) != (nib >> 2))) << j;
+        }
+        tb.e[p][nib] = make_uint2(w0, w1);
+    }
+    __syncthreads();
+
+    const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.res32 + p0);
+    const uint32_t nvec = n >> 2;
+    auto vec = [&](const uint4 &r, uint64_t pos) {
+        const uint32_t a0 = accept_le4(tb, r.x), a1 = accept_le4(tb, r.y), a2 = accept_le4(tb, r.z), a3 = accept_le4(tb, r.w);
+        if (a0 | a1 | a2 | a3) {
+            if (a0) scan_emit32(a, slice, it.groupStart, a0, r.x, pos);
+            if (a1) scan_emit32(a, slice, it.groupStart, a1, r.y, pos + 1);
+            if (a2) scan_emit32(a, slice, it.groupStart, a2, r.z, pos + 2);
+            if (a3) scan_emit32(a, slice, it.groupStart, a3, r.w, pos + 3);
+        }
+    };
+    uint32_t i = tid;
+    for (; i + kScanThreads < nvec; i += 2 * kScanThreads) {
+        const uint4 r0 = __ldcs(v4 + i), r1 = __ldcs(v4 + i + kScanThreads);
+        vec(r0, p0 + 4ull * i);
+        vec(r1, p0 + 4ull * (i + kScanThreads));
+    }
+    for (; i < nvec; i += kScanThreads) {
+        const uint4 r = __ldcs(v4 + i);
+        vec(r, p0 + 4ull * i);
+    }
+    if (tid < (n & 3u)) {
+        const uint64_t pos = p0 + 4ull * nvec + tid;
+        const uint32_t r = a.iv.res32[pos];
+        const uint32_t acc = accept_le4(tb, r);
+        if (acc) scan_emit32(a, slice, it.groupStart, acc, r, pos);
+    }
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanArgs a)
 {
     const ScanItem it = a.items[blockIdx.x];
     const uint32_t groupSize = (uint32_t)(it.p0Slice >> 40) & 0xFFu;
+    if (LAYOUT == kRes32) {
+        __shared__ BitSliceTable tb;
+        __shared__ uint32_t gres[32];
+        if (groupSize > kMaxGroup) { scan_body_bitsliced(a, it, tb, gres); return; }
+    }
     if (groupSize > 4) scan_body<LAYOUT, 8>(a, it);
     else if (groupSize > 2) scan_body<LAYOUT, 4>(a, it);
     else if (groupSize == 2) scan_body<LAYOUT, 2>(a, it);
@@ -338,8 +454,16 @@ __global__ void k_pair_keys(IndexView iv, const uint64_t *guides, const uint8_t 
 // Group shape of sorted pair i: runs of equal list id are cut into groups of 8; a remainder r is
 // cut as 7..8 -> one group, 5..6 -> 4 + (r - 4), 1..4 -> one group.  Returns the group size when i
 // is the first member of a group, else 0.
-__device__ __forceinline__ uint32_t group_head_size(uint32_t rank, uint32_t runLen)
+__device__ __forceinline__ uint32_t group_head_size(uint32_t rank, uint32_t runLen, uint32_t maxGroup)
 {
+    if (maxGroup >= (uint32_t)kBigGroup) {   // bit-sliced blocks of up to 32 first
+        const uint32_t rem = runLen % kBigGroup;
+        const uint32_t bigEnd = runLen - rem + (rem >= (uint32_t)kBigGroupMin ? rem : 0u);
+        if (rank < bigEnd) return (rank % kBigGroup) == 0 ? min((uint32_t)kBigGroup, bigEnd - rank) : 0u;
+        rank -= bigEnd; runLen -= bigEnd;
+    } else if (maxGroup < 8) {
+        return (rank % maxGroup) == 0 ? min(maxGroup, runLen - rank) : 0u;
+    }
     const uint32_t base = runLen & ~7u, r = runLen - base;
     if (rank < base) return (rank & 7u) == 0 ? 8u : 0u;
     const uint32_t q = rank - base;
@@ -360,7 +484,7 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *keys, uint32
 
 // pass 2: items per sorted pair (non-zero only at group heads)
 __global__ void k_group_count(IndexView iv, const uint32_t *sortedKeys, uint32_t nPairs, uint32_t nLists, uint32_t chunk,
-                              uint32_t *counts, unsigned long long *streamed)
+                              uint32_t maxGroup, uint32_t *counts, unsigned long long *streamed)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nPairs) return;
@@ -368,7 +492,7 @@ __global__ void k_group_count(IndexView iv, const uint32_t *sortedKeys, uint32_t
     const uint32_t key = sortedKeys[i];
     if (key < nLists) {
         const uint32_t lb = lower_bound_u32(sortedKeys, nPairs, key), ub = lower_bound_u32(sortedKeys, nPairs, key + 1);
-        if (group_head_size(i - lb, ub - lb)) {
+        if (group_head_size(i - lb, ub - lb, maxGroup)) {
             const uint64_t len = iv.listLen[key];
             c = (uint32_t)((len + chunk - 1) / chunk);
             atomicAdd(streamed, (unsigned long long)len);
@@ -379,14 +503,14 @@ __global__ void k_group_count(IndexView iv, const uint32_t *sortedKeys, uint32_t
 
 // pass 3: write the items of every group at its scanned offset
 __global__ void k_group_fill(IndexView iv, const uint32_t *sortedKeys, uint32_t nPairs, uint32_t nLists, uint32_t chunk,
-                             const uint32_t *offsets, ScanItem *items)
+                             uint32_t maxGroup, const uint32_t *offsets, ScanItem *items)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nPairs) return;
     const uint32_t key = sortedKeys[i];
     if (key >= nLists) return;
     const uint32_t lb = lower_bound_u32(sortedKeys, nPairs, key), ub = lower_bound_u32(sortedKeys, nPairs, key + 1);
-    const uint32_t size = group_head_size(i - lb, ub - lb);
+    const uint32_t size = group_head_size(i - lb, ub - lb, maxGroup);
     if (!size) return;
     const uint64_t len = iv.listLen[key], start = iv.listStart[key];
     const uint64_t slice = key / iv.sliceLimit;

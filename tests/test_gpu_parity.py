@@ -123,6 +123,48 @@ def test_fresh_inputs_against_oracle(seed, w, n_random, families, fsize):
     dev.close()
 
 
+@pytest.mark.parametrize("max_group", [1, 4, 8, 32])
+@pytest.mark.parametrize("w", [8, 10])
+def test_guide_groups_and_bitsliced_path(max_group, w):
+    """Many guides per slice list: exercises the register groups (2/4/8) and, for max_group 32, the
+    bit-sliced blocks of 9..32 guides; every grouping must give the oracle's exact answer."""
+    text = td.make_offtargets(31, n_random=60_000, n_families=30, family_size=400, max_sub_rate=0.12)
+    img = oracle.create_index(text, 20, w)
+    rng = np.random.default_rng(32)
+    roots = td.pack_guides(td.make_guides(33, text, n=40, frac_exact=1.0, frac_mut=0.0))
+    guides = []
+    for r in roots:                                   # 75 variants per root with 0-3 substitutions
+        for _ in range(75):
+            g = int(r)
+            for pos in rng.choice(20, size=int(rng.integers(0, 4)), replace=False):
+                g ^= int(rng.integers(1, 4)) << (2 * int(pos))
+            guides.append(g)
+    guides = np.array(guides, dtype=np.uint64)
+    os.environ["ISSL_MAX_GROUP"] = str(max_group)
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, "auto")
+    finally:
+        del os.environ["ISSL_MAX_GROUP"]
+    for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("avg", 50, 3), ("or", 0, 0), ("and", 0, 5)):
+        want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
+        mit, cfd = dev.score(guides, md, thr, method)
+        assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (max_group, method, thr, md)
+        assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (max_group, method, thr, md)
+        if thr == 0:
+            st = dev.stats
+            assert st["candidates"] == int(want["candidates"].sum())
+            if max_group == 1:
+                assert st["streamed"] == st["candidates"]
+            elif max_group == 32 and md <= 4:
+                assert st["candidates"] > 4 * st["streamed"]          # blocks of up to 32 guides share a chunk
+            else:
+                assert st["candidates"] > 2 * st["streamed"]
+    _, _, hits = dev.score_hits(guides, 4, 0, "and")
+    want = oracle.score(img, guides, 4, 0, "and", threads=1, want_hits=True)["hits"]
+    assert np.array_equal(hits, np.stack([want[k].astype(np.int64) for k in ("guide", "id", "dist", "occ")], axis=1))
+    dev.close()
+
+
 def test_edge_cases():
     case = golden_case("w8_families")
     dev = device_for("w8_families", "auto")
