@@ -334,10 +334,8 @@ def main() -> int:
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t_ms.item())
+    from crackling_b200.sharding import max_over_ranks
+    ms_total_max = max_over_ranks(ms_total, dist, "cuda")
     ms_per_step = ms_total_max / args.steps
     value = args.guides * world / (ms_per_step / 1e3)
 
@@ -354,11 +352,9 @@ def main() -> int:
         dev.score_into(hg, args.max_dist, args.threshold, args.method, hm, hc)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.barrier()
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = args.guides * world * args.steps / float(t_e.item())
+    e2e_value = args.guides * world * args.steps / max_over_ranks(e2e_s, dist, "cuda")
     assert np.array_equal(hm, d_mit.cpu().numpy()) and np.array_equal(hc, d_cfd.cpu().numpy()), "host and device paths disagree"
 
     if rank != 0:
