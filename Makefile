@@ -5,7 +5,7 @@
 #   make oracle   -> oracle/_build/libissl_oracle.so
 #   make ref      -> oracle/_ref/* (the unmodified reference, compiled from /root/reference)
 NVCC      ?= /usr/local/cuda/bin/nvcc
-CXX       ?= g++
+CXX       := g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 CSRC      := crackling_b200/csrc
 LIBDIR    := crackling_b200/lib
@@ -27,7 +27,7 @@ $(LIBDIR)/libissl_cuda.so: $(LIBDIR)/issl_host.o $(LIBDIR)/issl_device.o
 
 bin/isslScoreOfftargets: $(CSRC)/isslScoreOfftargets.cpp include/issl_cuda.h $(LIBDIR)/libissl_cuda.so
 	@mkdir -p bin
-	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lissl_cuda -pthread '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
+	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lissl_cuda -pthread '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
 
 oracle:
 	$(MAKE) -C oracle oracle

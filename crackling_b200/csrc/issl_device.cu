@@ -59,6 +59,19 @@ struct DBuf {
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// host copy into a pinned staging buffer with all cores (a single memcpy stream tops out near 10 GB/s,
+// well below what PCIe Gen5 can take)
+inline void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kSlice = 1u << 20;
+    const long slices = (long)((bytes + kSlice - 1) / kSlice);
+#pragma omp parallel for schedule(static) if (slices > 4)
+    for (long i = 0; i < slices; i++) {
+        const size_t o = (size_t)i * kSlice, n = std::min(kSlice, bytes - o);
+        memcpy(static_cast<uint8_t *>(dst) + o, static_cast<const uint8_t *>(src) + o, n);
+    }
+}
+
 }  // namespace
 
 struct issl_device {
@@ -82,7 +95,7 @@ struct issl_device {
     DBuf guides, totMit, totCfd, done, pairKeys, pairVals, pairKeysSorted, pairValsSorted, pairCounts, pairOffsets, items, keysA, keysB, sortTemp, scanTemp,
         contribMit, contribCfd, counters, outMit, outCfd, hitId, hitDist, hitOcc, scoredEnd, segBegin;
     unsigned long long *hCounters = nullptr;   // pinned: [0] total candidates, [1] hit count, [2] items, [3] done
-    uint64_t hitCap = 0;
+    uint64_t hitCap = 0, hitCapAuto = 0;
     std::vector<cudaEvent_t> evPool;
     issl_stats stats{};
     uint32_t maxBatch = 1u << 20;
@@ -276,7 +289,7 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
 
     const uint64_t N = ix->info.offtargetsCount, S = ix->info.sliceCount;
     // signatures first (the re-layout kernel gathers them)
-    constexpr size_t kStage = 64ull << 20;
+    constexpr size_t kStage = 256ull << 20;
     uint8_t *stage[2] = {nullptr, nullptr};
     cudaEvent_t freeEv[2] = {nullptr, nullptr};
     DBuf dstage[2];
@@ -311,7 +324,7 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
     for (uint64_t o = 0; o < N * 8; o += kStage) {
         const size_t n = (size_t)std::min<uint64_t>(kStage, N * 8 - o);
         CKF(cudaEventSynchronize(freeEv[buf]));
-        memcpy(stage[buf], reinterpret_cast<const uint8_t *>(ix->offtargets) + o, n);
+        parallel_copy(stage[buf], reinterpret_cast<const uint8_t *>(ix->offtargets) + o, n);
         CKF(cudaMemcpyAsync(d->sig.as<uint8_t>() + o, stage[buf], n, cudaMemcpyHostToDevice, d->stream));
         CKF(cudaEventRecord(freeEv[buf], d->stream));
         buf ^= 1;
@@ -323,7 +336,7 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
             const uint64_t n = std::min<uint64_t>(chunkEntries, (s + 1) * N - q0);
             const int hasPrev = q0 > s * N;
             CKF(cudaEventSynchronize(freeEv[buf]));
-            memcpy(stage[buf], ix->entries + q0 - hasPrev, (n + hasPrev) * 8);
+            parallel_copy(stage[buf], ix->entries + q0 - hasPrev, (n + hasPrev) * 8);
             CKF(cudaMemcpyAsync(dstage[buf].p, stage[buf], (n + hasPrev) * 8, cudaMemcpyHostToDevice, d->stream));
             RelayoutArgs a;
             a.iv = d->iv; a.entries = dstage[buf].as<uint64_t>(); a.filePrefix = d->filePrefix.as<uint64_t>();
@@ -666,8 +679,9 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         // K1 (re-run with a larger survivor buffer if it overflowed)
         uint64_t nHits = 0;
         for (;;) {
-            if (d->hitCap == 0) {
-                d->hitCap = 1ull << 22;
+            const uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, 384ull * n), 1ull << 28);
+            if (d->hitCap < wantCap && d->hitCap == d->hitCapAuto) {   // first sizing for this batch size (uniform genomes: ~275 survivors per guide)
+                d->hitCap = d->hitCapAuto = wantCap;
                 CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
             }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));

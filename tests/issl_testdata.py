@@ -85,3 +85,26 @@ def pack_guides(guide_file: bytes, seq_length: int = 20) -> np.ndarray:
     codes = lut[arr]
     shifts = (np.arange(seq_length, dtype=np.uint64) * np.uint64(2))
     return np.bitwise_or.reduce(codes << shifts, axis=1).astype(np.uint64) if n else np.zeros(0, dtype=np.uint64)
+
+
+def make_genome(seed: int, lengths=(4_800_000, 200_000)) -> list[bytes]:
+    """i.i.d. uniform ACGT records (config 1 of BASELINE.json: a 5 Mbp bacterial-size genome; two
+    records because the reference extractor fails on a single-record FASTA)."""
+    rng = np.random.default_rng(seed)
+    return [BASES[rng.integers(0, 4, size=n, dtype=np.uint8)].tobytes() for n in lengths]
+
+
+def write_fasta(path, records: list[bytes], width: int = 70) -> None:
+    with open(path, "wb") as f:
+        for k, rec in enumerate(records):
+            f.write(b">record%d\n" % k)
+            for o in range(0, len(rec), width):
+                f.write(rec[o:o + width] + b"\n")
+
+
+def sample_guides(seed: int, pool: np.ndarray, n: int) -> bytes:
+    """n guides drawn without replacement from a pool of 20-mers (rows of letters)."""
+    rng = np.random.default_rng(seed)
+    pick = rng.choice(pool.shape[0], size=n, replace=False)
+    lines = np.concatenate([pool[pick], np.full((n, 1), ord("\n"), dtype=np.uint8)], axis=1)
+    return lines.tobytes()

@@ -100,6 +100,24 @@ def test_host_program_stdout_byte_identical(name, tmp_path):
         assert p.stdout.decode() == run["stdout"]
 
 
+def test_host_program_on_several_gpus(tmp_path):
+    """Index replicated per GPU, guides split into contiguous ranges, output in input order."""
+    n = cb.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    case = golden_case("w8_families")
+    (tmp_path / "i.issl").write_bytes(case.issl)
+    (tmp_path / "g.txt").write_bytes(case.guides)
+    for run in case.expected["runs"][::17]:
+        env = dict(os.environ, ISSL_GPUS=str(n), ISSL_TIMING="1")
+        p = subprocess.run([str(cb.cli_path()), str(tmp_path / "i.issl"), str(tmp_path / "g.txt"), str(run["maxDist"]),
+                            str(run["threshold"]), run["method"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.decode() == run["stdout"]
+        if run["method"] != "bogus":
+            assert p.stderr.decode().count("[issl] gpu ") == n
+
+
 @pytest.mark.parametrize("seed,w,n_random,families,fsize", [(11, 8, 200_000, 40, 300), (12, 10, 120_000, 20, 200),
                                                             (13, 4, 20_000, 10, 100), (14, 8, 1, 0, 0)])
 def test_fresh_inputs_against_oracle(seed, w, n_random, families, fsize):
