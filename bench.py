@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--threshold", type=float, default=THRESHOLD)
     ap.add_argument("--families", type=int, default=0)
     ap.add_argument("--family-size", type=int, default=0)
+    ap.add_argument("--family-guides", type=float, default=0.0,
+                    help="fraction of guides drawn from the planted families' roots (0-2 substitutions), config 4")
     ap.add_argument("--cpu-guides", type=int, default=0, help="guides in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-group", type=int, default=32, choices=[1, 2, 4, 8, 32],
@@ -74,13 +76,42 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_guides(dev, n: int, seed: int) -> np.ndarray:
-    """90 % of the guides are sites of the index itself, 10 % uniform random 20-mers."""
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser, same as mix64() in csrc/issl_kernels.cuh."""
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def family_roots(seed: int, families: int) -> np.ndarray:
+    """Roots of the planted near-repeat families, recomputed as k_synth_sites derives them."""
+    f = np.arange(families, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        def rng3(a):
+            return _mix64(_mix64(_mix64(np.full(families, seed, dtype=np.uint64)) ^ np.uint64(a)) ^ (f * np.uint64(0xD6E8FEB86659FD93)))
+        root = (rng3(3) & np.uint64((1 << 40) - 1) & ~np.uint64(3)) | (rng3(4) % np.uint64(3))
+    return root
+
+
+def make_guides(dev, n: int, seed: int, families: int = 0, family_frac: float = 0.0, index_seed: int = 1) -> np.ndarray:
+    """90 % of the guides are sites of the index itself, 10 % uniform random 20-mers (SURVEY 8d, C2);
+    with family_frac > 0 that fraction is drawn from the planted families instead (config 4)."""
     rng = np.random.default_rng(seed)
-    n_own = (n * 9) // 10
+    n_fam = int(n * family_frac) if families else 0
+    n_own = ((n - n_fam) * 9) // 10
     own = dev.read_sites(rng.integers(0, dev.info["offtargetsCount"], n_own).astype(np.uint64))
-    rnd = rng.integers(0, 1 << 40, n - n_own, dtype=np.uint64)
-    g = np.concatenate([own, rnd])
+    rnd = rng.integers(0, 1 << 40, n - n_fam - n_own, dtype=np.uint64)
+    parts = [own, rnd]
+    if n_fam:
+        fam = family_roots(index_seed, families)[rng.integers(0, families, n_fam)].copy()
+        for _ in range(2):                                   # up to two substitutions per guide
+            pos = rng.integers(0, 20, n_fam).astype(np.uint64) * np.uint64(2)
+            sub = rng.integers(0, 4, n_fam).astype(np.uint64)           # 0 = no change
+            fam ^= sub << pos
+        parts.append(fam)
+    g = np.concatenate(parts)
     rng.shuffle(g)
     return g
 
@@ -267,13 +298,14 @@ def main() -> int:
     t_build = time.perf_counter() - t_build
     info = dev.info
     layout_name = {1: "res32", 2: "sig64", 3: "gather"}[info["layout"]]
-    guides = make_guides(dev, args.guides, seed=2 + rank)
+    guides = make_guides(dev, args.guides, seed=2 + rank, families=args.families, family_frac=args.family_guides)
     workload = (f"synthetic human-scale index: {args.sites} uniform NGG sites -> {info['offtargetsCount']} distinct, "
                 f"l=20 w={args.slice_width}, {args.guides} guides/GPU (90% index sites, 10% random), method {args.method}, "
                 f"maxDist {args.max_dist}, threshold {args.threshold:g}")
     config = {"workload": workload, "sites": info["offtargetsCount"], "guides_per_gpu": args.guides,
               "global_guides": args.guides * world, "method": args.method, "max_dist": args.max_dist,
               "threshold": args.threshold, "slice_width": args.slice_width, "hbm_layout": layout_name,
+              "families": args.families, "family_size": args.family_size, "family_guides": args.family_guides,
               "max_group": args.max_group,
               "index_hbm_gb": round(info["hbm_bytes"] / 1e9, 2), "index_build_s": round(t_build, 2),
               "parallelism": f"replicated index, guides partitioned x{world}, no collective",

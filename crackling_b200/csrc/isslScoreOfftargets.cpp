@@ -174,7 +174,7 @@ int main(int argc, char **argv)
     // parallel chunks (glibc's %f is the slow part at millions of guides) and written sequentially.
     {
         const size_t L = info.seqLength;
-        const size_t chunkLines = 1 << 15;
+        const size_t chunkLines = 1 << 11;
         const size_t nChunks = (queryCount + chunkLines - 1) / chunkLines;
         std::vector<std::string> chunks(nChunks);
 #pragma omp parallel for schedule(dynamic, 1)

@@ -10,7 +10,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 GOLDEN = ROOT / "tests" / "golden"
-GOLDEN_CASES = sorted(p.name for p in GOLDEN.iterdir() if (p / "expected.json").exists())
+GOLDEN_CASES = sorted(p.name for p in GOLDEN.iterdir() if (p / "offtargets.txt").exists())
 
 
 def pytest_configure(config):

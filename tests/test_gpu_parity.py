@@ -267,3 +267,20 @@ def test_synthetic_index_is_what_the_reference_builder_would_write(w, layout, tm
     assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64))
     assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64))
     dev.close()
+
+
+def test_family_roots_match_the_device_generator(tmp_path):
+    """bench.py recomputes the planted families' roots on the host (config 4 guides)."""
+    import bench
+    dev = cb.Device.synthetic(0, "auto", seed=7, uniform_sites=2000, families=6, family_size=50, max_sub_rate=0.0)
+    dev.write_issl(tmp_path / "f.issl")
+    img = (tmp_path / "f.issl").read_bytes()
+    hd = oracle.header(img)
+    off = 48 + 16 * hd["scoresCount"]
+    sigs = np.frombuffer(img[off:off + 8 * hd["offtargetsCount"]], dtype=np.uint64)
+    ent = np.frombuffer(img[off + 8 * hd["offtargetsCount"] + 8 * hd["sliceCount"] * 256:], dtype=np.uint64)[:hd["offtargetsCount"]]
+    occ = dict(zip((ent & np.uint64(0xFFFFFFFF)).tolist(), (ent >> np.uint64(32)).tolist()))
+    for root in bench.family_roots(7, 6):
+        where = np.flatnonzero(sigs == root)
+        assert where.size == 1 and occ[int(where[0])] >= 50
+    dev.close()
