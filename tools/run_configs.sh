@@ -1,0 +1,22 @@
+#!/bin/bash
+# Runs the BASELINE.json configs beyond the headline one (config 2 = default bench.py) on one B200 and
+# collects one JSON line per run in gpurun_out/configs.jsonl.  Usage: bash tools/run_configs.sh
+out=gpurun_out/configs.jsonl; : > $out
+run() { echo "# $*" >&2; timeout 900 python bench.py --no-cpu-baseline "$@" >> $out 2>> gpurun_out/configs.err || echo "{\"failed\": \"$*\"}" >> $out; }
+# config 5: slice-width sweep and maxDist sweep on the human-scale genome
+run --slice-width 8 --max-dist 2 --steps 3 --warmup 1
+run --slice-width 8 --max-dist 3 --steps 3 --warmup 1
+run --slice-width 8 --max-dist 5 --steps 3 --warmup 1
+run --slice-width 10 --max-dist 3 --steps 3 --warmup 1
+run --slice-width 10 --max-dist 4 --steps 3 --warmup 1
+run --slice-width 4 --max-dist 4 --guides 10000 --steps 2 --warmup 1
+# config 4: repeat-rich mouse-scale genome (2.7 Gbp -> 506.25 M uniform sites + 2000 planted families of 5000 copies),
+# half of the guides from the families, thresholds 0 (full scan) and 75 (early exit)
+run --sites 506250000 --families 2000 --family-size 5000 --family-guides 0.5 --threshold 0 --steps 3 --warmup 1
+run --sites 506250000 --families 2000 --family-size 5000 --family-guides 0.5 --threshold 75 --steps 3 --warmup 1
+# layouts on the headline workload: the north-star's ids+gather layout and the 64-bit inline layout
+run --layout gather --guides 20000 --steps 2 --warmup 1
+run --layout sig64 --guides 20000 --steps 2 --warmup 1
+run --layout gather --guides 20000 --steps 2 --warmup 1 --max-group 1
+# config 3 flavour: 1 M guides in one call (internal batches), method and
+run --guides 1000000 --steps 1 --warmup 1
