@@ -1,6 +1,8 @@
 # Top-level build.  Products:
 #   crackling_b200/lib/libissl_cuda.so   C-ABI library (include/issl_cuda.h), sm_100a only
 #   bin/isslScoreOfftargets              drop-in host program (same CLI as the reference binary)
+#   bin/isslScoreServer                  resident scorer behind the same CLI (index stays in HBM between pages)
+#   bin/isslCreateIndex                  drop-in index builder (same CLI, byte-identical .issl)
 # Test infrastructure (never linked into the products):
 #   make oracle   -> oracle/_build/libissl_oracle.so
 #   make ref      -> oracle/_ref/* (the unmodified reference, compiled from /root/reference)
@@ -12,7 +14,7 @@ LIBDIR    := crackling_b200/lib
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-fopenmp,-Wall -Iinclude -I$(CSRC) --expt-relaxed-constexpr
 CXXFLAGS  := -O3 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Iinclude -I$(CSRC)
 
-all: $(LIBDIR)/libissl_cuda.so bin/isslScoreOfftargets
+all: $(LIBDIR)/libissl_cuda.so bin/isslScoreOfftargets bin/isslCreateIndex bin/isslScoreServer
 
 $(LIBDIR)/issl_host.o: $(CSRC)/issl_host.cpp $(CSRC)/issl_internal.h include/issl_cuda.h
 	@mkdir -p $(LIBDIR)
@@ -25,9 +27,19 @@ $(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_kernels.cuh $(CSRC)
 $(LIBDIR)/libissl_cuda.so: $(LIBDIR)/issl_host.o $(LIBDIR)/issl_device.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xcompiler -fopenmp -lgomp
 
-bin/isslScoreOfftargets: $(CSRC)/isslScoreOfftargets.cpp include/issl_cuda.h $(LIBDIR)/libissl_cuda.so
+HOSTHDR   := include/issl_cuda.h $(CSRC)/issl_hostcommon.h $(CSRC)/issl_wire.h
+
+bin/isslScoreOfftargets: $(CSRC)/isslScoreOfftargets.cpp $(HOSTHDR) $(LIBDIR)/libissl_cuda.so
 	@mkdir -p bin
-	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lissl_cuda -pthread '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
+	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Wextra -Iinclude -I$(CSRC) -o $@ $< -L$(LIBDIR) -lissl_cuda -pthread '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
+
+bin/isslScoreServer: $(CSRC)/isslScoreServer.cpp $(HOSTHDR) $(LIBDIR)/libissl_cuda.so
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -I$(CSRC) -o $@ $< -L$(LIBDIR) -lissl_cuda -pthread '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
+
+bin/isslCreateIndex: $(CSRC)/isslCreateIndex.cpp include/issl_cuda.h $(LIBDIR)/libissl_cuda.so
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lissl_cuda '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
 
 oracle:
 	$(MAKE) -C oracle oracle

@@ -424,7 +424,7 @@ def main() -> int:
     sm_hz = (clk["sm_mhz"] or 1965.0) * 1e6
     pairs_per_s = candidates / max(scan_launches, 1) / (per_launch_ms / 1e3)
     streamed_gbs = bpc * streamed / max(scan_launches, 1) / (per_launch_ms / 1e3) / 1e9
-    if args.max_group == 32 and layout_name == "res32" and args.max_dist <= 4:
+    if args.max_group == 32 and layout_name == "res32" and args.max_dist <= 7:
         # bit-sliced path: 40 ALU-pipe instructions (16 nibble extractions + 24 adder/threshold LOP3) per 32 pairs,
         # ALU pipe = 64 lanes/clk/SM  ->  51.2 pairs/clk/SM
         pipe, per_clk = "alu (bit-sliced: 1.25 ALU-pipe instr per pair at 64 lanes/clk/SM x 148 SMs)", 64 / 1.25

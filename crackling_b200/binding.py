@@ -10,6 +10,7 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 LIB = ROOT / "crackling_b200" / "lib" / "libissl_cuda.so"
 CLI = ROOT / "bin" / "isslScoreOfftargets"
+CREATE_CLI = ROOT / "bin" / "isslCreateIndex"
 
 METHODS = {"unknown": 0, "mit": 1, "cfd": 2, "and": 3, "or": 4, "avg": 5}
 LAYOUTS = {"auto": 0, "res32": 1, "sig64": 2, "gather": 3}
@@ -57,6 +58,10 @@ def cli_path() -> pathlib.Path:
     return CLI
 
 
+def create_cli_path() -> pathlib.Path:
+    return CREATE_CLI
+
+
 def lib() -> C.CDLL:
     """Loads the in-tree shared library; fails loudly when it has not been built."""
     global _lib
@@ -77,6 +82,7 @@ def lib() -> C.CDLL:
             "issl_device_count": ([], i),
             "issl_device_create": ([vp, i, i, pp], i),
             "issl_device_create_synthetic": ([i, i, u64, u64, C.c_uint32, C.c_uint32, d, C.c_uint32, C.c_uint32, pp], i),
+            "issl_device_create_from_text": ([C.c_char_p, sz, C.c_uint32, C.c_uint32, i, i, pp], i),
             "issl_device_get_info": ([vp, C.POINTER(_DeviceInfo)], i),
             "issl_device_destroy": ([vp], None),
             "issl_device_write_issl": ([vp, C.c_char_p], i),
@@ -196,6 +202,15 @@ class Device:
         lay = LAYOUTS[layout] if isinstance(layout, str) else int(layout)
         _check(lib().issl_device_create_synthetic(cuda_device, lay, seed, uniform_sites, families, family_size,
                                                   float(max_sub_rate), seq_length, slice_width, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_text(cls, text: bytes, seq_length: int = 20, slice_width: int = 8, cuda_device: int = 0,
+                  layout: str | int = "auto") -> "Device":
+        """issl_device_create_from_text: the device-side isslCreateIndex."""
+        h = C.c_void_p()
+        lay = LAYOUTS[layout] if isinstance(layout, str) else int(layout)
+        _check(lib().issl_device_create_from_text(text, len(text), seq_length, slice_width, cuda_device, lay, C.byref(h)))
         return cls(h)
 
     @property

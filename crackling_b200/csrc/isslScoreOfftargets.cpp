@@ -13,59 +13,101 @@
 //   ISSL_DEVICES=a,b,..  explicit CUDA device ordinals (overrides ISSL_GPUS)
 //   ISSL_LAYOUT=res32|sig64|gather   HBM layout of the slice lists (default: automatic)
 //   ISSL_TIMING=1        phase timings on stderr
+//   ISSL_SERVER=<socket> score through a resident isslScoreServer on that unix socket (the index stays in HBM
+//                        between invocations -- the pipeline starts this program once per page of guides,
+//                        Crackling.py:737-778); ISSL_SERVER_AUTOSTART=1 starts the server when nobody listens
+//                        (ISSL_SERVER_LOG=<file> receives its stderr).  Output is the same either way.
 #include <algorithm>
-#include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <string>
 #include <sys/stat.h>
-#include <thread>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <vector>
 
 #include "issl_cuda.h"
+#include "issl_hostcommon.h"
+#include "issl_wire.h"
 
 namespace {
 
-double now_s()
+using issl_host::now_s;
+
+// Starts bin/isslScoreServer (next to this executable) detached from the caller's terminal and pipes.
+bool spawn_server(const char *sockPath)
 {
-    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    char self[PATH_MAX];
+    const ssize_t n = readlink("/proc/self/exe", self, sizeof self - 1);
+    if (n <= 0) return false;
+    self[n] = 0;
+    std::string exe(self);
+    exe = exe.substr(0, exe.rfind('/') + 1) + "isslScoreServer";
+    if (access(exe.c_str(), X_OK) != 0) return false;
+    const pid_t pid = fork();
+    if (pid < 0) return false;
+    if (pid == 0) {
+        setsid();
+        if (fork() != 0) _exit(0);   // grandchild is re-parented to init: nobody has to wait for it
+        const int nul = open("/dev/null", O_RDWR);
+        const char *logPath = getenv("ISSL_SERVER_LOG");
+        const int log = logPath ? open(logPath, O_WRONLY | O_CREAT | O_APPEND, 0600) : -1;
+        dup2(nul, 0); dup2(nul, 1); dup2(log >= 0 ? log : nul, 2);   // never hold the caller's stdout redirect open
+        for (int fd = 3; fd < 1024; fd++) close(fd);
+        execl(exe.c_str(), exe.c_str(), sockPath, (char *)nullptr);
+        _exit(127);
+    }
+    int status;
+    waitpid(pid, &status, 0);
+    return true;
 }
 
-std::vector<int> pick_devices(size_t nGuides)
+// Scores through the resident server.  Returns 0 on success, 1 when the server answered with an error
+// (message already on stderr), -1 when no server could be reached (the caller then scores in-process).
+int score_remote(const char *sockPath, const char *indexPath, const std::vector<uint64_t> &guides, int maxDist, double threshold,
+                 int method, std::vector<double> &mit, std::vector<double> &cfd, bool timing)
 {
-    std::vector<int> devs;
-    if (const char *e = getenv("ISSL_DEVICES")) {
-        for (const char *p = e; *p;) {
-            char *end;
-            const long v = strtol(p, &end, 10);
-            if (end == p) break;
-            devs.push_back((int)v);
-            p = (*end == ',') ? end + 1 : end;
+    using namespace issl_wire;
+    int fd = connect_to(sockPath);
+    if (fd < 0 && getenv("ISSL_SERVER_AUTOSTART") && atoi(getenv("ISSL_SERVER_AUTOSTART")) != 0 && spawn_server(sockPath)) {
+        for (int tries = 0; tries < 600 && fd < 0; tries++) {   // the server's first cudaInit can take a while
+            usleep(50 * 1000);
+            fd = connect_to(sockPath);
         }
-        if (!devs.empty()) return devs;
     }
-    int want = issl_device_count();
-    if (const char *e = getenv("ISSL_GPUS")) {
-        const int v = atoi(e);
-        if (v > 0 && v < want) want = v;
-    } else {
-        const size_t byWork = (nGuides + 65535) / 65536;
-        if ((size_t)want > byWork) want = (int)(byWork ? byWork : 1);
+    if (fd < 0) return -1;
+    char real[PATH_MAX];
+    if (!realpath(indexPath, real)) { close(fd); return -1; }
+    Request req{};
+    memcpy(req.magic, kReqMagic, 8);
+    req.op = kScore; req.maxDist = maxDist; req.threshold = threshold; req.method = method;
+    req.layout = issl_host::layout_from_env();
+    req.nGuides = guides.size();
+    req.pathLen = (uint32_t)strlen(real);
+    std::vector<int> devs = issl_host::devices_from_env();
+    if (devs.empty() && getenv("ISSL_GPUS")) devs = issl_host::pick_devices(guides.size());
+    req.nDevices = (uint32_t)std::min<size_t>(devs.size(), kMaxDevices);
+    for (uint32_t k = 0; k < req.nDevices; k++) req.devices[k] = devs[k];
+    Response rsp{};
+    std::string msg;
+    bool ok = write_full(fd, &req, sizeof req) && write_full(fd, real, req.pathLen) &&
+              (guides.empty() || write_full(fd, guides.data(), guides.size() * 8)) && read_full(fd, &rsp, sizeof rsp) &&
+              memcmp(rsp.magic, kRspMagic, 8) == 0;
+    if (ok && rsp.msgLen) { msg.resize(rsp.msgLen); ok = read_full(fd, msg.data(), rsp.msgLen); }
+    if (ok && rsp.status == ISSL_OK) {
+        ok = rsp.n == guides.size() && (rsp.n == 0 || (read_full(fd, mit.data(), rsp.n * 8) && read_full(fd, cfd.data(), rsp.n * 8)));
     }
-    if (want < 1) want = 1;   // device 0: creation will fail loudly when there is no GPU
-    for (int d = 0; d < want; d++) devs.push_back(d);
-    return devs;
-}
-
-int layout_from_env()
-{
-    const char *e = getenv("ISSL_LAYOUT");
-    if (!e) return ISSL_LAYOUT_AUTO;
-    if (!strcmp(e, "res32")) return ISSL_LAYOUT_RES32;
-    if (!strcmp(e, "sig64")) return ISSL_LAYOUT_SIG64;
-    if (!strcmp(e, "gather")) return ISSL_LAYOUT_GATHER;
-    return ISSL_LAYOUT_AUTO;
+    close(fd);
+    if (!ok) { fprintf(stderr, "isslScoreOfftargets: the score server on %s hung up\n", sockPath); return 1; }
+    if (rsp.status != ISSL_OK) { fprintf(stderr, "%s\n", msg.c_str()); return 1; }
+    if (timing)
+        fprintf(stderr, "[issl] server: %u GPU(s), index %s (%.3f s), scoring %.3f s, candidates %llu hits %llu early-exits %llu\n",
+                rsp.nDevices, rsp.cached ? "resident" : "loaded", rsp.loadSeconds, rsp.scoreSeconds,
+                (unsigned long long)rsp.candidates, (unsigned long long)rsp.hits, (unsigned long long)rsp.earlyExits);
+    return 0;
 }
 
 }  // namespace
@@ -129,43 +171,28 @@ int main(int argc, char **argv)
     // index replicated per GPU, guides partitioned into contiguous ranges, no cross-GPU reduction
     double tLoad = 0, tScore = 0;
     if (calcMit || calcCfd) {
-        const std::vector<int> devs = pick_devices(queryCount);
-        const size_t nd = devs.size();
-        std::vector<std::string> errors(nd);
-        std::vector<double> loadS(nd, 0), scoreS(nd, 0);
-        const int layout = layout_from_env();
-        auto worker = [&](size_t k) {
-            const size_t b = queryCount * k / nd, e = queryCount * (k + 1) / nd;
-            const double a0 = now_s();
-            issl_device *dev = nullptr;
-            if (issl_device_create(index, devs[k], layout, &dev) != ISSL_OK) { errors[k] = issl_last_error(); return; }
-            const double a1 = now_s();
-            if (issl_score(dev, querySignatures.data() + b, e - b, maxDist, threshold, method, mit.data() + b, cfd.data() + b) != ISSL_OK)
-                errors[k] = issl_last_error();
-            const double a2 = now_s();
-            loadS[k] = a1 - a0; scoreS[k] = a2 - a1;
-            if (timing) {
-                issl_stats s;
-                issl_last_stats(dev, &s);
-                fprintf(stderr, "[issl] gpu %d: guides %zu candidates %llu hits %llu early-exits %llu scan %.3f ms device-total %.3f ms\n",
-                        devs[k], e - b, (unsigned long long)s.candidates, (unsigned long long)s.hits,
-                        (unsigned long long)s.early_exits, s.scan_ms, s.total_ms);
-            }
-            issl_device_destroy(dev);
-        };
-        if (nd == 1) worker(0);
-        else {
-            std::vector<std::thread> pool;
-            for (size_t k = 0; k < nd; k++) pool.emplace_back(worker, k);
-            for (auto &t : pool) t.join();
+        int remote = -1;
+        const char *server = getenv("ISSL_SERVER");
+        if (server && *server) {
+            remote = score_remote(server, argv[1], querySignatures, maxDist, threshold, method, mit, cfd, timing);
+            if (remote == 1) return 1;
+            if (remote < 0) fprintf(stderr, "isslScoreOfftargets: no score server on %s, scoring in-process\n", server);
         }
-        for (size_t k = 0; k < nd; k++) {
-            if (!errors[k].empty()) {
-                fprintf(stderr, "%s\n", errors[k].c_str());
+        if (remote != 0) {
+            const std::vector<int> devs = issl_host::pick_devices(queryCount);
+            issl_host::DeviceSet set;
+            std::string err;
+            const double a0 = now_s();
+            if (set.ensure(index, devs, issl_host::layout_from_env(), &err) != ISSL_OK) {
+                fprintf(stderr, "%s\n", err.c_str());
                 return 1;
             }
-            tLoad = loadS[k] > tLoad ? loadS[k] : tLoad;
-            tScore = scoreS[k] > tScore ? scoreS[k] : tScore;
+            const double a1 = now_s();
+            if (set.score(devs, querySignatures.data(), queryCount, maxDist, threshold, method, mit.data(), cfd.data(), nullptr, &err, timing) != ISSL_OK) {
+                fprintf(stderr, "%s\n", err.c_str());
+                return 1;
+            }
+            tLoad = a1 - a0; tScore = now_s() - a1;
         }
     }
     const double t2 = now_s();

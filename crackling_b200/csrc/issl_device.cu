@@ -16,63 +16,10 @@
 #include <cub/device/device_scan.cuh>
 
 #include "issl_internal.h"
+#include "issl_device_common.cuh"
 #include "issl_kernels.cuh"
 
 using namespace issl;
-
-#define CK(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return issl_set_error(ISSL_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-#define CKR(call)                       \
-    do {                                \
-        int r_ = (call);                \
-        if (r_ != ISSL_OK) return r_;   \
-    } while (0)
-
-namespace {
-
-// growable device buffer
-struct DBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap) return ISSL_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        const size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            e = cudaMalloc(&p, bytes);
-            if (e != cudaSuccess) { p = nullptr; return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
-            cap = bytes;
-        } else cap = want;
-        return ISSL_OK;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-
-inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
-
-// host copy into a pinned staging buffer with all cores (a single memcpy stream tops out near 10 GB/s,
-// well below what PCIe Gen5 can take)
-inline void parallel_copy(void *dst, const void *src, size_t bytes)
-{
-    constexpr size_t kSlice = 1u << 20;
-    const long slices = (long)((bytes + kSlice - 1) / kSlice);
-#pragma omp parallel for schedule(static) if (slices > 4)
-    for (long i = 0; i < slices; i++) {
-        const size_t o = (size_t)i * kSlice, n = std::min(kSlice, bytes - o);
-        memcpy(static_cast<uint8_t *>(dst) + o, static_cast<const uint8_t *>(src) + o, n);
-    }
-}
-
-}  // namespace
 
 struct issl_device {
     int dev = -1;
@@ -363,6 +310,9 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
 // ---------------------------------------------------------------------------------------------
 // on-device construction from sorted keys (synthetic indexes)
 // ---------------------------------------------------------------------------------------------
+static int collapse_and_build(issl_device *d, int layout, const uint64_t *dKeys, DBuf &flags, bool haveFlags,
+                              bool valuesAreSortKeys, uint64_t nRaw, uint32_t L, uint32_t w);
+
 static int build_from_sites(issl_device *d, int layout, uint64_t *dKeys, uint64_t nRaw, uint32_t L, uint32_t w,
                             DBuf &keysAlt)
 {
@@ -378,11 +328,27 @@ static int build_from_sites(issl_device *d, int layout, uint64_t *dKeys, uint64_
         tmp.release();
         if (db.Current() != dKeys) CK(cudaMemcpyAsync(dKeys, db.Current(), nRaw * 8, cudaMemcpyDeviceToDevice, st));
     }
+    DBuf flags;
+    const int rc = collapse_and_build(d, layout, dKeys, flags, false, true, nRaw, L, w);
+    flags.release();
+    return rc;
+}
+
+// Everything isslCreateIndex does after reading its input (ref isslCreateIndex.cpp:184-252), on the device:
+// run-length collapse of adjacent equal records into (signature, occurrences), per-slice lists, score table.
+// dKeys[nRaw]: one value per input record in input order -- sort keys (synthetic path) or signatures (text path).
+// flags[nRaw] (optional): 1 where a record differs from its predecessor (the text path compares the text itself,
+// as the reference's memcmp at :192 does); computed from value equality otherwise.
+static int collapse_and_build(issl_device *d, int layout, const uint64_t *dKeys, DBuf &flags, bool haveFlags,
+                              bool valuesAreSortKeys, uint64_t nRaw, uint32_t L, uint32_t w)
+{
+    cudaStream_t st = d->stream;
+    if (nRaw >= (1ull << 32)) return issl_set_error(ISSL_ERR_UNSUPPORTED, "more than 2^32 input records");
     // run-length collapse (ref isslCreateIndex.cpp:184-207)
-    DBuf flags, ranks, runStart;
+    DBuf ranks, runStart;
     CKR(flags.ensure(nRaw * 4));
     CKR(ranks.ensure(nRaw * 8));
-    k_run_flags<<<blocks_for(nRaw, 256), 256, 0, st>>>(dKeys, nRaw, flags.as<uint32_t>());
+    if (!haveFlags) k_run_flags<<<blocks_for(nRaw, 256), 256, 0, st>>>(dKeys, nRaw, flags.as<uint32_t>());
     {
         size_t tb = 0;
         CK(cub::DeviceScan::InclusiveSum(nullptr, tb, flags.as<uint32_t>(), ranks.as<uint64_t>(), nRaw, st));
@@ -393,7 +359,7 @@ static int build_from_sites(issl_device *d, int layout, uint64_t *dKeys, uint64_
         tmp.release();
     }
     const uint64_t N = d->hCounters[0];
-    if (N >= (1ull << 32)) return issl_set_error(ISSL_ERR_UNSUPPORTED, "synthetic index: more than 2^32 distinct sites");
+    if (N >= (1ull << 32)) return issl_set_error(ISSL_ERR_UNSUPPORTED, "more than 2^32 distinct sites");
 
     issl_info f{};
     f.offtargetsCount = N; f.seqLength = L; f.seqCount = nRaw; f.sliceWidth = w; f.sliceCount = (2 * L) / w;
@@ -410,11 +376,11 @@ static int build_from_sites(issl_device *d, int layout, uint64_t *dKeys, uint64_
     DBuf sigTmp, occTmp;
     CKR(sigTmp.ensure(N * 8)); CKR(occTmp.ensure(N * 4)); CKR(runStart.ensure(N * 8));
     k_run_scatter<<<blocks_for(nRaw, 256), 256, 0, st>>>(dKeys, flags.as<uint32_t>(), ranks.as<uint64_t>(), nRaw, L,
-                                                        sigTmp.as<uint64_t>(), runStart.as<uint64_t>());
+                                                        valuesAreSortKeys ? 1 : 0, sigTmp.as<uint64_t>(), runStart.as<uint64_t>());
     k_run_lengths<<<blocks_for(N, 256), 256, 0, st>>>(runStart.as<uint64_t>(), N, nRaw, occTmp.as<uint32_t>());
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
-    flags.release(); ranks.release(); runStart.release();
+    ranks.release(); runStart.release();
 
     // per-slice values, histograms
     const uint64_t S = f.sliceCount, sliceLimit = 1ull << w;
@@ -492,6 +458,105 @@ extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_
         cudaError_t e = cudaStreamSynchronize(d->stream);
         if (e != cudaSuccess) rc = issl_set_error(ISSL_ERR_CUDA, "synthetic build: %s", cudaGetErrorString(e));
     }
+    if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
+    *out = d;
+    return ISSL_OK;
+}
+
+// internal (issl_sites.cu): an index from `nRaw` site sort keys already on this device, in any order.  Both key
+// buffers are scratch afterwards; the caller still owns them.
+int issl_internal_device_from_keys(int cuda_device, int layout, uint64_t *dKeys, uint64_t *dKeysAlt, uint64_t nRaw,
+                                   uint32_t seqLength, uint32_t sliceWidth, issl_device **out)
+{
+    *out = nullptr;
+    if (seqLength == 0 || seqLength > 32 || sliceWidth < 2 || sliceWidth > 24 || (2 * seqLength) / sliceWidth == 0)
+        return issl_set_error(ISSL_ERR_ARG, "bad sequence length / slice width");
+    if (nRaw == 0) return issl_set_error(ISSL_ERR_ARG, "no sites");
+    issl_info f{};
+    f.seqLength = seqLength; f.sliceWidth = sliceWidth; f.sliceCount = (2 * seqLength) / sliceWidth;
+    int lay = 0;
+    CKR(choose_layout(f, layout, &lay));
+    issl_device *d = nullptr;
+    CKR(new_device(cuda_device, &d));
+    DBuf alt;   // non-owning view
+    alt.p = dKeysAlt; alt.cap = nRaw * 8;
+    int rc = build_from_sites(d, lay, dKeys, nRaw, seqLength, sliceWidth, alt);
+    if (rc == ISSL_OK) {
+        cudaError_t e = cudaStreamSynchronize(d->stream);
+        if (e != cudaSuccess) rc = issl_set_error(ISSL_ERR_CUDA, "index build: %s", cudaGetErrorString(e));
+    }
+    if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
+    *out = d;
+    return ISSL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// construction from the text file isslCreateIndex reads (ref isslCreateIndex.cpp:138-207)
+// ---------------------------------------------------------------------------------------------
+extern "C" int issl_device_create_from_text(const char *text, size_t bytes, uint32_t seqLength, uint32_t sliceWidth,
+                                            int cuda_device, int layout, issl_device **out)
+{
+    if (!out || (bytes && !text)) return issl_set_error(ISSL_ERR_ARG, "issl_device_create_from_text: null argument");
+    *out = nullptr;
+    if (seqLength == 0 || seqLength > 32)   // ref :142-145
+        return issl_set_error(ISSL_ERR_ARG, "Sequence length is greater than 32, which is the maximum supported currently");
+    if (sliceWidth < 2 || sliceWidth > 24 || (2 * seqLength) / sliceWidth == 0 || (2 * seqLength) / sliceWidth - 1 >= 20)
+        return issl_set_error(ISSL_ERR_ARG, "issl_device_create_from_text: unsupported slice width %u", sliceWidth);
+    const size_t line = seqLength + 1;
+    if (bytes % line != 0)                  // ref :147-153
+        return issl_set_error(ISSL_ERR_ARG, "Error: file does is not a multiple of the expected line length (%zu)", line);
+    const uint64_t nRaw = bytes / line;
+    if (nRaw == 0) return issl_set_error(ISSL_ERR_IO, "Failed to read in file.");   // ref :176-179
+    issl_info f{};
+    f.seqLength = seqLength; f.sliceWidth = sliceWidth; f.sliceCount = (2 * seqLength) / sliceWidth;
+    int lay = 0;
+    CKR(choose_layout(f, layout, &lay));
+    issl_device *d = nullptr;
+    CKR(new_device(cuda_device, &d));
+
+    DBuf sigRaw, flags, dtext[2];
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t freeEv[2] = {nullptr, nullptr};
+    int rc = ISSL_OK;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; b++) {
+            if (stage[b]) cudaFreeHost(stage[b]);
+            if (freeEv[b]) cudaEventDestroy(freeEv[b]);
+            dtext[b].release();
+        }
+        sigRaw.release(); flags.release();
+    };
+    // chunks of whole lines, each preceded by one line of overlap (for the "differs from predecessor" test)
+    const uint64_t linesPerChunk = std::max<uint64_t>(1, (192ull << 20) / line);
+    const size_t chunkBytes = (size_t)((linesPerChunk + 1) * line);
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == ISSL_OK) rc = issl_set_error(ISSL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    if ((rc = sigRaw.ensure(nRaw * 8)) == ISSL_OK) rc = flags.ensure(nRaw * 4);
+    for (int b = 0; b < 2 && rc == ISSL_OK; b++) {
+        cu(cudaMallocHost(&stage[b], chunkBytes), "cudaMallocHost");
+        cu(cudaEventCreateWithFlags(&freeEv[b], cudaEventDisableTiming), "cudaEventCreate");
+        if (rc == ISSL_OK) rc = dtext[b].ensure(chunkBytes);
+    }
+    int buf = 0;
+    for (uint64_t l0 = 0; l0 < nRaw && rc == ISSL_OK; l0 += linesPerChunk) {
+        const uint64_t n = std::min<uint64_t>(linesPerChunk, nRaw - l0);
+        const int hasPrev = l0 > 0;
+        if (!cu(cudaEventSynchronize(freeEv[buf]), "cudaEventSynchronize")) break;
+        parallel_copy(stage[buf], text + (l0 - hasPrev) * line, (size_t)((n + hasPrev) * line));
+        if (!cu(cudaMemcpyAsync(dtext[buf].p, stage[buf], (size_t)((n + hasPrev) * line), cudaMemcpyHostToDevice, d->stream), "H2D of site text")) break;
+        k_pack_lines<<<blocks_for(n, 256), 256, 0, d->stream>>>(dtext[buf].as<char>(), n, hasPrev, seqLength,
+                                                               sigRaw.as<uint64_t>() + l0, flags.as<uint32_t>() + l0);
+        cu(cudaGetLastError(), "k_pack_lines");
+        cu(cudaEventRecord(freeEv[buf], d->stream), "cudaEventRecord");
+        buf ^= 1;
+    }
+    if (rc == ISSL_OK) cu(cudaStreamSynchronize(d->stream), "site text upload");
+    for (int b = 0; b < 2; b++) dtext[b].release();
+    if (rc == ISSL_OK) rc = collapse_and_build(d, lay, sigRaw.as<uint64_t>(), flags, true, false, nRaw, seqLength, sliceWidth);
+    if (rc == ISSL_OK) cu(cudaStreamSynchronize(d->stream), "index build");
+    cleanup();
     if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
     *out = d;
     return ISSL_OK;
@@ -657,7 +722,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         const uint32_t chunk = (uint32_t)chunk64;
 
         uint32_t maxGroup = d->maxGroup;
-        if (maxGroup > kMaxGroup && !(d->layout == ISSL_LAYOUT_RES32 && maxDist <= 4)) maxGroup = kMaxGroup;
+        if (maxGroup > kMaxGroup && !(d->layout == ISSL_LAYOUT_RES32 && maxDist <= 7)) maxGroup = kMaxGroup;
         CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
         k_group_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
                                                              maxGroup, d->pairCounts.as<uint32_t>(), dc + 4);

@@ -30,4 +30,8 @@ int issl_set_error(int code, const char *fmt, ...);
 void issl_sorted_score_table(const uint64_t *pairs, uint64_t n, std::vector<uint64_t> &masks,
                              std::vector<double> &scores);
 
+// issl_device.cu: builds a resident index from unsorted site sort keys that already lie on `cuda_device`.
+int issl_internal_device_from_keys(int cuda_device, int layout, uint64_t *dKeys, uint64_t *dKeysAlt, uint64_t nRaw,
+                                   uint32_t seqLength, uint32_t sliceWidth, issl_device **out);
+
 #endif

@@ -292,7 +292,7 @@ __device__ __forceinline__ void scan_body(const ScanArgs &a, const ScanItem &it)
     }
 }
 
-// Bit-sliced path (kRes32, maxDist <= 4, groups of 9..32 guides): no POPC at all.
+// Bit-sliced path (kRes32, maxDist <= 7, groups of 9..32 guides): no POPC at all.
 //
 // Every 32-bit word holds one bit per GUIDE of the group.  For each pair of adjacent residual
 // bases (a nibble of the candidate, 8 nibbles) a 16-entry shared-memory table gives, for the 16
@@ -302,7 +302,7 @@ __device__ __forceinline__ void scan_body(const ScanArgs &a, const ScanItem &it)
 // carry-save adder tree (11 full adders = 22 LOP3) counts them per bit lane, and 4 more LOP3
 // give the lanes whose count is <= 4.  24 + 16 ALU-pipe instructions test 32 (guide, candidate)
 // pairs, against 32 POPC (XU pipe, 16 lanes/clk) + 80 ALU for the same pairs on the register path.
-// The accept word is exact for maxDist = 4 and a superset for maxDist < 4; survivors are re-tested.
+// The accept word is exact for maxDist = 4..7 and a superset for maxDist < 4; survivors are re-tested.
 struct BitSliceTable { uint2 e[8][16]; };
 
 __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
@@ -311,7 +311,9 @@ __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uin
     carry = (a & b) | (c & (a ^ b));
 }
 
-__device__ __forceinline__ uint32_t accept_le4(const BitSliceTable &tb, uint32_t c)
+// MD selects the threshold the accept word encodes: count <= 4 (used for every maxDist <= 4), <= 5, <= 6, <= 7.
+template <int MD>
+__device__ __forceinline__ uint32_t accept_le(const BitSliceTable &tb, uint32_t c)
 {
     uint32_t f[16];
 #pragma unroll
@@ -331,9 +333,15 @@ __device__ __forceinline__ uint32_t accept_le4(const BitSliceTable &tb, uint32_t
     full_add(k0, k1, k2, u0, q0);          // weight 2
     full_add(k3, k4, k5, u1, q1);
     full_add(u0, u1, k6, m, q2);           // weight-2 bit left: m; weight-4 bits: q0, q1, q2
-    // count = t0 + t1 + 2 m + 4 (q0 + q1 + q2) >= 5  <=>  two of q set, or one q set and any of t0, t1, m
-    const uint32_t reject = ((q0 & q1) | (q2 & (q0 ^ q1))) | ((q0 | q1 | q2) & (t0 | t1 | m));
-    return ~reject;
+    // count = low + 4 (q0 + q1 + q2) with low = t0 + t1 + 2 m in 0..4.  Two q bits set means count >= 8: always
+    // rejected.  With exactly one q bit set, count = 4 + low is rejected when low exceeds MD - 4.
+    const uint32_t two = (q0 & q1) | (q2 & (q0 ^ q1)), any = q0 | q1 | q2;
+    uint32_t lowTooBig;
+    if (MD <= 4) lowTooBig = t0 | t1 | m;               // low >= 1
+    else if (MD == 5) lowTooBig = m | (t0 & t1);        // low >= 2
+    else if (MD == 6) lowTooBig = m & (t0 | t1);        // low >= 3
+    else lowTooBig = m & t0 & t1;                       // low >= 4  (MD == 7)
+    return ~(two | (any & lowTooBig));
 }
 
 __device__ __noinline__ void scan_emit32(const ScanArgs &a, uint32_t slice, uint32_t groupStart, uint32_t accept,
@@ -350,6 +358,7 @@ __device__ __noinline__ void scan_emit32(const ScanArgs &a, uint32_t slice, uint
     }
 }
 
+template <int MD>
 __device__ __forceinline__ void scan_body_bitsliced(const ScanArgs &a, const ScanItem &it, BitSliceTable &tb, uint32_t *gres)
 {
     const uint32_t slice = (uint32_t)(it.p0Slice >> 56);
@@ -376,7 +385,7 @@ __device__ __forceinline__ void scan_body_bitsliced(const ScanArgs &a, const Sca
     const uint4 *__restrict__ v4 = reinterpret_cast<const uint4 *>(a.iv.res32 + p0);
     const uint32_t nvec = n >> 2;
     auto vec = [&](const uint4 &r, uint64_t pos) {
-        const uint32_t a0 = accept_le4(tb, r.x), a1 = accept_le4(tb, r.y), a2 = accept_le4(tb, r.z), a3 = accept_le4(tb, r.w);
+        const uint32_t a0 = accept_le<MD>(tb, r.x), a1 = accept_le<MD>(tb, r.y), a2 = accept_le<MD>(tb, r.z), a3 = accept_le<MD>(tb, r.w);
         if (a0 | a1 | a2 | a3) {
             if (a0) scan_emit32(a, slice, it.groupStart, a0, r.x, pos);
             if (a1) scan_emit32(a, slice, it.groupStart, a1, r.y, pos + 1);
@@ -397,7 +406,7 @@ __device__ __forceinline__ void scan_body_bitsliced(const ScanArgs &a, const Sca
     if (tid < (n & 3u)) {
         const uint64_t pos = p0 + 4ull * nvec + tid;
         const uint32_t r = a.iv.res32[pos];
-        const uint32_t acc = accept_le4(tb, r);
+        const uint32_t acc = accept_le<MD>(tb, r);
         if (acc) scan_emit32(a, slice, it.groupStart, acc, r, pos);
     }
 }
@@ -410,7 +419,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanArgs a)
     if (LAYOUT == kRes32) {
         __shared__ BitSliceTable tb;
         __shared__ uint32_t gres[32];
-        if (groupSize > kMaxGroup) { scan_body_bitsliced(a, it, tb, gres); return; }
+        if (groupSize > kMaxGroup) {
+            if (a.maxDist <= 4) scan_body_bitsliced<4>(a, it, tb, gres);
+            else if (a.maxDist == 5) scan_body_bitsliced<5>(a, it, tb, gres);
+            else if (a.maxDist == 6) scan_body_bitsliced<6>(a, it, tb, gres);
+            else scan_body_bitsliced<7>(a, it, tb, gres);
+            return;
+        }
     }
     if (groupSize > 4) scan_body<LAYOUT, 8>(a, it);
     else if (groupSize > 2) scan_body<LAYOUT, 4>(a, it);
@@ -806,13 +821,34 @@ __global__ void k_run_flags(const uint64_t *keys, uint64_t n, uint32_t *flags)
 
 // scatter run heads: runStart[rank] = t, sig[rank] = signature (rank = inclusive scan of flags - 1)
 __global__ void k_run_scatter(const uint64_t *keys, const uint32_t *flags, const uint64_t *rankIncl, uint64_t n,
-                              uint32_t L, uint64_t *sig, uint64_t *runStart)
+                              uint32_t L, int valuesAreSortKeys, uint64_t *sig, uint64_t *runStart)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n || !flags[t]) return;
     const uint64_t r = rankIncl[t] - 1;
     runStart[r] = t;
-    sig[r] = sig_to_sortkey(keys[t], L);   // the key transform is an involution (base order reversal)
+    sig[r] = valuesAreSortKeys ? sig_to_sortkey(keys[t], L) : keys[t];   // the key transform is an involution (base order reversal)
+}
+
+// isslCreateIndex's input: fixed-width text lines (ref isslCreateIndex.cpp:39-47 packing, :158-161 table: anything
+// but C, G, T packs as 0).  text holds n lines preceded by one more line when hasPrev.  flags[i] = 1 when line i
+// differs from its predecessor as TEXT (the reference's memcmp at :192), which starts a new distinct site.
+__global__ void k_pack_lines(const char *text, uint64_t n, int hasPrev, uint32_t L, uint64_t *sig, uint32_t *flags)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t line = L + 1;
+    const char *p = text + (t + (hasPrev ? 1 : 0)) * line;
+    uint64_t s = 0;
+    bool differs = !(hasPrev || t > 0);
+    for (uint32_t j = 0; j < L; j++) {
+        const char c = p[j];
+        const uint64_t code = c == 'C' ? 1ull : c == 'G' ? 2ull : c == 'T' ? 3ull : 0ull;
+        s |= code << (2 * j);
+        if (hasPrev || t > 0) differs |= (c != p[(long long)j - (long long)line]);
+    }
+    sig[t] = s;
+    flags[t] = differs ? 1u : 0u;
 }
 
 __global__ void k_run_lengths(const uint64_t *runStart, uint64_t nRuns, uint64_t n, uint32_t *occ)

@@ -143,6 +143,15 @@ int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uin
                                  uint32_t families, uint32_t family_size, double max_sub_rate,
                                  uint32_t seqLength, uint32_t sliceWidth, issl_device **out);
 
+/* Builds the index on the device from the text file isslCreateIndex reads: fixed-width lines of seqLength
+ * bases + LF, sorted, duplicates adjacent.  Replaces isslCreateIndex.cpp:138-252 (record packing :39-47,
+ * run-length collapse of identical adjacent lines into occurrence counts :184-207, slice lists with the 8-bit
+ * slice-value truncation :216-234, local MIT score table :239-252).  Together with issl_device_write_issl
+ * (:256-289) this is a drop-in for the isslCreateIndex executable (bin/isslCreateIndex); the handle can also
+ * be scored directly, skipping the .issl file. */
+int issl_device_create_from_text(const char *text, size_t bytes, uint32_t seqLength, uint32_t sliceWidth,
+                                 int cuda_device, int layout, issl_device **out);
+
 int issl_device_get_info(const issl_device *dev, issl_device_info *out);
 void issl_device_destroy(issl_device *dev);
 
