@@ -2,6 +2,7 @@
 #   crackling_b200/lib/libissl_cuda.so   C-ABI library (include/issl_cuda.h), sm_100a only
 #   bin/isslScoreOfftargets              drop-in host program (same CLI as the reference binary)
 #   bin/isslScoreServer                  resident scorer behind the same CLI (index stays in HBM between pages)
+#   bin/extractOfftargets                drop-in off-target site extractor (FASTA -> sorted site list, optionally -> .issl)
 #   bin/isslCreateIndex                  drop-in index builder (same CLI, byte-identical .issl)
 # Test infrastructure (never linked into the products):
 #   make oracle   -> oracle/_build/libissl_oracle.so
@@ -14,17 +15,21 @@ LIBDIR    := crackling_b200/lib
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-fopenmp,-Wall -Iinclude -I$(CSRC) --expt-relaxed-constexpr
 CXXFLAGS  := -O3 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Iinclude -I$(CSRC)
 
-all: $(LIBDIR)/libissl_cuda.so bin/isslScoreOfftargets bin/isslCreateIndex bin/isslScoreServer
+all: $(LIBDIR)/libissl_cuda.so bin/isslScoreOfftargets bin/isslCreateIndex bin/isslScoreServer bin/extractOfftargets
 
 $(LIBDIR)/issl_host.o: $(CSRC)/issl_host.cpp $(CSRC)/issl_internal.h include/issl_cuda.h
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) -c -o $@ $<
 
-$(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_kernels.cuh $(CSRC)/issl_internal.h $(CSRC)/cfd_tables.h include/issl_cuda.h
+$(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_device_common.cuh $(CSRC)/issl_kernels.cuh $(CSRC)/issl_internal.h $(CSRC)/cfd_tables.h include/issl_cuda.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o $@ $< 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 
-$(LIBDIR)/libissl_cuda.so: $(LIBDIR)/issl_host.o $(LIBDIR)/issl_device.o
+$(LIBDIR)/issl_sites.o: $(CSRC)/issl_sites.cu $(CSRC)/issl_device_common.cuh $(CSRC)/issl_internal.h include/issl_cuda.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o $@ $< 2> $(LIBDIR)/ptxas_sites.log || (cat $(LIBDIR)/ptxas_sites.log; false)
+
+$(LIBDIR)/libissl_cuda.so: $(LIBDIR)/issl_host.o $(LIBDIR)/issl_device.o $(LIBDIR)/issl_sites.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xcompiler -fopenmp -lgomp
 
 HOSTHDR   := include/issl_cuda.h $(CSRC)/issl_hostcommon.h $(CSRC)/issl_wire.h
@@ -38,6 +43,10 @@ bin/isslScoreServer: $(CSRC)/isslScoreServer.cpp $(HOSTHDR) $(LIBDIR)/libissl_cu
 	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -I$(CSRC) -o $@ $< -L$(LIBDIR) -lissl_cuda -pthread '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
 
 bin/isslCreateIndex: $(CSRC)/isslCreateIndex.cpp include/issl_cuda.h $(LIBDIR)/libissl_cuda.so
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lissl_cuda '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
+
+bin/extractOfftargets: $(CSRC)/extractOfftargets.cpp include/issl_cuda.h $(LIBDIR)/libissl_cuda.so
 	@mkdir -p bin
 	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lissl_cuda '-Wl,-rpath,$$ORIGIN/../$(LIBDIR)'
 

@@ -11,6 +11,7 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 LIB = ROOT / "crackling_b200" / "lib" / "libissl_cuda.so"
 CLI = ROOT / "bin" / "isslScoreOfftargets"
 CREATE_CLI = ROOT / "bin" / "isslCreateIndex"
+EXTRACT_CLI = ROOT / "bin" / "extractOfftargets"
 
 METHODS = {"unknown": 0, "mit": 1, "cfd": 2, "and": 3, "or": 4, "avg": 5}
 LAYOUTS = {"auto": 0, "res32": 1, "sig64": 2, "gather": 3}
@@ -62,6 +63,10 @@ def create_cli_path() -> pathlib.Path:
     return CREATE_CLI
 
 
+def extract_cli_path() -> pathlib.Path:
+    return EXTRACT_CLI
+
+
 def lib() -> C.CDLL:
     """Loads the in-tree shared library; fails loudly when it has not been built."""
     global _lib
@@ -83,6 +88,13 @@ def lib() -> C.CDLL:
             "issl_device_create": ([vp, i, i, pp], i),
             "issl_device_create_synthetic": ([i, i, u64, u64, C.c_uint32, C.c_uint32, d, C.c_uint32, C.c_uint32, pp], i),
             "issl_device_create_from_text": ([C.c_char_p, sz, C.c_uint32, C.c_uint32, i, i, pp], i),
+            "issl_sites_create": ([i, pp], i),
+            "issl_sites_destroy": ([vp], None),
+            "issl_sites_add_fasta": ([vp, C.c_char_p, sz, i], i),
+            "issl_sites_count": ([vp, C.POINTER(u64), C.POINTER(u64)], i),
+            "issl_sites_write_text": ([vp, C.c_char_p], i),
+            "issl_sites_read_keys": ([vp, u64, u64, vp], i),
+            "issl_device_create_from_sites": ([vp, C.c_uint32, i, pp], i),
             "issl_device_get_info": ([vp, C.POINTER(_DeviceInfo)], i),
             "issl_device_destroy": ([vp], None),
             "issl_device_write_issl": ([vp, C.c_char_p], i),
@@ -213,6 +225,14 @@ class Device:
         _check(lib().issl_device_create_from_text(text, len(text), seq_length, slice_width, cuda_device, lay, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def from_sites(cls, sites: "Sites", slice_width: int = 8, layout: str | int = "auto") -> "Device":
+        """issl_device_create_from_sites: extracted sites -> index, on the device."""
+        h = C.c_void_p()
+        lay = LAYOUTS[layout] if isinstance(layout, str) else int(layout)
+        _check(lib().issl_device_create_from_sites(sites._h, slice_width, lay, C.byref(h)))
+        return cls(h)
+
     @property
     def info(self) -> dict:
         s = _DeviceInfo()
@@ -281,6 +301,49 @@ class Device:
         if self._h:
             lib().issl_device_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Sites:
+    """issl_sites: the device-side extractOfftargets."""
+
+    def __init__(self, cuda_device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().issl_sites_create(cuda_device, C.byref(self._h)))
+
+    def add_fasta(self, text: bytes, single_input: bool = True):
+        _check(lib().issl_sites_add_fasta(self._h, text, len(text), 1 if single_input else 0))
+
+    @property
+    def count(self) -> int:
+        n, c = C.c_uint64(), C.c_uint64()
+        _check(lib().issl_sites_count(self._h, C.byref(n), C.byref(c)))
+        return n.value
+
+    @property
+    def characters(self) -> int:
+        n, c = C.c_uint64(), C.c_uint64()
+        _check(lib().issl_sites_count(self._h, C.byref(n), C.byref(c)))
+        return c.value
+
+    def write_text(self, path):
+        _check(lib().issl_sites_write_text(self._h, str(path).encode()))
+
+    def keys(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = self.count - first if n is None else n
+        out = np.empty(n, dtype=np.uint64)
+        _check(lib().issl_sites_read_keys(self._h, first, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().issl_sites_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:

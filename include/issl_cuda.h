@@ -152,6 +152,38 @@ int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uin
 int issl_device_create_from_text(const char *text, size_t bytes, uint32_t seqLength, uint32_t sliceWidth,
                                  int cuda_device, int layout, issl_device **out);
 
+/* ---- off-target site extraction (the step before the index) ------------------------------- */
+
+/* The off-target sites of a genome, held as sort keys in one GPU's HBM.  Replaces
+ * /root/reference/src/crackling/utils/extractOfftargets.py: FASTA reading (:26-62, :73-90), the two look-ahead
+ * regexes (:23-24: forward [ACG][ACGT]{19}[ACGT][AG]G, reverse C[CT][ACGT][ACGT]{19}[TGC]), the slicing
+ * (:97-106: match[0:20], reverse-complemented on the reverse strand) and the global sort (:112-191). */
+typedef struct issl_sites issl_sites;
+
+int issl_sites_create(int cuda_device, issl_sites **out);
+void issl_sites_destroy(issl_sites *sites);
+
+/* Extracts the sites of one FASTA / multi-FASTA / plain-sequence buffer and appends them.  single_input != 0
+ * selects the reading rules of the tool's one-input path (explodeMultiFastaFile, :26-62: lines stripped on both
+ * sides, every record kept); 0 those of its several-inputs path (processingNode, :73-90: lines stripped on the
+ * right only, records keyed by header text so that a repeated header discards the earlier record, :83).
+ * Lines end at LF, CR or CRLF (Python's universal newlines); characters are upper-cased (:59, :89). */
+int issl_sites_add_fasta(issl_sites *sites, const char *text, size_t bytes, int single_input);
+
+/* Sites found so far (before duplicate collapsing) and sequence characters scanned. */
+int issl_sites_count(const issl_sites *sites, uint64_t *n_sites, uint64_t *n_characters);
+
+/* Writes the sorted text file the tool writes (20 bases + LF per site, Python string order; ref :112-191). */
+int issl_sites_write_text(issl_sites *sites, const char *path);
+
+/* Copies sorted sites [first, first + n) to the host as sort keys: base 0 in bits 38..39, ..., base 19 in bits
+ * 0..1 (A=0 C=1 G=2 T=3), so ascending keys are ascending text lines. */
+int issl_sites_read_keys(issl_sites *sites, uint64_t first, uint64_t n, uint64_t *out);
+
+/* Builds the index from the extracted sites on the same GPU, without the text file in between: what
+ * extractOfftargets followed by isslCreateIndex (seqLength 20) produces. */
+int issl_device_create_from_sites(issl_sites *sites, uint32_t sliceWidth, int layout, issl_device **out);
+
 int issl_device_get_info(const issl_device *dev, issl_device_info *out);
 void issl_device_destroy(issl_device *dev);
 

@@ -63,3 +63,56 @@ def guide_candidates(records: list[bytes]) -> np.ndarray:
         ok = (s[i + 21] == G) & (s[i + 22] == G)
         out.append(_windows(s, i[ok], 20))
     return np.concatenate(out, axis=0)
+
+
+# ---- FASTA reading (the tool's two input paths) -------------------------------------------------
+
+def _lines(raw: bytes):
+    """Lines as Python's open(path, 'r') yields them: universal newlines, terminators translated to LF."""
+    import io
+    return io.TextIOWrapper(io.BytesIO(raw), encoding="utf-8", newline=None)
+
+
+def read_single_input(raw: bytes) -> list[bytes]:
+    """One input file: explodeMultiFastaFile (extractOfftargets.py:26-62) writes each record to its own file
+    (header, then every other line strip()ped and upper-cased, concatenated), and processingNode (:73-90) reads
+    that file back.  The tool indexes line[0] of the stripped line, so a blank line -- or sequence before the
+    first header -- makes it crash; here blank lines are skipped and leading sequence forms a record."""
+    records, cur = [], None
+    for line in _lines(raw):
+        line = line.strip()
+        if not line:
+            continue
+        if line[0] == ">":
+            cur = []
+            records.append(cur)
+        else:
+            if cur is None:
+                cur = []
+                records.append(cur)
+            cur.append(line.upper().strip())
+    return ["".join(r).rstrip().upper().encode() for r in records]
+
+
+def read_one_of_several_inputs(raw: bytes) -> list[bytes]:
+    """Several input files: processingNode (:73-90) reads each directly.  Records are keyed by header text
+    (line[1:]), a repeated header starts its record afresh (:83), lines are rstrip()ped only (:89)."""
+    seqs, header = {}, None
+    for line in _lines(raw):
+        if line[0] == ">":
+            header = line[1:]
+            seqs[header] = []
+        else:
+            if header not in seqs:
+                seqs[header] = []
+            seqs[header].append(line.rstrip().upper())
+    return ["".join(v).encode() for v in seqs.values()]
+
+
+def extract_from_inputs(inputs: list[bytes]) -> bytes:
+    """What `extractOfftargets.py output inputs...` writes for these file contents."""
+    if len(inputs) == 1:
+        records = read_single_input(inputs[0])
+    else:
+        records = [r for raw in inputs for r in read_one_of_several_inputs(raw)]
+    return extract_offtargets(records)
