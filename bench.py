@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sites", type=int, default=HUMAN_SITES, help="uniform synthetic sites before duplicate collapsing")
     ap.add_argument("--guides", type=int, default=GUIDES_PER_GPU, help="guides per GPU")
-    ap.add_argument("--layout", default="auto", choices=["auto", "res32", "sig64", "gather"])
+    ap.add_argument("--layout", default="auto", choices=["auto", "triple", "res32", "sig64", "gather"])
     ap.add_argument("--slice-width", type=int, default=8)
     ap.add_argument("--method", default=METHOD)
     ap.add_argument("--max-dist", type=int, default=MAX_DIST)
@@ -297,7 +297,7 @@ def main() -> int:
                               family_size=args.family_size, max_sub_rate=0.15, seq_length=20, slice_width=args.slice_width)
     t_build = time.perf_counter() - t_build
     info = dev.info
-    layout_name = {1: "res32", 2: "sig64", 3: "gather"}[info["layout"]]
+    layout_name = {1: "res32", 2: "sig64", 3: "gather", 4: "triple"}[info["layout"]]
     guides = make_guides(dev, args.guides, seed=2 + rank, families=args.families, family_frac=args.family_guides)
     workload = (f"synthetic human-scale index: {args.sites} uniform NGG sites -> {info['offtargetsCount']} distinct, "
                 f"l=20 w={args.slice_width}, {args.guides} guides/GPU (90% index sites, 10% random), method {args.method}, "
@@ -361,7 +361,7 @@ def main() -> int:
 
     for _ in range(args.warmup):
         step_device()
-    scan_ms, scan_launches, launches, candidates, hits, streamed = 0.0, 0, 0, 0, 0, 0
+    scan_ms, scan_launches, launches, candidates, hits, streamed, bucket_visits = 0.0, 0, 0, 0, 0, 0, 0
     barrier()
     with ClockSampler(local_rank) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,6 +371,7 @@ def main() -> int:
             st = dev.stats
             scan_ms += st["scan_ms"]; scan_launches += st["scan_launches"]; launches += st["launches"]
             candidates += st["candidates"]; hits += st["hits"]; streamed += st["streamed"]
+            bucket_visits += st["bucket_visits"]
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)

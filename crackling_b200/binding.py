@@ -14,7 +14,7 @@ CREATE_CLI = ROOT / "bin" / "isslCreateIndex"
 EXTRACT_CLI = ROOT / "bin" / "extractOfftargets"
 
 METHODS = {"unknown": 0, "mit": 1, "cfd": 2, "and": 3, "or": 4, "avg": 5}
-LAYOUTS = {"auto": 0, "res32": 1, "sig64": 2, "gather": 3}
+LAYOUTS = {"auto": 0, "res32": 1, "sig64": 2, "gather": 3, "triple": 4}
 
 
 class IsslError(RuntimeError):
@@ -37,7 +37,8 @@ class _DeviceInfo(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("guides", C.c_uint64), ("candidates", C.c_uint64), ("hits", C.c_uint64),
                 ("scan_launches", C.c_uint64), ("launches", C.c_uint64), ("scan_ms", C.c_double),
-                ("total_ms", C.c_double), ("early_exits", C.c_uint64), ("streamed", C.c_uint64)]
+                ("total_ms", C.c_double), ("early_exits", C.c_uint64), ("streamed", C.c_uint64),
+                ("bucket_visits", C.c_uint64)]
 
 
 _lib = None
@@ -105,6 +106,7 @@ def lib() -> C.CDLL:
             "issl_last_stats": ([vp, C.POINTER(_Stats)], i),
             "issl_local_mit_score": ([u64, sz], d),
             "issl_mit_table": ([sz, sz, vp, vp, sz, C.POINTER(u64)], sz),
+            "issl_triple_visits": ([C.c_int, vp, sz, vp], sz),
             "issl_last_error": ([], C.c_char_p),
             "issl_abi_version": ([], i),
         }
@@ -153,6 +155,15 @@ def mit_table(seq_length: int, slice_width: int):
     scores = np.zeros(count.value, dtype=np.float64)
     n = lib().issl_mit_table(seq_length, slice_width, masks.ctypes.data, scores.ctypes.data, count.value, C.byref(count))
     return masks[:n], scores[:n], int(count.value)
+
+
+def triple_visits(max_dist: int):
+    """(entries, waveStart[6]) of issl_triple_visits: pattern24 | triple << 24 | budget << 28, ordered by slice."""
+    wave = np.zeros(6, dtype=np.uint32)
+    n = lib().issl_triple_visits(int(max_dist), None, 0, wave.ctypes.data)
+    out = np.zeros(max(n, 1), dtype=np.uint32)
+    n = lib().issl_triple_visits(int(max_dist), out.ctypes.data, n, wave.ctypes.data)
+    return out[:n], wave
 
 
 def _info_dict(s) -> dict:

@@ -18,6 +18,7 @@
 #include "issl_internal.h"
 #include "issl_device_common.cuh"
 #include "issl_kernels.cuh"
+#include "issl_triple.cuh"
 
 using namespace issl;
 
@@ -47,6 +48,14 @@ struct issl_device {
     issl_stats stats{};
     uint32_t maxBatch = 1u << 20;
     uint32_t maxGroup = kBigGroup;   // ISSL_MAX_GROUP: 32 bit-sliced blocks + register groups (default), 8/4/2 register groups only, 1 no list reuse
+
+    // ISSL_LAYOUT_TRIPLE
+    DBuf tripleRes, tripleIds, tripleOffs, visits;
+    TripleView tv{};
+    int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
+    bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
+    int visitsDist = -100;           // maxDist the resident visit table was built for
+    uint32_t waveStart[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -88,6 +97,18 @@ static int upload_constants()
 {
     CK(cudaMemcpyToSymbol(c_cfdPos, ISSL_CFD_POS, sizeof(double) * 320));
     CK(cudaMemcpyToSymbol(c_cfdPam, ISSL_CFD_PAM, sizeof(double) * 16));
+    // resp(E) of issl_triple_visits: three lowest slices of E, completed with the lowest slices outside E
+    uint8_t resp[32];
+    for (uint32_t E = 0; E < 32; E++) {
+        int pick[3], np = 0;
+        for (int s = 0; s < 5 && np < 3; s++) if (E & (1u << s)) pick[np++] = s;
+        for (int s = 0; s < 5 && np < 3; s++) if (!(E & (1u << s))) pick[np++] = s;
+        std::sort(pick, pick + 3);
+        static const int T[10][3] = {{0, 1, 2}, {0, 1, 3}, {0, 1, 4}, {0, 2, 3}, {0, 2, 4}, {0, 3, 4}, {1, 2, 3}, {1, 2, 4}, {1, 3, 4}, {2, 3, 4}};
+        resp[E] = 0xFF;
+        for (int t = 0; t < 10; t++) if (T[t][0] == pick[0] && T[t][1] == pick[1] && T[t][2] == pick[2]) resp[E] = (uint8_t)t;
+    }
+    CK(cudaMemcpyToSymbol(c_tripleResp, resp, sizeof resp));
     return ISSL_OK;
 }
 
@@ -95,10 +116,14 @@ static int choose_layout(const issl_info &f, int requested, int *out)
 {
     const uint32_t w = (uint32_t)f.sliceWidth, kb = std::min<uint32_t>(w, 8);
     const bool res32ok = (w % 2 == 0) && (2 * f.seqLength >= kb) && (2 * f.seqLength - kb <= 32);
-    if (requested == ISSL_LAYOUT_AUTO) requested = res32ok ? ISSL_LAYOUT_RES32 : ISSL_LAYOUT_SIG64;
+    const bool tripleok = f.seqLength == 20 && w == 8 && f.sliceCount == 5;
+    if (requested == ISSL_LAYOUT_AUTO) requested = tripleok ? ISSL_LAYOUT_TRIPLE : res32ok ? ISSL_LAYOUT_RES32 : ISSL_LAYOUT_SIG64;
     if (requested == ISSL_LAYOUT_RES32 && !res32ok)
         return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout RES32 needs an even slice width and 2*seqLength - min(width,8) <= 32");
-    if (requested != ISSL_LAYOUT_RES32 && requested != ISSL_LAYOUT_SIG64 && requested != ISSL_LAYOUT_GATHER)
+    if (requested == ISSL_LAYOUT_TRIPLE && !tripleok)
+        return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout TRIPLE needs seqLength 20 and sliceWidth 8");
+    if (requested != ISSL_LAYOUT_RES32 && requested != ISSL_LAYOUT_SIG64 && requested != ISSL_LAYOUT_GATHER &&
+        requested != ISSL_LAYOUT_TRIPLE)
         return issl_set_error(ISSL_ERR_ARG, "unknown layout %d", requested);
     *out = requested;
     return ISSL_OK;
@@ -132,7 +157,8 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     CKR(d->occ.ensure(N * 4));
     CKR(d->ids.ensure(P * 4));
     CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
-    if (layout == ISSL_LAYOUT_RES32) { CKR(d->res32.ensure(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
+    const bool res32 = layout == ISSL_LAYOUT_RES32 || layout == ISSL_LAYOUT_TRIPLE;   // TRIPLE keeps the RES32 lists (maxDist > tripleMaxDist, .issl export)
+    if (res32) { CKR(d->res32.ensure(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
     if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.ensure(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
     CKR(d->listStart.ensure(d->nLists * 8));
     CKR(d->listLen.ensure(d->nLists * 8));
@@ -154,9 +180,9 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     v.sliceCount = (uint32_t)f.sliceCount; v.sliceLimit = (uint32_t)sliceLimit;
     v.sliceMask = (uint32_t)(sliceLimit - 1);
     v.knownBits = std::min<uint32_t>((uint32_t)f.sliceWidth, 8);
-    v.layout = layout;
+    v.layout = res32 ? (int)ISSL_LAYOUT_RES32 : layout;
 
-    d->hbmBytes = N * 12 + P * 4 + (layout == ISSL_LAYOUT_RES32 ? P * 4 : 0) + (layout == ISSL_LAYOUT_SIG64 ? P * 8 : 0) +
+    d->hbmBytes = N * 12 + P * 4 + (res32 ? P * 4 : 0) + (layout == ISSL_LAYOUT_SIG64 ? P * 8 : 0) +
                   d->nLists * 24;
     return ISSL_OK;
 }
@@ -174,6 +200,53 @@ static int upload_mit_table(issl_device *d)
     return ISSL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ISSL_LAYOUT_TRIPLE: ten bucketed copies of the sites (issl_triple.cuh), built from sig[] once the
+// index itself is resident and validated
+// ---------------------------------------------------------------------------------------------
+static int build_triple(issl_device *d)
+{
+    if (d->layout != ISSL_LAYOUT_TRIPLE) return ISSL_OK;
+    cudaStream_t st = d->stream;
+    const uint64_t N = d->info.offtargetsCount;
+    const uint64_t stride = (N + 64 + 7) / 8 * 8;
+    const uint64_t need = kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + N * 16 + (64ull << 20);
+    size_t freeB = 0, totalB = 0;
+    CK(cudaMemGetInfo(&freeB, &totalB));
+    if (need > freeB) {
+        if (d->layoutAuto) { d->layout = ISSL_LAYOUT_RES32; return ISSL_OK; }
+        return issl_set_error(ISSL_ERR_NOMEM, "layout TRIPLE needs %.1f GB of free HBM, %.1f GB available", need / 1e9, freeB / 1e9);
+    }
+    CKR(d->tripleRes.ensure(kTripleCount * stride * 2));
+    CKR(d->tripleIds.ensure(kTripleCount * stride * 4));
+    CKR(d->tripleOffs.ensure(kTripleCount * (kTripleBuckets + 1ull) * 4));
+    CK(cudaMemsetAsync(d->tripleRes.p, 0, kTripleCount * stride * 2, st));
+    DBuf keysIn, keysOut, idsIn, tmp;
+    CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(),
+                                       d->tripleIds.as<uint32_t>(), N, 0, 24, st));
+    CKR(tmp.ensure(tb));
+    for (uint32_t t = 0; t < kTripleCount; t++) {
+        uint32_t *ids = d->tripleIds.as<uint32_t>() + t * stride;
+        k_triple_keys<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), N, t, keysIn.as<uint32_t>(), idsIn.as<uint32_t>());
+        // stable: ids stay ascending inside a bucket, as inside the reference's lists (isslCreateIndex.cpp:225-233)
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(), ids, N, 0, 24, st));
+        k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, d->tripleRes.as<uint16_t>() + t * stride);
+        k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
+                                                                                d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));
+    for (DBuf *b : {&keysIn, &keysOut, &idsIn, &tmp}) b->release();
+    d->tv.res = d->tripleRes.as<uint16_t>();
+    d->tv.ids = d->tripleIds.as<uint32_t>();
+    d->tv.offs = d->tripleOffs.as<uint32_t>();
+    d->tv.stride = stride;
+    d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4);
+    return ISSL_OK;
+}
+
 static int new_device(int cuda_device, issl_device **out)
 {
     CKR(select_device(cuda_device));
@@ -186,6 +259,10 @@ static int new_device(int cuda_device, issl_device **out)
     if (const char *e = getenv("ISSL_MAX_GROUP")) {
         const long v = atol(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
+    }
+    if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
+        const long v = atol(e);
+        if (v >= -1 && v <= 7) d->tripleMaxDist = (int)v;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&d->hCounters, 8 * sizeof(unsigned long long));
@@ -208,7 +285,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin})
+                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
     if (d->hCounters) cudaFreeHost(d->hCounters);
@@ -227,6 +304,7 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
     CKR(choose_layout(ix->info, layout, &lay));
     issl_device *d = nullptr;
     CKR(new_device(cuda_device, &d));
+    d->layoutAuto = (layout == ISSL_LAYOUT_AUTO);
     auto fail = [&](int rc) { issl_device_destroy(d); return rc; };
 
     int rc = init_geometry(d, ix->info, lay, ix->sizes);
@@ -303,6 +381,7 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
         return fail(issl_set_error(ISSL_ERR_UNSUPPORTED,
                                    "Error reading index: %llu list entries violate the isslCreateIndex invariants "
                                    "(id range, list membership, ascending ids or occurrence counts)", bad));
+    if ((rc = build_triple(d)) != ISSL_OK) return fail(rc);
     *out = d;
     return ISSL_OK;
 }
@@ -426,7 +505,7 @@ static int collapse_and_build(issl_device *d, int layout, const uint64_t *dKeys,
         CK(cudaStreamSynchronize(st));   // vs[] is a stack buffer
     }
     for (DBuf *b : {&values, &valuesSorted, &idsTmp, &idsSorted, &hist, &valueStart, &tmp}) b->release();
-    return ISSL_OK;
+    return build_triple(d);
 }
 
 extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uint64_t uniform_sites,
@@ -445,6 +524,7 @@ extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_
     CKR(choose_layout(f, layout, &lay));
     issl_device *d = nullptr;
     CKR(new_device(cuda_device, &d));
+    d->layoutAuto = (layout == ISSL_LAYOUT_AUTO);
     DBuf keys, keysAlt;
     int rc = keys.ensure(nRaw * 8);
     if (rc == ISSL_OK) rc = keysAlt.ensure(nRaw * 8);
@@ -478,6 +558,7 @@ int issl_internal_device_from_keys(int cuda_device, int layout, uint64_t *dKeys,
     CKR(choose_layout(f, layout, &lay));
     issl_device *d = nullptr;
     CKR(new_device(cuda_device, &d));
+    d->layoutAuto = (layout == ISSL_LAYOUT_AUTO);
     DBuf alt;   // non-owning view
     alt.p = dKeysAlt; alt.cap = nRaw * 8;
     int rc = build_from_sites(d, lay, dKeys, nRaw, seqLength, sliceWidth, alt);
@@ -513,6 +594,7 @@ extern "C" int issl_device_create_from_text(const char *text, size_t bytes, uint
     CKR(choose_layout(f, layout, &lay));
     issl_device *d = nullptr;
     CKR(new_device(cuda_device, &d));
+    d->layoutAuto = (layout == ISSL_LAYOUT_AUTO);
 
     DBuf sigRaw, flags, dtext[2];
     uint8_t *stage[2] = {nullptr, nullptr};
@@ -567,7 +649,7 @@ extern "C" int issl_device_get_info(const issl_device *d, issl_device_info *out)
     if (!d || !out) return issl_set_error(ISSL_ERR_ARG, "issl_device_get_info: null argument");
     out->cuda_device = d->dev;
     out->layout = d->layout;
-    out->bytes_per_candidate = d->layout == ISSL_LAYOUT_RES32 ? 4 : (d->layout == ISSL_LAYOUT_SIG64 ? 8 : 12);
+    out->bytes_per_candidate = d->layout == ISSL_LAYOUT_TRIPLE ? 2 : d->layout == ISSL_LAYOUT_RES32 ? 4 : (d->layout == ISSL_LAYOUT_SIG64 ? 8 : 12);
     out->hbm_bytes = d->hbmBytes;
     out->list_entries = d->info.sliceCount * d->info.offtargetsCount;
     out->info = d->info;
@@ -662,6 +744,75 @@ struct EventTimer {
 
 }  // namespace
 
+static int ensure_hit_buffers(issl_device *d, uint32_t n)
+{
+    const uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, 384ull * n), 1ull << 28);
+    if (d->hitCap < wantCap && d->hitCap == d->hitCapAuto) {   // first sizing for this batch size (uniform genomes: ~275 survivors per guide)
+        d->hitCap = d->hitCapAuto = wantCap;
+        CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+    }
+    return ISSL_OK;
+}
+
+// ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
+static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint32_t s0, uint32_t ns,
+                       const uint8_t *doneMask, int maxDist, EventTimer &timer, uint64_t *nHitsOut)
+{
+    unsigned long long *dc = d->counters.as<unsigned long long>();
+    if (d->visitsDist != maxDist) {   // the visit table depends on maxDist only
+        std::vector<uint32_t> v(issl_triple_visits(maxDist, nullptr, 0, nullptr));
+        issl_triple_visits(maxDist, v.data(), v.size(), d->waveStart);
+        CKR(d->visits.ensure(std::max<size_t>(1, v.size()) * 4));
+        CK(cudaMemcpyAsync(d->visits.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // v is a local
+        d->visitsDist = maxDist;
+    }
+    const uint32_t v0 = d->waveStart[s0], v1 = d->waveStart[s0 + ns], nv = v1 - v0;
+    CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
+    k_wave_candidates<<<blocks_for((uint64_t)n * ns, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
+    d->stats.launches += 1;
+    *nHitsOut = 0;
+    if (nv) {
+        // enough CTAs to fill the machine even for a handful of guides
+        constexpr uint32_t kOctets = kTripleThreads / 8;
+        uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
+        chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
+        chunks = std::min<uint32_t>(chunks, 65535u);
+        for (;;) {
+            CKR(ensure_hit_buffers(d, n));
+            CK(cudaMemsetAsync(dc + 1, 0, 8, st));
+            CK(cudaMemsetAsync(dc + 4, 0, 16, st));
+            TripleArgs a;
+            a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<uint32_t>() + v0;
+            a.nVisits = nv; a.visitsPerCta = (nv + chunks - 1) / chunks;
+            a.hitKeys = d->keysA.as<uint64_t>(); a.hitCount = dc + 1; a.hitCap = d->hitCap; a.streamed = dc + 4;
+            a.maxDist = maxDist;
+            cudaEvent_t e0, e1;
+            CKR(timer.get(&e0)); CKR(timer.get(&e1));
+            timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
+            CK(cudaEventRecord(e0, st));
+            k_scan_triple<<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1, st));
+            CK(cudaMemcpyAsync(d->hCounters, dc, 6 * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            d->stats.scan_launches += 1;
+            d->stats.launches += 1;
+            if (d->hCounters[1] <= d->hitCap) break;
+            d->hitCap = d->hCounters[1] + d->hCounters[1] / 4;
+            CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+        }
+        *nHitsOut = d->hCounters[1];
+        d->stats.streamed += d->hCounters[4];
+        d->stats.bucket_visits += d->hCounters[5];
+    } else {
+        CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    d->stats.candidates += d->hCounters[0];
+    return ISSL_OK;
+}
+
 // one batch of <= maxBatch guides, already resident at dGuides
 static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint64_t guideBase, int maxDist,
                        double threshold, int method, double *dMit, double *dCfd, HitSink *sink, EventTimer &timer)
@@ -693,6 +844,12 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         const uint64_t pairs = (uint64_t)n * ns;
         const uint8_t *doneMask = checkExit ? d->done.as<uint8_t>() : nullptr;
 
+        const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= d->tripleMaxDist;
+        const int posBits = useTriple ? kTripleKeyBits : d->pbits;
+        uint64_t nHits = 0;
+        if (useTriple) {
+            CKR(triple_wave(d, st, dGuides, n, s0, ns, doneMask, maxDist, timer, &nHits));
+        } else {
         // group the (guide, slice) pairs by the list they select: radix sort of (list id, guide index)
         const uint32_t nLists = (uint32_t)d->nLists;
         CKR(d->pairKeys.ensure(pairs * 4)); CKR(d->pairVals.ensure(pairs * 4));
@@ -722,7 +879,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         const uint32_t chunk = (uint32_t)chunk64;
 
         uint32_t maxGroup = d->maxGroup;
-        if (maxGroup > kMaxGroup && !(d->layout == ISSL_LAYOUT_RES32 && maxDist <= 7)) maxGroup = kMaxGroup;
+        if (maxGroup > kMaxGroup && !(d->iv.layout == ISSL_LAYOUT_RES32 && maxDist <= 7)) maxGroup = kMaxGroup;
         CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
         k_group_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
                                                              maxGroup, d->pairCounts.as<uint32_t>(), dc + 4);
@@ -742,13 +899,8 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         d->stats.launches += 4;
 
         // K1 (re-run with a larger survivor buffer if it overflowed)
-        uint64_t nHits = 0;
         for (;;) {
-            const uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, 384ull * n), 1ull << 28);
-            if (d->hitCap < wantCap && d->hitCap == d->hitCapAuto) {   // first sizing for this batch size (uniform genomes: ~275 survivors per guide)
-                d->hitCap = d->hitCapAuto = wantCap;
-                CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
-            }
+            CKR(ensure_hit_buffers(d, n));
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
             ScanArgs a;
             a.iv = d->iv; a.items = d->items.as<ScanItem>(); a.guides = dGuides;
@@ -758,8 +910,8 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
             CK(cudaEventRecord(e0, st));
-            if (d->layout == ISSL_LAYOUT_RES32) k_scan<kRes32><<<nItems, kScanThreads, 0, st>>>(a);
-            else if (d->layout == ISSL_LAYOUT_SIG64) k_scan<kSig64><<<nItems, kScanThreads, 0, st>>>(a);
+            if (d->iv.layout == ISSL_LAYOUT_RES32) k_scan<kRes32><<<nItems, kScanThreads, 0, st>>>(a);
+            else if (d->iv.layout == ISSL_LAYOUT_SIG64) k_scan<kSig64><<<nItems, kScanThreads, 0, st>>>(a);
             else k_scan<kGather><<<nItems, kScanThreads, 0, st>>>(a);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
@@ -772,25 +924,26 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             d->hitCap = nHits + nHits / 4;
             CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
         }
+        }   // list scan
         if (nHits == 0) continue;
 
         // canonical order: sort keys (guide, position)
         int gbits = 1;
         while ((1ull << gbits) < n) gbits++;
         cub::DoubleBuffer<uint64_t> db(d->keysA.as<uint64_t>(), d->keysB.as<uint64_t>());
-        tb = 0;
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, nHits, 0, d->pbits + gbits, st));
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, nHits, 0, posBits + gbits, st));
         CKR(d->sortTemp.ensure(tb));
-        CK(cub::DeviceRadixSort::SortKeys(d->sortTemp.p, tb, db, nHits, 0, d->pbits + gbits, st));
+        CK(cub::DeviceRadixSort::SortKeys(d->sortTemp.p, tb, db, nHits, 0, posBits + gbits, st));
         const uint64_t *sorted = db.Current();
-        d->stats.launches += (uint64_t)((d->pbits + gbits + 7) / 8) * 2 + 1;   // histogram + onesweep passes (approximate)
+        d->stats.launches += (uint64_t)((posBits + gbits + 7) / 8) * 2 + 1;   // histogram + onesweep passes (approximate)
 
         CKR(d->contribMit.ensure(nHits * 8)); CKR(d->contribCfd.ensure(nHits * 8));
         if (sink) { CKR(d->hitId.ensure(nHits * 4)); CKR(d->hitDist.ensure(nHits * 4)); CKR(d->hitOcc.ensure(nHits * 4)); }
         ContribArgs c;
         c.iv = d->iv; c.keys = sorted; c.nHits = nHits; c.guides = dGuides;
         c.mitMasks = d->mitMasks.as<uint64_t>(); c.mitScores = d->mitScores.as<double>(); c.mitCount = d->mitCount;
-        c.pbits = d->pbits; c.calcMit = calcMit; c.calcCfd = calcCfd;
+        c.pbits = posBits; c.idInKey = useTriple ? 1 : 0; c.calcMit = calcMit; c.calcCfd = calcCfd;
         c.contribMit = d->contribMit.as<double>(); c.contribCfd = d->contribCfd.as<double>();
         c.hitId = sink ? d->hitId.as<uint32_t>() : nullptr;
         c.hitDist = sink ? d->hitDist.as<int32_t>() : nullptr;
@@ -799,7 +952,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
 
         AccumArgs ac;
         ac.keys = sorted; ac.nHits = nHits; ac.contribMit = c.contribMit; ac.contribCfd = c.contribCfd;
-        ac.nGuides = n; ac.pbits = d->pbits; ac.method = method; ac.checkExit = checkExit; ac.maximumSum = maximumSum;
+        ac.nGuides = n; ac.pbits = posBits; ac.method = method; ac.checkExit = checkExit; ac.maximumSum = maximumSum;
         ac.totMit = d->totMit.as<double>(); ac.totCfd = d->totCfd.as<double>(); ac.done = d->done.as<uint8_t>();
         ac.scoredEnd = sink ? d->scoredEnd.as<uint64_t>() : nullptr;
         ac.segBegin = sink ? d->segBegin.as<uint64_t>() : nullptr;

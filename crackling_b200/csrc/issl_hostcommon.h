@@ -62,6 +62,7 @@ inline int layout_from_env()
     if (!strcmp(e, "res32")) return ISSL_LAYOUT_RES32;
     if (!strcmp(e, "sig64")) return ISSL_LAYOUT_SIG64;
     if (!strcmp(e, "gather")) return ISSL_LAYOUT_GATHER;
+    if (!strcmp(e, "triple")) return ISSL_LAYOUT_TRIPLE;
     return ISSL_LAYOUT_AUTO;
 }
 

@@ -554,6 +554,7 @@ struct ContribArgs {
     const double *mitScores;
     uint32_t mitCount;
     int pbits;
+    int idInKey;              // TRIPLE: the key's low 32 bits are the site id itself (bits 32..34: slice), not a list position
     int calcMit, calcCfd;
     double *contribMit;       // [nHits]
     double *contribCfd;       // [nHits]
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(256) k_contrib(const ContribArgs a)
     const uint64_t key = a.keys[j];
     const uint64_t pos = key & ((1ull << a.pbits) - 1ull);
     const uint64_t g = a.guides[key >> a.pbits];
-    const uint32_t id = a.iv.ids[pos];
+    const uint32_t id = a.idInKey ? (uint32_t)pos : a.iv.ids[pos];
     const uint64_t site = a.iv.sig[id];
     const uint32_t occ = a.iv.occ[id];
     const uint64_t mm = mismatch_mask64(g ^ site);

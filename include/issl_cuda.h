@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ISSL_CUDA_ABI_VERSION 1
+#define ISSL_CUDA_ABI_VERSION 2
 
 typedef enum issl_status {
     ISSL_OK = 0,
@@ -66,11 +66,18 @@ typedef struct issl_info {
 
 /* How the index lies in HBM (DESIGN.md "Data layout"). */
 typedef enum issl_layout {
-    ISSL_LAYOUT_AUTO = 0,     /* RES32 when the file allows it, else SIG64                  */
+    ISSL_LAYOUT_AUTO = 0,     /* TRIPLE when it applies and fits, else RES32 when the file allows it, else SIG64 */
     ISSL_LAYOUT_RES32 = 1,    /* slice lists hold 32-bit residual signatures inline: 4 B / candidate */
     ISSL_LAYOUT_SIG64 = 2,    /* slice lists hold the 64-bit signature inline: 8 B / candidate      */
-    ISSL_LAYOUT_GATHER = 3    /* slice lists hold 32-bit ids, signatures gathered: 4 + 8 B / candidate
+    ISSL_LAYOUT_GATHER = 3,   /* slice lists hold 32-bit ids, signatures gathered: 4 + 8 B / candidate
                                  (the layout BASELINE.json's north_star describes; kept for comparison) */
+    ISSL_LAYOUT_TRIPLE = 4    /* seqLength 20, sliceWidth 8 only.  RES32 plus, for each of the 10 slice triples,
+                                 the sites bucketed by their three slice values (2^24 buckets, ascending id inside)
+                                 with the remaining 16 signature bits inline: every slice list sub-divided by two
+                                 more slices.  A guide then reads only the sub-buckets that can hold a site within
+                                 maxDist (issl_triple_visits) -- 2 B per entry actually read, ~250x fewer entries
+                                 than the whole lists at maxDist 4 -- with identical results.
+                                 Used for maxDist <= 6; larger distances take the RES32 path. */
 } issl_layout;
 
 typedef struct issl_device_info {
@@ -92,7 +99,9 @@ typedef struct issl_stats {
     double scan_ms;            /* device time of the scan kernel(s), CUDA events on the call's stream */
     double total_ms;           /* device time of the whole call (setup + scan + sort + score)      */
     uint64_t early_exits;      /* guides that stopped before the last slice (threshold > 0)        */
-    uint64_t streamed;         /* list entries actually read from HBM (each chunk once per guide GROUP) */
+    uint64_t streamed;         /* list entries actually read from HBM (each chunk once per guide GROUP;
+                                  TRIPLE: entries of the sub-buckets visited)                        */
+    uint64_t bucket_visits;    /* TRIPLE: (guide, sub-bucket) visits = bucket-offset pairs read; 0 otherwise */
 } issl_stats;
 
 typedef struct issl_index issl_index;     /* a parsed .issl image in host memory          */
@@ -232,6 +241,16 @@ double issl_local_mit_score(uint64_t mask, size_t seqLength);
  * entries written (<= cap) and the header's scoresCount through *scoresCount. */
 size_t issl_mit_table(size_t seqLength, size_t sliceWidth, uint64_t *masks, double *scores, size_t cap,
                       uint64_t *scoresCount);
+
+/* ISSL_LAYOUT_TRIPLE: the sub-buckets one guide has to read for a given maxDist, as XOR patterns relative to
+ * the guide's own bucket.  Entry = pattern24 | triple << 24 | budget << 28: `triple` indexes the slice triples
+ * (a<b<c) of {0..4} in lexicographic order; pattern24 is XORed onto the guide's bucket key
+ * (slice a | slice b << 8 | slice c << 16); an entry of that bucket can only be a hit if its 16 residual bits
+ * differ from the guide's in at most `budget` bases.  Entries are ordered by the lowest slice on which their hits
+ * match the guide exactly -- the slice through which the reference meets them first
+ * (isslScoreOfftargets.cpp:330-390) -- and waveStart[s] .. waveStart[s+1] delimits slice s.
+ * Returns the number of entries (written up to cap); out may be NULL to size the table.  0 <= maxDist <= 7. */
+size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6]);
 
 const char *issl_last_error(void);
 int issl_abi_version(void);

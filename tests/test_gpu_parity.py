@@ -32,7 +32,8 @@ def fmt_stdout(guides_packed, mit, cfd, seq_length=20):
 def layouts_for(case):
     w, L = case.slice_width, case.seq_length
     res32 = w % 2 == 0 and 2 * L - min(w, 8) <= 32
-    return (["res32"] if res32 else []) + ["sig64", "gather"]
+    triple = w == 8 and L == 20
+    return (["triple"] if triple else []) + (["res32"] if res32 else []) + ["sig64", "gather"]
 
 
 _devices = {}
@@ -160,7 +161,7 @@ def test_guide_groups_and_bitsliced_path(max_group, w):
     guides = np.array(guides, dtype=np.uint64)
     os.environ["ISSL_MAX_GROUP"] = str(max_group)
     try:
-        dev = cb.Device.from_index(cb.Index(img), 0, "auto")
+        dev = cb.Device.from_index(cb.Index(img), 0, "res32")
     finally:
         del os.environ["ISSL_MAX_GROUP"]
     for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("avg", 50, 3), ("or", 0, 0), ("and", 0, 5), ("and", 0, 6),
@@ -183,6 +184,55 @@ def test_guide_groups_and_bitsliced_path(max_group, w):
     _, _, hits = dev.score_hits(guides, 4, 0, "and")
     want = oracle.score(img, guides, 4, 0, "and", threads=1, want_hits=True)["hits"]
     assert np.array_equal(hits, np.stack([want[k].astype(np.int64) for k in ("guide", "id", "dist", "occ")], axis=1))
+    dev.close()
+
+
+@pytest.mark.parametrize("triple_max", [6, 3])
+def test_triple_layout_sub_bucket_scan(triple_max):
+    """ISSL_LAYOUT_TRIPLE reads only the sub-buckets that can hold a hit (issl_triple_visits) and must still give
+    the oracle's exact answer -- scores bit-identical, hit tuples identical including order, early exits at the same
+    survivor -- on dense families (many hits per guide, many sites per bucket), for every maxDist it serves, and
+    hand over to the RES32 list scan above ISSL_TRIPLE_MAXDIST."""
+    text = td.make_offtargets(41, n_random=150_000, n_families=40, family_size=500, max_sub_rate=0.15)
+    img = oracle.create_index(text, 20, 8)
+    rng = np.random.default_rng(42)
+    roots = td.pack_guides(td.make_guides(43, text, n=60, frac_exact=1.0, frac_mut=0.0))
+    guides = []
+    for r in roots:
+        for _ in range(20):
+            g = int(r)
+            for pos in rng.choice(20, size=int(rng.integers(0, 5)), replace=False):
+                g ^= int(rng.integers(1, 4)) << (2 * int(pos))
+            guides.append(g)
+    guides = np.concatenate([np.array(guides, dtype=np.uint64), rng.integers(0, 1 << 40, 300, dtype=np.uint64)])
+    os.environ["ISSL_TRIPLE_MAXDIST"] = str(triple_max)
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, "triple")
+    finally:
+        del os.environ["ISSL_TRIPLE_MAXDIST"]
+    assert dev.info["layout"] == cb.LAYOUTS["triple"]
+    for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("avg", 50, 3), ("or", 0, 0), ("mit", 0, 1), ("cfd", 0, 2),
+                            ("and", 0, 5), ("or", 30, 5), ("and", 0, 6), ("and", 60, 6), ("mit", 0, 7), ("cfd", 0, 9)):
+        want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
+        mit, cfd = dev.score(guides, md, thr, method)
+        if method != "cfd":
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (method, thr, md)
+        if method != "mit":
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (method, thr, md)
+        st = dev.stats
+        if thr == 0:
+            assert st["candidates"] == int(want["candidates"].sum())
+        if md <= triple_max:
+            visits, _ = cb.triple_visits(md)
+            assert st["bucket_visits"] > 0 and st["streamed"] < st["candidates"]
+            if thr == 0:
+                assert st["bucket_visits"] == visits.size * guides.size
+        else:
+            assert st["bucket_visits"] == 0
+    for md, thr in ((4, 0), (5, 0), (4, 75), (2, 0)):
+        _, _, hits = dev.score_hits(guides, md, thr, "and")
+        want = oracle.score(img, guides, md, thr, "and", threads=1, want_hits=True)["hits"]
+        assert np.array_equal(hits, np.stack([want[k].astype(np.int64) for k in ("guide", "id", "dist", "occ")], axis=1)), (md, thr)
     dev.close()
 
 
@@ -241,7 +291,7 @@ def test_corrupt_lists_are_refused():
     assert e.value.code == 6
 
 
-@pytest.mark.parametrize("w,layout", [(8, "res32"), (8, "gather"), (10, "res32"), (4, "sig64")])
+@pytest.mark.parametrize("w,layout", [(8, "triple"), (8, "res32"), (8, "gather"), (10, "res32"), (4, "sig64")])
 def test_synthetic_index_is_what_the_reference_builder_would_write(w, layout, tmp_path):
     dev = cb.Device.synthetic(0, layout, seed=5, uniform_sites=30_000, families=8, family_size=400, max_sub_rate=0.1,
                               slice_width=w)

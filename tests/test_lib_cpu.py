@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libissl_cuda.so does not export {n}"
     assert set(L._issl_symbols) == set(names), "binding.py and issl_cuda.h disagree"
-    assert L.issl_abi_version() == 1
+    assert L.issl_abi_version() == 2
 
 
 def test_pack_unpack_and_methods():
@@ -128,3 +128,74 @@ def test_product_never_touches_the_oracle():
             assert "issl_oracle" not in text and "from oracle" not in text and "import oracle" not in text, path
     out = subprocess.run(["ldd", str(cb.lib_path())], stdout=subprocess.PIPE).stdout.decode()
     assert "oracle" not in out
+
+
+# --- ISSL_LAYOUT_TRIPLE: the sub-bucket visit table (host arithmetic, no GPU) -------------------------------
+
+_TRIPLES = [(0, 1, 2), (0, 1, 3), (0, 1, 4), (0, 2, 3), (0, 2, 4), (0, 3, 4), (1, 2, 3), (1, 2, 4), (1, 3, 4), (2, 3, 4)]
+_HAM4 = np.array([sum(1 for f in range(4) if (x >> (2 * f)) & 3) for x in range(256)])
+
+
+def _resp(E):
+    E = sorted(E)
+    rest = [s for s in range(5) if s not in E]
+    return tuple(sorted((E + rest)[:3] if len(E) < 3 else E[:3]))
+
+
+def test_triple_visit_table_counts():
+    # 10 exact triples; + 10 pairs x {x: 1 <= ham4(x) <= D-2}; + 5 singles x {(xj, xk): ham4 sum <= D-2}
+    for d, want in ((-1, 0), (0, 10), (2, 10), (3, 130), (4, 1390), (5, 8950), (6, 37300)):
+        v, wave = cb.triple_visits(d)
+        assert v.size == want and wave[0] == 0 and wave[5] == want
+        assert np.unique(v & 0x0FFFFFFF).size == v.size, "a bucket would be read twice"
+        assert np.all(np.diff(wave.astype(np.int64)) >= 0)
+
+
+@pytest.mark.parametrize("max_dist", [0, 1, 3, 4, 5])
+def test_triple_visits_cover_every_reference_hit_exactly_once(max_dist):
+    """Brute force over planted neighbourhoods: the sites found through the visit table, filtered by the
+    kernel's rule resp(E) == triple, are exactly the sites the reference scores (in a looked-up list, i.e.
+    some slice matches exactly, and dist <= maxDist; isslScoreOfftargets.cpp:330-390), each exactly once and
+    attributed to the lowest matching slice."""
+    rng = np.random.default_rng(100 + max_dist)
+    visits, wave = cb.triple_visits(max_dist)
+    by_wave = np.searchsorted(wave[1:], np.arange(visits.size), side="right")
+
+    def slices(s):
+        return [(s >> (8 * k)) & 0xFF for k in range(5)]
+
+    for g in (int(x) for x in rng.integers(0, 1 << 40, 4)):
+        sites = {g}
+        for _ in range(1500):
+            s = g
+            for p in rng.choice(20, int(rng.integers(0, 8)), replace=False):
+                s ^= int(rng.integers(1, 4)) << (2 * int(p))
+            sites.add(s)
+        gs = slices(g)
+        buckets = [dict() for _ in _TRIPLES]
+        for s in sites:
+            sl = slices(s)
+            for t, T in enumerate(_TRIPLES):
+                buckets[t].setdefault(sl[T[0]] | sl[T[1]] << 8 | sl[T[2]] << 16, []).append(s)
+        want = {}
+        for s in sites:
+            sl = slices(s)
+            E = [k for k in range(5) if sl[k] == gs[k]]
+            if E and sum(_HAM4[a ^ b] for a, b in zip(sl, gs)) <= max_dist:
+                want[s] = min(E)
+        got = {}
+        for e, w in zip(visits.tolist(), by_wave.tolist()):
+            t, budget, pat = (e >> 24) & 15, e >> 28, e & 0xFFFFFF
+            T = _TRIPLES[t]
+            comp = [k for k in range(5) if k not in T]
+            key = (gs[T[0]] | gs[T[1]] << 8 | gs[T[2]] << 16) ^ pat
+            for s in buckets[t].get(key, []):
+                sl = slices(s)
+                if sum(_HAM4[sl[c] ^ gs[c]] for c in comp) > budget:
+                    continue   # the kernel's fast-path filter must never drop a true hit (checked by got == want)
+                E = [k for k in range(5) if sl[k] == gs[k]]
+                if E and sum(_HAM4[a ^ b] for a, b in zip(sl, gs)) <= max_dist and _resp(E) == T:
+                    assert s not in got, "hit produced twice"
+                    assert min(E) == w, "hit attributed to the wrong slice wave"
+                    got[s] = w
+        assert got == want
