@@ -97,18 +97,6 @@ static int upload_constants()
 {
     CK(cudaMemcpyToSymbol(c_cfdPos, ISSL_CFD_POS, sizeof(double) * 320));
     CK(cudaMemcpyToSymbol(c_cfdPam, ISSL_CFD_PAM, sizeof(double) * 16));
-    // resp(E) of issl_triple_visits: three lowest slices of E, completed with the lowest slices outside E
-    uint8_t resp[32];
-    for (uint32_t E = 0; E < 32; E++) {
-        int pick[3], np = 0;
-        for (int s = 0; s < 5 && np < 3; s++) if (E & (1u << s)) pick[np++] = s;
-        for (int s = 0; s < 5 && np < 3; s++) if (!(E & (1u << s))) pick[np++] = s;
-        std::sort(pick, pick + 3);
-        static const int T[10][3] = {{0, 1, 2}, {0, 1, 3}, {0, 1, 4}, {0, 2, 3}, {0, 2, 4}, {0, 3, 4}, {1, 2, 3}, {1, 2, 4}, {1, 3, 4}, {2, 3, 4}};
-        resp[E] = 0xFF;
-        for (int t = 0; t < 10; t++) if (T[t][0] == pick[0] && T[t][1] == pick[1] && T[t][2] == pick[2]) resp[E] = (uint8_t)t;
-    }
-    CK(cudaMemcpyToSymbol(c_tripleResp, resp, sizeof resp));
     return ISSL_OK;
 }
 
@@ -760,10 +748,21 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
 {
     unsigned long long *dc = d->counters.as<unsigned long long>();
     if (d->visitsDist != maxDist) {   // the visit table depends on maxDist only
-        std::vector<uint32_t> v(issl_triple_visits(maxDist, nullptr, 0, nullptr));
-        issl_triple_visits(maxDist, v.data(), v.size(), d->waveStart);
-        CKR(d->visits.ensure(std::max<size_t>(1, v.size()) * 4));
-        CK(cudaMemcpyAsync(d->visits.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice, st));
+        std::vector<uint32_t> raw(issl_triple_visits(maxDist, nullptr, 0, nullptr));
+        issl_triple_visits(maxDist, raw.data(), raw.size(), d->waveStart);
+        static const uint8_t slices[10][5] = {{0, 1, 2, 3, 4}, {0, 1, 3, 2, 4}, {0, 1, 4, 2, 3}, {0, 2, 3, 1, 4}, {0, 2, 4, 1, 3},
+                                              {0, 3, 4, 1, 2}, {1, 2, 3, 0, 4}, {1, 2, 4, 0, 3}, {1, 3, 4, 0, 2}, {2, 3, 4, 0, 1}};
+        std::vector<TripleVisit> v(raw.size());
+        for (size_t i = 0; i < raw.size(); i++) {
+            const uint32_t t = (raw[i] >> 24) & 15u;
+            uint32_t exact = 0;   // slices of the triple on which the bucket agrees with the guide
+            for (int k = 0; k < 3; k++)
+                if (((raw[i] >> (8 * k)) & 0xFFu) == 0) exact |= 1u << slices[t][k];
+            v[i].x = raw[i];
+            v[i].y = exact | ((uint32_t)slices[t][3] << 8) | ((uint32_t)slices[t][4] << 12);
+        }
+        CKR(d->visits.ensure(std::max<size_t>(1, v.size()) * sizeof(TripleVisit)));
+        CK(cudaMemcpyAsync(d->visits.p, v.data(), v.size() * sizeof(TripleVisit), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));   // v is a local
         d->visitsDist = maxDist;
     }
@@ -783,7 +782,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
             CK(cudaMemsetAsync(dc + 4, 0, 16, st));
             TripleArgs a;
-            a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<uint32_t>() + v0;
+            a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<TripleVisit>() + v0;
             a.nVisits = nv; a.visitsPerCta = (nv + chunks - 1) / chunks;
             a.hitKeys = d->keysA.as<uint64_t>(); a.hitCount = dc + 1; a.hitCap = d->hitCap; a.streamed = dc + 4;
             a.maxDist = maxDist;
