@@ -21,7 +21,7 @@ $(LIBDIR)/issl_host.o: $(CSRC)/issl_host.cpp $(CSRC)/issl_internal.h include/iss
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) -c -o $@ $<
 
-$(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_device_common.cuh $(CSRC)/issl_kernels.cuh $(CSRC)/issl_internal.h $(CSRC)/cfd_tables.h include/issl_cuda.h
+$(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_device_common.cuh $(CSRC)/issl_kernels.cuh $(CSRC)/issl_triple.cuh $(CSRC)/issl_internal.h $(CSRC)/cfd_tables.h include/issl_cuda.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o $@ $< 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 

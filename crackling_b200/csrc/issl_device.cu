@@ -50,9 +50,11 @@ struct issl_device {
     uint32_t maxGroup = kBigGroup;   // ISSL_MAX_GROUP: 32 bit-sliced blocks + register groups (default), 8/4/2 register groups only, 1 no list reuse
 
     // ISSL_LAYOUT_TRIPLE
-    DBuf tripleRes, tripleIds, tripleOffs, visits;
+    DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt;
+    DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
+    bool tripleFuse = true;          // ISSL_TRIPLE_FUSE=0: survivors go through the global sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
     int visitsDist = -100;           // maxDist the resident visit table was built for
     uint32_t waveStart[6] = {0, 0, 0, 0, 0, 0};
@@ -97,6 +99,7 @@ static int upload_constants()
 {
     CK(cudaMemcpyToSymbol(c_cfdPos, ISSL_CFD_POS, sizeof(double) * 320));
     CK(cudaMemcpyToSymbol(c_cfdPam, ISSL_CFD_PAM, sizeof(double) * 16));
+    CK(cudaMemcpyToSymbol(g_cfdPos, ISSL_CFD_POS, sizeof(double) * 320));
     return ISSL_OK;
 }
 
@@ -185,7 +188,30 @@ static int upload_mit_table(issl_device *d)
         CK(cudaMemcpyAsync(d->mitScores.p, d->hMitScores.data(), d->mitCount * 8ull, cudaMemcpyHostToDevice, d->stream));
     }
     d->hbmBytes += d->mitCount * 16ull;
+    if (d->info.seqLength <= 20) {
+        // dense copy: index = set of mismatching positions, 0.0 where the file has no entry (ref :394)
+        std::vector<double> dense(1u << 20, 0.0);
+        for (size_t k = 0; k < d->hMitMasks.size(); k++) {
+            const uint64_t mk = d->hMitMasks[k];
+            if ((mk & 0xAAAAAAAAAAAAAAAAull) || (mk >> 40)) continue;   // never looked up: masks only carry even bits below 2*seqLength
+            uint32_t idx = 0;
+            for (int p = 0; p < 20; p++) idx |= (uint32_t)((mk >> (2 * p)) & 1ull) << p;
+            dense[idx] = d->hMitScores[k];
+        }
+        CKR(d->mitDense.ensure(dense.size() * 8));
+        CK(cudaMemcpyAsync(d->mitDense.p, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaStreamSynchronize(d->stream));   // dense is a local
+        d->hbmBytes += dense.size() * 8;
+    }
     return ISSL_OK;
+}
+
+static ScoreTables score_tables(const issl_device *d)
+{
+    ScoreTables tb;
+    tb.mitMasks = d->mitMasks.as<uint64_t>(); tb.mitScores = d->mitScores.as<double>(); tb.mitCount = d->mitCount;
+    tb.mitDense = d->mitDense.as<double>();
+    return tb;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,17 +224,31 @@ static int build_triple(issl_device *d)
     cudaStream_t st = d->stream;
     const uint64_t N = d->info.offtargetsCount;
     const uint64_t stride = (N + 64 + 7) / 8 * 8;
-    const uint64_t need = kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + N * 16 + (64ull << 20);
+    // blocked copy of the residuals (issl_triple.cuh): block size from the mean bucket occupancy, so that all but
+    // a few buckets fit; ISSL_TRIPLE_BLOCKS = 0 (off), 32 / 64 / 128 (forced), unset = automatic
+    uint32_t pitch = 0;
+    {
+        const double lambda = (double)N / kTripleBuckets, want = lambda + 4.5 * std::sqrt(lambda);
+        if (lambda >= 2.0) pitch = want <= 31 ? 32 : want <= 63 ? 64 : want <= 127 ? 128 : 0;
+        if (const char *e = getenv("ISSL_TRIPLE_BLOCKS")) {
+            const long v = atol(e);
+            if (v == 0 || v == 32 || v == 64 || v == 128) pitch = (uint32_t)v;
+        }
+    }
     size_t freeB = 0, totalB = 0;
     CK(cudaMemGetInfo(&freeB, &totalB));
-    if (need > freeB) {
-        if (d->layoutAuto) { d->layout = ISSL_LAYOUT_RES32; return ISSL_OK; }
-        return issl_set_error(ISSL_ERR_NOMEM, "layout TRIPLE needs %.1f GB of free HBM, %.1f GB available", need / 1e9, freeB / 1e9);
-    }
+    const uint64_t needBase = kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + N * 16 + (64ull << 20);
+    uint64_t needBlk = (uint64_t)kTripleCount * kTripleBuckets * pitch * 2;
+    if (needBase + needBlk > freeB) { pitch = 0; needBlk = 0; }
+    const uint64_t need = needBase;
     CKR(d->tripleRes.ensure(kTripleCount * stride * 2));
     CKR(d->tripleIds.ensure(kTripleCount * stride * 4));
     CKR(d->tripleOffs.ensure(kTripleCount * (kTripleBuckets + 1ull) * 4));
     CK(cudaMemsetAsync(d->tripleRes.p, 0, kTripleCount * stride * 2, st));
+    if (pitch) {
+        CKR(d->tripleBlk.ensure(needBlk));
+        CK(cudaMemsetAsync(d->tripleBlk.p, 0, needBlk, st));
+    }
     DBuf keysIn, keysOut, idsIn, tmp;
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
     size_t tb = 0;
@@ -223,6 +263,10 @@ static int build_triple(issl_device *d)
         k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, d->tripleRes.as<uint16_t>() + t * stride);
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
+        if (pitch)
+            k_triple_blocks<<<blocks_for(N, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), d->tripleRes.as<uint16_t>() + t * stride,
+                                                               d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull), N, pitch,
+                                                               d->tripleBlk.as<uint16_t>() + (uint64_t)t * kTripleBuckets * pitch);
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(st));
@@ -231,7 +275,9 @@ static int build_triple(issl_device *d)
     d->tv.ids = d->tripleIds.as<uint32_t>();
     d->tv.offs = d->tripleOffs.as<uint32_t>();
     d->tv.stride = stride;
-    d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4);
+    d->tv.blk = pitch ? d->tripleBlk.as<uint16_t>() : nullptr;
+    d->tv.pitch = pitch;
+    d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
     return ISSL_OK;
 }
 
@@ -248,6 +294,7 @@ static int new_device(int cuda_device, issl_device **out)
         const long v = atol(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
     }
+    if (const char *e = getenv("ISSL_TRIPLE_FUSE")) d->tripleFuse = atoi(e) != 0;
     if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
         const long v = atol(e);
         if (v >= -1 && v <= 7) d->tripleMaxDist = (int)v;
@@ -273,7 +320,8 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits})
+                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk,
+                    &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
     if (d->hCounters) cudaFreeHost(d->hCounters);
@@ -743,8 +791,14 @@ static int ensure_hit_buffers(issl_device *d, uint32_t n)
 }
 
 // ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
+struct WaveScoring {   // what k_score_segments needs to finish the guides
+    bool fuse, calcMit, calcCfd, checkExit;
+    int method;
+    double maximumSum;
+};
+
 static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint32_t s0, uint32_t ns,
-                       const uint8_t *doneMask, int maxDist, EventTimer &timer, uint64_t *nHitsOut)
+                       const uint8_t *doneMask, int maxDist, const WaveScoring &ws, EventTimer &timer, uint64_t *nHitsOut)
 {
     unsigned long long *dc = d->counters.as<unsigned long long>();
     if (d->visitsDist != maxDist) {   // the visit table depends on maxDist only
@@ -773,27 +827,35 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     *nHitsOut = 0;
     if (nv) {
         // enough CTAs to fill the machine even for a handful of guides
-        constexpr uint32_t kOctets = kTripleThreads / 8;
+        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 8) : kTripleThreads / 8;   // lane groups per CTA
         uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
         chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
         chunks = std::min<uint32_t>(chunks, 65535u);
+        const bool fuse = ws.fuse && chunks == 1;   // per-guide key segments need all hits of a guide in one CTA
+        if (fuse) { CKR(d->segOff.ensure(n * 8ull)); CKR(d->segCnt.ensure(n * 4ull)); }
         for (;;) {
             CKR(ensure_hit_buffers(d, n));
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
-            CK(cudaMemsetAsync(dc + 4, 0, 16, st));
+            CK(cudaMemsetAsync(dc + 4, 0, 24, st));
+            if (fuse) CK(cudaMemsetAsync(d->segCnt.p, 0, n * 4ull, st));
             TripleArgs a;
             a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<TripleVisit>() + v0;
             a.nVisits = nv; a.visitsPerCta = (nv + chunks - 1) / chunks;
             a.hitKeys = d->keysA.as<uint64_t>(); a.hitCount = dc + 1; a.hitCap = d->hitCap; a.streamed = dc + 4;
             a.maxDist = maxDist;
+            a.segOff = fuse ? d->segOff.as<uint64_t>() : nullptr; a.segCnt = fuse ? d->segCnt.as<uint32_t>() : nullptr;
+            a.overflowGuides = dc + 6;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
             CK(cudaEventRecord(e0, st));
-            k_scan_triple<<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            if (d->tv.pitch == 32) k_scan_triple_blocked<4><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            else if (d->tv.pitch == 64) k_scan_triple_blocked<8><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            else if (d->tv.pitch == 128) k_scan_triple_blocked<16><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            else k_scan_triple<<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
-            CK(cudaMemcpyAsync(d->hCounters, dc, 6 * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(d->hCounters, dc, 7 * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             d->stats.scan_launches += 1;
             d->stats.launches += 1;
@@ -804,6 +866,20 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         *nHitsOut = d->hCounters[1];
         d->stats.streamed += d->hCounters[4];
         d->stats.bucket_visits += d->hCounters[5];
+        if (fuse && d->hCounters[6] == 0 && *nHitsOut) {
+            // every guide's hits lie in its own segment: finish them there, nothing is left for the global tail
+            SegmentArgs sa;
+            sa.keys = d->keysA.as<uint64_t>(); sa.segOff = d->segOff.as<uint64_t>(); sa.segCnt = d->segCnt.as<uint32_t>();
+            sa.guides = dGuides; sa.sig = d->iv.sig; sa.occ = d->iv.occ; sa.tb = score_tables(d);
+            sa.calcMit = ws.calcMit; sa.calcCfd = ws.calcCfd; sa.method = ws.method; sa.checkExit = ws.checkExit;
+            sa.maximumSum = ws.maximumSum;
+            sa.totMit = d->totMit.as<double>(); sa.totCfd = d->totCfd.as<double>(); sa.done = d->done.as<uint8_t>();
+            k_score_segments<<<n, kTripleThreads, 0, st>>>(sa);
+            CK(cudaGetLastError());
+            d->stats.launches += 1;
+            d->stats.hits += *nHitsOut;
+            *nHitsOut = 0;
+        }
     } else {
         CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -847,7 +923,10 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         const int posBits = useTriple ? kTripleKeyBits : d->pbits;
         uint64_t nHits = 0;
         if (useTriple) {
-            CKR(triple_wave(d, st, dGuides, n, s0, ns, doneMask, maxDist, timer, &nHits));
+            WaveScoring ws;
+            ws.fuse = sink == nullptr && d->tripleFuse; ws.calcMit = calcMit; ws.calcCfd = calcCfd; ws.checkExit = checkExit;
+            ws.method = method; ws.maximumSum = maximumSum;
+            CKR(triple_wave(d, st, dGuides, n, s0, ns, doneMask, maxDist, ws, timer, &nHits));
         } else {
         // group the (guide, slice) pairs by the list they select: radix sort of (list id, guide index)
         const uint32_t nLists = (uint32_t)d->nLists;
@@ -941,7 +1020,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         if (sink) { CKR(d->hitId.ensure(nHits * 4)); CKR(d->hitDist.ensure(nHits * 4)); CKR(d->hitOcc.ensure(nHits * 4)); }
         ContribArgs c;
         c.iv = d->iv; c.keys = sorted; c.nHits = nHits; c.guides = dGuides;
-        c.mitMasks = d->mitMasks.as<uint64_t>(); c.mitScores = d->mitScores.as<double>(); c.mitCount = d->mitCount;
+        c.tb = score_tables(d);
         c.pbits = posBits; c.idInKey = useTriple ? 1 : 0; c.calcMit = calcMit; c.calcCfd = calcCfd;
         c.contribMit = d->contribMit.as<double>(); c.contribCfd = d->contribCfd.as<double>();
         c.hitId = sink ? d->hitId.as<uint32_t>() : nullptr;

@@ -52,6 +52,8 @@ constexpr int kBigGroupMin = 14;   // a remainder of at least this many guides s
 
 __constant__ double c_cfdPos[320];
 __constant__ double c_cfdPam[16];
+__device__ double g_cfdPos[320];   // the same table in global memory: survivors index it divergently, which the
+                                   // constant cache serialises; through L1 it is one transaction per distinct line
 
 // ------------------------------------------------------------------------------------------------
 // bit helpers
@@ -545,14 +547,73 @@ __global__ void k_group_fill(IndexView iv, const uint32_t *sortedKeys, uint32_t 
 // MIT: table[mismatch mask] * occ when dist > 0 (missing mask -> 0.0, the inserting operator[] at :394).
 // CFD: 1 when dist == 0, else PAM(GG) * prod over mismatching positions < 20, ascending (:411-458); * occ.
 // ------------------------------------------------------------------------------------------------
+// The score tables of one index.  mitDense (seqLength <= 20 only) is the file's table spread over all 2^20
+// position sets -- one load instead of a binary search; absent masks hold 0.0, which is what the reference's
+// inserting operator[] yields for them (:394).
+struct ScoreTables {
+    const uint64_t *mitMasks;   // sorted ascending
+    const double *mitScores;
+    uint32_t mitCount;
+    const double *mitDense;     // [2^20] or nullptr
+};
+
+// bits 0, 2, 4, ... of x packed into the low half
+__device__ __forceinline__ uint32_t compress_even_bits(uint64_t x)
+{
+    x &= 0x5555555555555555ull;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)x;
+}
+
+// local MIT and CFD contribution of one scored site, ref :392-461, both already multiplied by the occurrences
+__device__ __forceinline__ void hit_contrib(const ScoreTables &tb, uint64_t g, uint64_t site, uint32_t occ, int calcMit,
+                                            int calcCfd, double &cm, double &cc, int &dist)
+{
+    const uint64_t mm = mismatch_mask64(g ^ site);
+    dist = __popcll(mm);
+    const double docc = (double)occ;
+    uint32_t m20 = compress_even_bits(mm);   // mismatch flags of positions 0..31, one bit each
+    cm = 0.0; cc = 0.0;
+    if (calcMit && dist > 0) {
+        double s;
+        if (tb.mitDense && (mm >> 40) == 0) {
+            s = __ldg(tb.mitDense + m20);
+        } else {
+            uint32_t lo = 0, hi = tb.mitCount;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (tb.mitMasks[mid] < mm) lo = mid + 1; else hi = mid;
+            }
+            s = (lo < tb.mitCount && tb.mitMasks[lo] == mm) ? tb.mitScores[lo] : 0.0;
+        }
+        cm = __dmul_rn(s, docc);
+    }
+    if (calcCfd) {
+        double cfd = 1.0;
+        if (dist > 0) {
+            cfd = c_cfdPam[10];   // 0b1010 = GG, ref :411
+            m20 &= 0xFFFFFu;      // the reference's loop covers positions 0..19 (:413)
+            while (m20) {
+                const int p = __ffs(m20) - 1;
+                m20 &= m20 - 1;
+                const uint32_t gb = (uint32_t)(g >> (2 * p)) & 3u, ob = (uint32_t)(site >> (2 * p)) & 3u;
+                cfd = __dmul_rn(cfd, __ldg(&g_cfdPos[(p << 4) | (gb << 2) | (ob ^ 3u)]));
+            }
+        }
+        cc = __dmul_rn(cfd, docc);
+    }
+}
+
 struct ContribArgs {
     IndexView iv;
     const uint64_t *keys;     // sorted
     uint64_t nHits;
     const uint64_t *guides;
-    const uint64_t *mitMasks; // sorted ascending
-    const double *mitScores;
-    uint32_t mitCount;
+    ScoreTables tb;
     int pbits;
     int idInKey;              // TRIPLE: the key's low 32 bits are the site id itself (bits 32..34: slice), not a list position
     int calcMit, calcCfd;
@@ -573,35 +634,9 @@ __global__ void __launch_bounds__(256) k_contrib(const ContribArgs a)
     const uint32_t id = a.idInKey ? (uint32_t)pos : a.iv.ids[pos];
     const uint64_t site = a.iv.sig[id];
     const uint32_t occ = a.iv.occ[id];
-    const uint64_t mm = mismatch_mask64(g ^ site);
-    const int dist = __popcll(mm);
-    const double docc = (double)occ;
-
-    double cm = 0.0, cc = 0.0;
-    if (a.calcMit && dist > 0) {
-        uint32_t lo = 0, hi = a.mitCount;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (a.mitMasks[mid] < mm) lo = mid + 1; else hi = mid;
-        }
-        const double s = (lo < a.mitCount && a.mitMasks[lo] == mm) ? a.mitScores[lo] : 0.0;
-        cm = __dmul_rn(s, docc);
-    }
-    if (a.calcCfd) {
-        double cfd = 1.0;
-        if (dist > 0) {
-            cfd = c_cfdPam[10];   // 0b1010 = GG, ref :411
-            uint32_t m20 = 0;     // mismatch flags of positions 0..19, one bit each (ref loop :413)
-            for (int p = 0; p < 20; p++) m20 |= (uint32_t)((mm >> (2 * p)) & 1ull) << p;
-            while (m20) {
-                const int p = __ffs(m20) - 1;
-                m20 &= m20 - 1;
-                const uint32_t gb = (uint32_t)(g >> (2 * p)) & 3u, ob = (uint32_t)(site >> (2 * p)) & 3u;
-                cfd = __dmul_rn(cfd, c_cfdPos[(p << 4) | (gb << 2) | (ob ^ 3u)]);
-            }
-        }
-        cc = __dmul_rn(cfd, docc);
-    }
+    double cm, cc;
+    int dist;
+    hit_contrib(a.tb, g, site, occ, a.calcMit, a.calcCfd, cm, cc, dist);
     a.contribMit[j] = cm;
     a.contribCfd[j] = cc;
     if (a.hitId) { a.hitId[j] = id; a.hitDist[j] = dist; a.hitOcc[j] = occ; }
@@ -638,6 +673,19 @@ __device__ __forceinline__ uint64_t lower_bound_key(const uint64_t *keys, uint64
     return lo;
 }
 
+// the method's early-exit predicate, ref :466-496
+__device__ __forceinline__ bool exit_predicate(int method, double mit, double cfd, double mx)
+{
+    switch (method) {
+    case ISSL_METHOD_AND: return mit > mx && cfd > mx;
+    case ISSL_METHOD_OR:  return mit > mx || cfd > mx;
+    case ISSL_METHOD_AVG: return __ddiv_rn(__dadd_rn(mit, cfd), 2.0) > mx;
+    case ISSL_METHOD_MIT: return mit > mx;
+    case ISSL_METHOD_CFD: return cfd > mx;
+    default: return false;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_accumulate(const AccumArgs a)
 {
     const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -653,16 +701,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const AccumArgs a)
     for (; j < hi && !stop; j++) {
         mit = __dadd_rn(mit, a.contribMit[j]);
         cfd = __dadd_rn(cfd, a.contribCfd[j]);
-        if (a.checkExit) {
-            switch (a.method) {
-            case ISSL_METHOD_AND: stop = (mit > mx && cfd > mx); break;
-            case ISSL_METHOD_OR:  stop = (mit > mx || cfd > mx); break;
-            case ISSL_METHOD_AVG: stop = (__ddiv_rn(__dadd_rn(mit, cfd), 2.0) > mx); break;
-            case ISSL_METHOD_MIT: stop = (mit > mx); break;
-            case ISSL_METHOD_CFD: stop = (cfd > mx); break;
-            default: break;
-            }
-        }
+        if (a.checkExit) stop = exit_predicate(a.method, mit, cfd, mx);
     }
     a.totMit[gi] = mit;
     a.totCfd[gi] = cfd;

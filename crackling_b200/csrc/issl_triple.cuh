@@ -33,7 +33,13 @@ struct TripleView {
     const uint32_t *ids;    // [10][stride] site id per bucket entry
     const uint32_t *offs;   // [10][2^24 + 1] first entry of every bucket
     uint64_t stride;        // entries reserved per triple (multiple of 8, >= N + 64)
+    // blocked copy of res (optional): bucket k of triple t owns the `pitch` 16-bit slots starting at
+    // ((t << 24) | k) * pitch: slot 0 = number of entries (kBlockOverflow: bucket does not fit, use res/offs),
+    // slots 1..count = the residuals.  One aligned read per visit, no offset lookup in front of it.
+    const uint16_t *blk;
+    uint32_t pitch;         // 0 (no blocked copy), 32, 64 or 128
 };
+constexpr uint32_t kBlockOverflow = 0xFFFFu;
 
 __host__ __device__ __forceinline__ uint32_t triple_key(uint64_t sig, uint32_t a, uint32_t b, uint32_t c)
 {
@@ -76,6 +82,20 @@ __global__ void k_triple_offsets(const uint32_t *sortedKeys, uint64_t n, uint32_
     offs[k] = (uint32_t)lo;
 }
 
+// blocked copy of one triple: entry i of the sorted order goes to slot 1 + rank of its bucket's block
+__global__ void k_triple_blocks(const uint32_t *sortedKeys, const uint16_t *res, const uint32_t *offs, uint64_t n,
+                                uint32_t pitch, uint16_t *blk /* this triple's 2^24 blocks, pre-zeroed */)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = sortedKeys[i];
+    const uint32_t start = offs[key], count = offs[key + 1] - start, rank = (uint32_t)i - start;
+    uint16_t *b = blk + (uint64_t)key * pitch;
+    if (count > pitch - 1) { if (rank == 0) b[0] = (uint16_t)kBlockOverflow; return; }
+    if (rank == 0) b[0] = (uint16_t)count;
+    b[1 + rank] = res[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1t: bucket scan.  ref isslScoreOfftargets.cpp:344-390 for one guide, restricted to the buckets
 // that can hold a site within maxDist.
@@ -96,6 +116,7 @@ __global__ void k_triple_offsets(const uint32_t *sortedKeys, uint64_t n, uint32_
 // key = guide << 35 | min(E) << 32 | id, which sorts back into the reference's visiting order.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kTripleHitCap = 768;   // per CTA; further hits are emitted straight to the global buffer
+constexpr uint32_t kTripleSortCap = 1024; // next power of two: the in-CTA bitonic sort works on a padded array
 
 struct TripleVisit {
     uint32_t x;   // pattern24 | triple << 24 | budget << 28   (issl_triple_visits)
@@ -111,9 +132,15 @@ struct TripleArgs {
     uint64_t *hitKeys;
     unsigned long long *hitCount;
     uint64_t hitCap;
-    unsigned long long *streamed; // [0] entries of visited buckets, [1] bucket visits
+    unsigned long long *streamed; // [0] entries of visited buckets, [1] bucket visits, [2] hits scored in-CTA
     int maxDist;
+    // per-guide segments of the key buffer (one CTA per guide only): lets k_score_segments finish each guide
+    // from its own contiguous keys instead of radix-sorting all survivors
+    uint64_t *segOff;             // [guides] first key of the guide, or nullptr
+    uint32_t *segCnt;             // [guides] number of keys (pre-zeroed); kSegOverflow: keys are scattered
+    unsigned long long *overflowGuides;
 };
+constexpr uint32_t kSegOverflow = 0xFFFFFFFFu;
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
 __host__ __device__ constexpr uint32_t triple_resp_of(uint32_t E)
@@ -137,24 +164,133 @@ __host__ __device__ constexpr uint64_t triple_resp_pack(uint32_t e0)
 }
 constexpr uint64_t kRespLo = triple_resp_pack(0), kRespHi = triple_resp_pack(16);
 
+// CTA-wide state of one guide's scan
+struct TripleShared {
+    uint32_t key[kTripleCount], res[kTripleCount];   // the guide's bucket key / residual (both halves) per triple
+    unsigned long long count[2];
+    uint2 hits[kTripleHitCap];    // x: position in the triple's copy -- or key | slot << 24 when y bit 8 is set
+    uint32_t nHits;               // (blocked scan: position = offs[key] + slot - 1); y: triple | min(E) << 4
+    unsigned long long base;
+};
+
+__device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShared &sh, uint64_t g)
+{
+    if (threadIdx.x < kTripleCount) {
+        const uint32_t t = threadIdx.x;
+        sh.key[t] = triple_key(g, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
+        sh.res[t] = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]) * 0x10001u;
+    }
+    if (threadIdx.x < 2) sh.count[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sh.nHits = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t hit_position(const TripleView &tv, uint2 h)
+{
+    if (!(h.y & 256u)) return h.x;
+    return __ldg(tv.offs + (uint64_t)(h.y & 15u) * (kTripleBuckets + 1) + (h.x & 0xFFFFFFu)) + (h.x >> 24) - 1u;
+}
+
+// A residual within the bucket's budget: derive E, keep the hit only in the triple responsible for it.
+__device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t x16,
+                                            uint32_t recX, uint32_t recFlag)
+{
+    const uint32_t t = (v.x >> 24) & 15u;
+    const uint32_t E = (v.y & 31u) | ((uint32_t)((x16 & 0xFFu) == 0) << ((v.y >> 8) & 7u)) |
+                       ((uint32_t)((x16 >> 8) == 0) << ((v.y >> 12) & 7u));
+    const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
+    if (resp != t) return;
+    const uint32_t minE = __ffs(E) - 1;
+    const uint2 h = make_uint2(recX, t | (minE << 4) | recFlag);
+    const uint32_t slot = atomicAdd(&sh.nHits, 1u);
+    if (slot < kTripleHitCap) {
+        sh.hits[slot] = h;
+    } else {   // rare (dense repeat families): straight to the global buffer
+        const uint32_t id = a.tv.ids[(uint64_t)t * a.tv.stride + hit_position(a.tv, h)];
+        const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
+        if (gs < a.hitCap) a.hitKeys[gs] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | id;
+    }
+}
+
+// 8 residuals of one 16-byte vector against the guide's; `valid` masks the slots that belong to the bucket
+template <class RecX>
+__device__ __forceinline__ void triple_vector(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t gg,
+                                              const uint4 &r, uint32_t valid, RecX recX, uint32_t recFlag)
+{
+    const int budget = (int)(v.x >> 28);
+    const uint32_t w0 = r.x ^ gg, w1 = r.y ^ gg, w2 = r.z ^ gg, w3 = r.w ^ gg;
+    const uint32_t f0 = w0 | (w0 >> 1), f1 = w1 | (w1 >> 1), f2 = w2 | (w2 >> 1), f3 = w3 | (w3 >> 1);
+    uint32_t pass = 0;
+    pass |= (uint32_t)(__popc(f0 & 0x5555u) <= budget) << 0;
+    pass |= (uint32_t)(__popc(f0 & 0x55550000u) <= budget) << 1;
+    pass |= (uint32_t)(__popc(f1 & 0x5555u) <= budget) << 2;
+    pass |= (uint32_t)(__popc(f1 & 0x55550000u) <= budget) << 3;
+    pass |= (uint32_t)(__popc(f2 & 0x5555u) <= budget) << 4;
+    pass |= (uint32_t)(__popc(f2 & 0x55550000u) <= budget) << 5;
+    pass |= (uint32_t)(__popc(f3 & 0x5555u) <= budget) << 6;
+    pass |= (uint32_t)(__popc(f3 & 0x55550000u) <= budget) << 7;
+    pass &= valid;
+    while (pass) {
+        const uint32_t i = __ffs(pass) - 1;
+        pass &= pass - 1;
+        const uint32_t ws = (i & 4u) ? ((i & 2u) ? w3 : w2) : ((i & 2u) ? w1 : w0);
+        triple_push(a, sh, guide, v, (ws >> ((i & 1u) * 16u)) & 0xFFFFu, recX(i), recFlag);
+    }
+}
+
+// bucket [start, end) of the contiguous copy, `lanes` consecutive lanes (this one is number `gl`) share it
+__device__ __forceinline__ void triple_bucket(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t start,
+                                              uint32_t end, uint32_t gl, uint32_t lanes)
+{
+    const uint32_t t = (v.x >> 24) & 15u;
+    const uint32_t gg = sh.res[t];
+    const uint4 *__restrict__ base = reinterpret_cast<const uint4 *>(a.tv.res + (uint64_t)t * a.tv.stride);
+    const uint32_t lastVec = (end - 1) >> 3;
+    for (uint32_t vi = (start >> 3) + gl; vi <= lastVec; vi += lanes) {
+        const uint4 r = __ldg(base + vi);
+        const uint32_t first = vi << 3;
+        const uint32_t lo = start > first ? start - first : 0u, hi = min(end - first, 8u);
+        triple_vector(a, sh, guide, v, gg, r, ((1u << hi) - 1u) & ~((1u << lo) - 1u),
+                      [first](uint32_t i) { return first + i; }, 0u);
+    }
+}
+
+// end of the scan: reserve a contiguous range of the key buffer, publish the guide's segment, resolve ids
+__device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleShared &sh, uint32_t guide,
+                                                unsigned long long entries, unsigned long long visited)
+{
+    if (a.streamed) {
+        if (entries) atomicAdd(&sh.count[0], entries);
+        if (visited) atomicAdd(&sh.count[1], visited);
+    }
+    __syncthreads();
+    const uint32_t nAll = sh.nHits, nLocal = min(nAll, kTripleHitCap);
+    if (a.streamed && threadIdx.x < 2 && sh.count[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, sh.count[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (nLocal) sh.base = atomicAdd(a.hitCount, (unsigned long long)nLocal);
+        if (a.segCnt) {
+            if (nAll > kTripleHitCap) { a.segCnt[guide] = kSegOverflow; atomicAdd(a.overflowGuides, 1ull); }
+            else if (nLocal) { a.segOff[guide] = sh.base; a.segCnt[guide] = nLocal; }
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < nLocal; j += kTripleThreads) {
+        const uint2 h = sh.hits[j];
+        const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+        const unsigned long long slot = sh.base + j;
+        if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)((h.y >> 4) & 7u) << 32) | id;
+    }
+}
+
+// contiguous copy: offsets, then the bucket (two dependent round trips; the next visit's offsets are requested
+// before the current bucket is processed)
 __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
     if (a.done && a.done[guide]) return;
-    __shared__ uint32_t sKey[kTripleCount], sRes[kTripleCount];
-    __shared__ unsigned long long sCount[2];
-    __shared__ uint2 sHits[kTripleHitCap];
-    __shared__ uint32_t sNHits;
-    __shared__ unsigned long long sBase;
+    __shared__ TripleShared sh;
     const uint64_t g = a.guides[guide];
-    if (threadIdx.x < kTripleCount) {
-        const uint32_t t = threadIdx.x;
-        sKey[t] = triple_key(g, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
-        sRes[t] = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]) * 0x10001u;
-    }
-    if (threadIdx.x < 2) sCount[threadIdx.x] = 0;
-    if (threadIdx.x == 0) sNHits = 0;
-    __syncthreads();
+    triple_prologue(a, sh, g);
 
     const uint32_t octet = threadIdx.x >> 3, lane8 = threadIdx.x & 7u;
     constexpr uint32_t kOctets = kTripleThreads / 8;
@@ -168,81 +304,199 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
     if (e < v1) {
         v = __ldg(visits + e);
         const uint32_t t = (v.x >> 24) & 15u;
-        const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + (sKey[t] ^ (v.x & 0xFFFFFFu));
+        const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + (sh.key[t] ^ (v.x & 0xFFFFFFu));
         start = __ldg(o); end = __ldg(o + 1);
     }
     while (e < v1) {
-        // request the next visit's offsets first
         const uint32_t en = e + kOctets;
         uint2 vn = make_uint2(0, 0);
         uint32_t startn = 0, endn = 0;
         if (en < v1) {
             vn = __ldg(visits + en);
             const uint32_t tn = (vn.x >> 24) & 15u;
-            const uint32_t *o = a.tv.offs + (uint64_t)tn * (kTripleBuckets + 1) + (sKey[tn] ^ (vn.x & 0xFFFFFFu));
+            const uint32_t *o = a.tv.offs + (uint64_t)tn * (kTripleBuckets + 1) + (sh.key[tn] ^ (vn.x & 0xFFFFFFu));
             startn = __ldg(o); endn = __ldg(o + 1);
         }
         if (start < end) {
-            const uint32_t t = (v.x >> 24) & 15u, budget = v.x >> 28;
-            const uint32_t gg = sRes[t];
-            const uint4 *__restrict__ base = reinterpret_cast<const uint4 *>(a.tv.res + (uint64_t)t * a.tv.stride);
-            const uint32_t lastVec = (end - 1) >> 3;
-            for (uint32_t vi = (start >> 3) + lane8; vi <= lastVec; vi += 8) {
-                const uint4 r = __ldg(base + vi);
-                const uint32_t w0 = r.x ^ gg, w1 = r.y ^ gg, w2 = r.z ^ gg, w3 = r.w ^ gg;
-                const uint32_t f0 = w0 | (w0 >> 1), f1 = w1 | (w1 >> 1), f2 = w2 | (w2 >> 1), f3 = w3 | (w3 >> 1);
-                uint32_t pass = 0;
-                pass |= (uint32_t)(__popc(f0 & 0x5555u) <= (int)budget) << 0;
-                pass |= (uint32_t)(__popc(f0 & 0x55550000u) <= (int)budget) << 1;
-                pass |= (uint32_t)(__popc(f1 & 0x5555u) <= (int)budget) << 2;
-                pass |= (uint32_t)(__popc(f1 & 0x55550000u) <= (int)budget) << 3;
-                pass |= (uint32_t)(__popc(f2 & 0x5555u) <= (int)budget) << 4;
-                pass |= (uint32_t)(__popc(f2 & 0x55550000u) <= (int)budget) << 5;
-                pass |= (uint32_t)(__popc(f3 & 0x5555u) <= (int)budget) << 6;
-                pass |= (uint32_t)(__popc(f3 & 0x55550000u) <= (int)budget) << 7;
-                const uint32_t first = vi << 3;
-                const uint32_t lo = start > first ? start - first : 0u, hi = min(end - first, 8u);
-                pass &= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                while (pass) {
-                    const uint32_t i = __ffs(pass) - 1;
-                    pass &= pass - 1;
-                    const uint32_t ws = (i & 4u) ? ((i & 2u) ? w3 : w2) : ((i & 2u) ? w1 : w0);
-                    const uint32_t x16 = (ws >> ((i & 1u) * 16u)) & 0xFFFFu;
-                    const uint32_t E = (v.y & 31u) | ((uint32_t)((x16 & 0xFFu) == 0) << ((v.y >> 8) & 7u)) |
-                                       ((uint32_t)((x16 >> 8) == 0) << ((v.y >> 12) & 7u));
-                    const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
-                    if (resp != t) continue;
-                    const uint32_t minE = __ffs(E) - 1;
-                    const uint32_t slot = atomicAdd(&sNHits, 1u);
-                    if (slot < kTripleHitCap) {
-                        sHits[slot] = make_uint2(first + i, t | (minE << 4));
-                    } else {   // rare (dense repeat families): straight to the global buffer
-                        const uint32_t id = a.tv.ids[(uint64_t)t * a.tv.stride + first + i];
-                        const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
-                        if (gs < a.hitCap) a.hitKeys[gs] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | id;
-                    }
-                }
-            }
+            triple_bucket(a, sh, guide, v, start, end, lane8, 8);
             if (lane8 == 0) entries += end - start;
         }
         if (lane8 == 0) visited++;
         e = en; v = vn; start = startn; end = endn;
     }
-    if (a.streamed) {
-        if (entries) atomicAdd(&sCount[0], entries);
-        if (visited) atomicAdd(&sCount[1], visited);
+    triple_epilogue(a, sh, guide, entries, visited);
+}
+
+// blocked copy: ONE aligned read of LANES x 16 bytes per visit (count + residuals), two visits in flight per
+// lane group; a bucket that did not fit its block (count slot = kBlockOverflow) is read from the contiguous copy
+template <int LANES>
+__global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const TripleArgs a)
+{
+    const uint32_t guide = blockIdx.x;
+    if (a.done && a.done[guide]) return;
+    __shared__ TripleShared sh;
+    const uint64_t g = a.guides[guide];
+    triple_prologue(a, sh, g);
+
+    constexpr uint32_t G = kTripleThreads / LANES;
+    const uint32_t grp = threadIdx.x / LANES, gl = threadIdx.x % LANES;
+    const uint32_t v0 = blockIdx.y * a.visitsPerCta, v1 = min(a.nVisits, v0 + a.visitsPerCta);
+    unsigned long long entries = 0, visited = 0;
+    const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
+    const uint4 *__restrict__ blk = reinterpret_cast<const uint4 *>(a.tv.blk);
+
+    auto one = [&](uint2 v, const uint4 &r, bool has) {
+        // every lane of the warp takes part in the shuffle; lanes without a visit carry zeros
+        const uint32_t cnt = __shfl_sync(0xffffffffu, r.x & 0xFFFFu, 0, LANES);
+        if (!has || cnt == 0) return;
+        const uint32_t t = (v.x >> 24) & 15u, key = sh.key[t] ^ (v.x & 0xFFFFFFu);
+        if (cnt == kBlockOverflow) {
+            const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
+            const uint32_t start = __ldg(o), end = __ldg(o + 1);
+            triple_bucket(a, sh, guide, v, start, end, gl, LANES);
+            if (gl == 0) entries += end - start;
+            return;
+        }
+        if (gl == 0) entries += cnt;
+        // slots gl*8 .. gl*8+7 of the block; slot 0 is the count, slots 1..cnt hold residuals
+        const int last = (int)cnt + 1 - (int)gl * 8;          // exclusive upper slot of this lane
+        if (last <= 0) return;
+        const uint32_t valid = ((1u << min(last, 8)) - 1u) & (gl == 0 ? ~1u : ~0u);
+        const uint32_t slot0 = gl * 8u;
+        triple_vector(a, sh, guide, v, sh.res[t], r, valid,
+                      [key, slot0](uint32_t i) { return key | ((slot0 + i) << 24); }, 256u);
+    };
+
+    const uint32_t nv = v1 > v0 ? v1 - v0 : 0u;
+    for (uint32_t e0 = v0; e0 < v0 + nv; e0 += 2 * G) {
+        const uint32_t ea = e0 + grp, eb = ea + G;
+        const bool hasA = ea < v1, hasB = eb < v1;
+        uint2 va = make_uint2(0, 0), vb = make_uint2(0, 0);
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+        if (hasA) {
+            va = __ldg(visits + ea);
+            const uint32_t t = (va.x >> 24) & 15u;
+            ra = __ldg(blk + (((uint64_t)t << 24) | (sh.key[t] ^ (va.x & 0xFFFFFFu))) * LANES + gl);
+        }
+        if (hasB) {
+            vb = __ldg(visits + eb);
+            const uint32_t t = (vb.x >> 24) & 15u;
+            rb = __ldg(blk + (((uint64_t)t << 24) | (sh.key[t] ^ (vb.x & 0xFFFFFFu))) * LANES + gl);
+        }
+        one(va, ra, hasA);
+        one(vb, rb, hasB);
+        if (gl == 0) visited += (hasA ? 1u : 0u) + (hasB ? 1u : 0u);
+    }
+    triple_epilogue(a, sh, guide, entries, visited);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2t: finish one guide per CTA from its own segment of the key buffer: sort the keys back into the
+// reference's visiting order (slice, then ascending id inside the list, ref :330-344) with a bitonic
+// network in shared memory, score every hit (ref :392-461), and accumulate in that order with the
+// reference's early exit (ref :394, :460, :466-502) -- replaces radix sort + k_contrib + k_accumulate
+// when every guide's hits fit a segment.
+// ------------------------------------------------------------------------------------------------
+struct SegmentArgs {
+    const uint64_t *keys;
+    const uint64_t *segOff;
+    const uint32_t *segCnt;
+    const uint64_t *guides;
+    const uint64_t *sig;          // [N] site signatures
+    const uint32_t *occ;          // [N] occurrences
+    ScoreTables tb;
+    int calcMit, calcCfd, method, checkExit;
+    double maximumSum;
+    double *totMit, *totCfd;      // running sums, carried across slice waves
+    uint8_t *done;
+};
+
+__global__ void __launch_bounds__(kTripleThreads) k_score_segments(const SegmentArgs a)
+{
+    const uint32_t guide = blockIdx.x;
+    const uint32_t n = a.segCnt[guide];
+    if (n == 0 || n == kSegOverflow) return;
+    // The order wanted is (slice, id).  Keys are first split by slice (5 groups, a counting pass), then every
+    // group's ids are sorted by ONE warp with a bitonic network over its own power-of-two region (__syncwarp
+    // only): ~55 ids per group on a uniform genome, 21 rounds, instead of 45 block-wide rounds over 512 keys.
+    constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
+    __shared__ uint32_t sIds[2 * kTripleHitCap + 8];      // group g occupies [sStart[g], sStart[g] + pow2(count g))
+    __shared__ double sMit[kTripleHitCap], sCfd[kTripleHitCap];
+    __shared__ uint32_t sCnt[5], sFill[5], sStart[6], sOut[6];
+    const uint64_t g = a.guides[guide];
+    const uint64_t *__restrict__ keys = a.keys + a.segOff[guide];
+    if (threadIdx.x < 5) { sCnt[threadIdx.x] = 0; sFill[threadIdx.x] = 0; }
+    __syncthreads();
+    uint32_t myId[kPerThread], mySlice[kPerThread];
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        mySlice[k] = 7;
+        if (j < n) {
+            const uint64_t key = keys[j];
+            myId[k] = (uint32_t)key; mySlice[k] = (uint32_t)(key >> 32) & 7u;
+            atomicAdd(&sCnt[mySlice[k]], 1u);
+        }
     }
     __syncthreads();
-    const uint32_t nLocal = min(sNHits, kTripleHitCap);
-    if (threadIdx.x == 0 && nLocal) sBase = atomicAdd(a.hitCount, (unsigned long long)nLocal);
-    if (a.streamed && threadIdx.x < 2 && sCount[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, sCount[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        uint32_t at = 0, out = 0;
+        for (uint32_t s = 0; s < 5; s++) {
+            uint32_t m = 1;
+            while (m < sCnt[s]) m <<= 1;
+            sStart[s] = at; sOut[s] = out;
+            at += sCnt[s] ? m : 0; out += sCnt[s];
+        }
+        sStart[5] = at; sOut[5] = out;
+    }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < nLocal; j += kTripleThreads) {
-        const uint2 h = sHits[j];
-        const uint32_t t = h.y & 15u;
-        const uint32_t id = __ldg(a.tv.ids + (uint64_t)t * a.tv.stride + h.x);
-        const unsigned long long slot = sBase + j;
-        if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)(h.y >> 4) << 32) | id;
+    for (uint32_t j = threadIdx.x; j < sStart[5]; j += kTripleThreads) sIds[j] = 0xFFFFFFFFu;   // padding sorts last
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++)
+        if (mySlice[k] < 5) sIds[sStart[mySlice[k]] + atomicAdd(&sFill[mySlice[k]], 1u)] = myId[k];
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t s = warp; s < 5; s += kTripleThreads / 32) {
+        const uint32_t cnt = sCnt[s];
+        if (cnt < 2) continue;
+        uint32_t m = 1;
+        while (m < cnt) m <<= 1;
+        uint32_t *v = sIds + sStart[s];
+        for (uint32_t size = 2; size <= m; size <<= 1)
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = lane; i < (m >> 1); i += 32) {
+                    const uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1)), hi = lo | stride;
+                    const uint32_t x = v[lo], y = v[hi];
+                    const bool up = (lo & size) == 0;
+                    if ((x > y) == up) { v[lo] = y; v[hi] = x; }
+                }
+                __syncwarp();
+            }
+    }
+    __syncthreads();
+    // contributions in the final order: hit j of slice s sits at sStart[s] + j and goes to slot sOut[s] + j
+    for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
+        uint32_t s = 0;
+        while (j >= sOut[s + 1]) s++;
+        const uint32_t id = sIds[sStart[s] + (j - sOut[s])];
+        double cm, cc;
+        int dist;
+        hit_contrib(a.tb, g, __ldg(a.sig + id), __ldg(a.occ + id), a.calcMit, a.calcCfd, cm, cc, dist);
+        sMit[j] = cm; sCfd[j] = cc;
+    }
+    __syncthreads();
+    // ordered accumulation with the reference's early exit (ref :394, :460, :466-502)
+    if (threadIdx.x == 0) {
+        double mit = a.totMit[guide], cfd = a.totCfd[guide];
+        bool stop = false;
+        for (uint32_t j = 0; j < n && !stop; j++) {
+            mit = __dadd_rn(mit, sMit[j]);
+            cfd = __dadd_rn(cfd, sCfd[j]);
+            if (a.checkExit) stop = exit_predicate(a.method, mit, cfd, a.maximumSum);
+        }
+        a.totMit[guide] = mit; a.totCfd[guide] = cfd;
+        if (stop) a.done[guide] = 1;
     }
 }
 
