@@ -229,7 +229,7 @@ static int build_triple(issl_device *d)
     uint32_t pitch = 0;
     {
         const double lambda = (double)N / kTripleBuckets, want = lambda + 4.5 * std::sqrt(lambda);
-        if (lambda >= 2.0) pitch = want <= 31 ? 32 : want <= 63 ? 64 : want <= 127 ? 128 : 0;
+        if (lambda >= 2.0) pitch = want <= 31 ? 32 : want <= 62 ? 64 : want <= 124 ? 128 : 0;
         if (const char *e = getenv("ISSL_TRIPLE_BLOCKS")) {
             const long v = atol(e);
             if (v == 0 || v == 32 || v == 64 || v == 128) pitch = (uint32_t)v;
@@ -246,8 +246,7 @@ static int build_triple(issl_device *d)
     CKR(d->tripleOffs.ensure(kTripleCount * (kTripleBuckets + 1ull) * 4));
     CK(cudaMemsetAsync(d->tripleRes.p, 0, kTripleCount * stride * 2, st));
     if (pitch) {
-        CKR(d->tripleBlk.ensure(needBlk));
-        CK(cudaMemsetAsync(d->tripleBlk.p, 0, needBlk, st));
+        CKR(d->tripleBlk.ensure(needBlk));   // every sub-block is written by k_triple_blocks
     }
     DBuf keysIn, keysOut, idsIn, tmp;
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
@@ -264,9 +263,9 @@ static int build_triple(issl_device *d)
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
         if (pitch)
-            k_triple_blocks<<<blocks_for(N, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), d->tripleRes.as<uint16_t>() + t * stride,
-                                                               d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull), N, pitch,
-                                                               d->tripleBlk.as<uint16_t>() + (uint64_t)t * kTripleBuckets * pitch);
+            k_triple_blocks<<<blocks_for((uint64_t)kTripleBuckets * (pitch / 32), 256), 256, 0, st>>>(
+                d->tripleRes.as<uint16_t>() + t * stride, d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull), pitch / 32,
+                d->tripleBlk.as<uint4>() + (uint64_t)t * kTripleBuckets * (pitch / 8));
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(st));
@@ -275,7 +274,7 @@ static int build_triple(issl_device *d)
     d->tv.ids = d->tripleIds.as<uint32_t>();
     d->tv.offs = d->tripleOffs.as<uint32_t>();
     d->tv.stride = stride;
-    d->tv.blk = pitch ? d->tripleBlk.as<uint16_t>() : nullptr;
+    d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = pitch;
     d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
     return ISSL_OK;
@@ -827,7 +826,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     *nHitsOut = 0;
     if (nv) {
         // enough CTAs to fill the machine even for a handful of guides
-        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 8) : kTripleThreads / 8;   // lane groups per CTA
+        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 32) : kTripleThreads / 8;   // visits in flight per CTA
         uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
         chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
         chunks = std::min<uint32_t>(chunks, 65535u);
@@ -849,9 +848,9 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
             CK(cudaEventRecord(e0, st));
-            if (d->tv.pitch == 32) k_scan_triple_blocked<4><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
-            else if (d->tv.pitch == 64) k_scan_triple_blocked<8><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
-            else if (d->tv.pitch == 128) k_scan_triple_blocked<16><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            if (d->tv.pitch == 32) k_scan_triple_blocked<1><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            else if (d->tv.pitch == 64) k_scan_triple_blocked<2><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            else if (d->tv.pitch == 128) k_scan_triple_blocked<4><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
             else k_scan_triple<<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));

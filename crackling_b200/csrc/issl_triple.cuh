@@ -33,13 +33,16 @@ struct TripleView {
     const uint32_t *ids;    // [10][stride] site id per bucket entry
     const uint32_t *offs;   // [10][2^24 + 1] first entry of every bucket
     uint64_t stride;        // entries reserved per triple (multiple of 8, >= N + 64)
-    // blocked copy of res (optional): bucket k of triple t owns the `pitch` 16-bit slots starting at
-    // ((t << 24) | k) * pitch: slot 0 = number of entries (kBlockOverflow: bucket does not fit, use res/offs),
-    // slots 1..count = the residuals.  One aligned read per visit, no offset lookup in front of it.
-    const uint16_t *blk;
-    uint32_t pitch;         // 0 (no blocked copy), 32, 64 or 128
+    // blocked, bit-sliced copy of res (optional): bucket k of triple t owns pitch/32 sub-blocks of 64 bytes at
+    // ((t << 24) | k) * pitch * 2 bytes.  A sub-block holds up to 31 residuals TRANSPOSED: word p (p = 0..15) is
+    // bit p of the residuals of its 32 slots; slot 0 is not a residual: its column holds the number of
+    // residuals in the sub-block (bits 0..4) and the flag "this bucket does not fit, read res/offs" (bit 5).
+    // A bucket fills sub-block 0 first.  One aligned read per visit, no offset lookup in front of it, and 32
+    // residuals are tested with ~30 bitwise instructions.
+    const uint4 *blk;
+    uint32_t pitch;         // 16-bit slots per bucket: 0 (no blocked copy), 32, 64 or 128
 };
-constexpr uint32_t kBlockOverflow = 0xFFFFu;
+constexpr uint32_t kSubEntries = 31;
 
 __host__ __device__ __forceinline__ uint32_t triple_key(uint64_t sig, uint32_t a, uint32_t b, uint32_t c)
 {
@@ -82,18 +85,34 @@ __global__ void k_triple_offsets(const uint32_t *sortedKeys, uint64_t n, uint32_
     offs[k] = (uint32_t)lo;
 }
 
-// blocked copy of one triple: entry i of the sorted order goes to slot 1 + rank of its bucket's block
-__global__ void k_triple_blocks(const uint32_t *sortedKeys, const uint16_t *res, const uint32_t *offs, uint64_t n,
-                                uint32_t pitch, uint16_t *blk /* this triple's 2^24 blocks, pre-zeroed */)
+// blocked copy of one triple: one thread transposes one sub-block
+__global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint32_t subs, uint4 *blk /* this triple's blocks */)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t key = sortedKeys[i];
-    const uint32_t start = offs[key], count = offs[key + 1] - start, rank = (uint32_t)i - start;
-    uint16_t *b = blk + (uint64_t)key * pitch;
-    if (count > pitch - 1) { if (rank == 0) b[0] = (uint16_t)kBlockOverflow; return; }
-    if (rank == 0) b[0] = (uint16_t)count;
-    b[1 + rank] = res[i];
+    if (i >= (uint64_t)kTripleBuckets * subs) return;
+    const uint32_t key = (uint32_t)(i / subs), sub = (uint32_t)(i % subs);
+    const uint32_t start = offs[key], count = offs[key + 1] - start;
+    uint32_t w[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) w[p] = 0;
+    if (count > subs * kSubEntries) {
+        w[5] = 1u;                                   // does not fit: every sub-block carries the flag
+    } else {
+        const uint32_t first = sub * kSubEntries;
+        const uint32_t n = count > first ? min(count - first, kSubEntries) : 0u;
+        for (uint32_t e = 0; e < n; e++) {
+            const uint32_t r = res[start + first + e];
+#pragma unroll
+            for (int p = 0; p < 16; p++) w[p] |= ((r >> p) & 1u) << (e + 1);
+        }
+#pragma unroll
+        for (int p = 0; p < 5; p++) w[p] |= (n >> p) & 1u;
+    }
+    uint4 *o = blk + i * 4;
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    o[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    o[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -167,6 +186,7 @@ constexpr uint64_t kRespLo = triple_resp_pack(0), kRespHi = triple_resp_pack(16)
 // CTA-wide state of one guide's scan
 struct TripleShared {
     uint32_t key[kTripleCount], res[kTripleCount];   // the guide's bucket key / residual (both halves) per triple
+    uint4 mask[kTripleCount][4];  // bit-sliced scan: word p = all ones when bit p of the guide's residual is set
     unsigned long long count[2];
     uint2 hits[kTripleHitCap];    // x: position in the triple's copy -- or key | slot << 24 when y bit 8 is set
     uint32_t nHits;               // (blocked scan: position = offs[key] + slot - 1); y: triple | min(E) << 4
@@ -178,7 +198,10 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
     if (threadIdx.x < kTripleCount) {
         const uint32_t t = threadIdx.x;
         sh.key[t] = triple_key(g, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
-        sh.res[t] = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]) * 0x10001u;
+        const uint32_t r = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]);
+        sh.res[t] = r * 0x10001u;
+        uint32_t *m = reinterpret_cast<uint32_t *>(sh.mask[t]);
+        for (int p = 0; p < 16; p++) m[p] = 0u - ((r >> p) & 1u);
     }
     if (threadIdx.x < 2) sh.count[threadIdx.x] = 0;
     if (threadIdx.x == 0) sh.nHits = 0;
@@ -192,12 +215,11 @@ __device__ __forceinline__ uint32_t hit_position(const TripleView &tv, uint2 h)
 }
 
 // A residual within the bucket's budget: derive E, keep the hit only in the triple responsible for it.
-__device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t x16,
-                                            uint32_t recX, uint32_t recFlag)
+__device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t pExact,
+                                            uint32_t qExact, uint32_t recX, uint32_t recFlag)
 {
     const uint32_t t = (v.x >> 24) & 15u;
-    const uint32_t E = (v.y & 31u) | ((uint32_t)((x16 & 0xFFu) == 0) << ((v.y >> 8) & 7u)) |
-                       ((uint32_t)((x16 >> 8) == 0) << ((v.y >> 12) & 7u));
+    const uint32_t E = (v.y & 31u) | (pExact << ((v.y >> 8) & 7u)) | (qExact << ((v.y >> 12) & 7u));
     const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
     if (resp != t) return;
     const uint32_t minE = __ffs(E) - 1;
@@ -234,7 +256,8 @@ __device__ __forceinline__ void triple_vector(const TripleArgs &a, TripleShared 
         const uint32_t i = __ffs(pass) - 1;
         pass &= pass - 1;
         const uint32_t ws = (i & 4u) ? ((i & 2u) ? w3 : w2) : ((i & 2u) ? w1 : w0);
-        triple_push(a, sh, guide, v, (ws >> ((i & 1u) * 16u)) & 0xFFFFu, recX(i), recFlag);
+        const uint32_t x16 = (ws >> ((i & 1u) * 16u)) & 0xFFFFu;
+        triple_push(a, sh, guide, v, (uint32_t)((x16 & 0xFFu) == 0), (uint32_t)((x16 >> 8) == 0), recX(i), recFlag);
     }
 }
 
@@ -327,9 +350,18 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
     triple_epilogue(a, sh, guide, entries, visited);
 }
 
-// blocked copy: ONE aligned read of LANES x 16 bytes per visit (count + residuals), two visits in flight per
-// lane group; a bucket that did not fit its block (count slot = kBlockOverflow) is read from the contiguous copy
-template <int LANES>
+// blocked, bit-sliced copy: ONE aligned read per visit.  SUBS lanes share a visit, each owning a 64-byte
+// sub-block: four 16-byte loads, then all 31 residuals at once --
+//   mismatch flag of base b (one bit per slot):  x_b = (plane[2b] ^ G[2b]) | (plane[2b+1] ^ G[2b+1])
+//   count of the 8 flags per slot with a carry-save adder (4 full + 3 half adders), compared with the budget,
+// 30 LOP3 for 31 (guide, site) pairs instead of ~7 instructions per pair; no POPC, no offset lookup.
+__device__ __forceinline__ void bs_full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
+{
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
+}
+
+template <int SUBS>
 __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
@@ -338,54 +370,62 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const Tr
     const uint64_t g = a.guides[guide];
     triple_prologue(a, sh, g);
 
-    constexpr uint32_t G = kTripleThreads / LANES;
-    const uint32_t grp = threadIdx.x / LANES, gl = threadIdx.x % LANES;
+    constexpr uint32_t V = kTripleThreads / SUBS;          // visits in flight per CTA
+    const uint32_t sub = threadIdx.x % SUBS, vslot = threadIdx.x / SUBS;
     const uint32_t v0 = blockIdx.y * a.visitsPerCta, v1 = min(a.nVisits, v0 + a.visitsPerCta);
-    unsigned long long entries = 0, visited = 0;
+    uint32_t entries = 0, visited = 0;
     const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
-    const uint4 *__restrict__ blk = reinterpret_cast<const uint4 *>(a.tv.blk);
 
-    auto one = [&](uint2 v, const uint4 &r, bool has) {
-        // every lane of the warp takes part in the shuffle; lanes without a visit carry zeros
-        const uint32_t cnt = __shfl_sync(0xffffffffu, r.x & 0xFFFFu, 0, LANES);
-        if (!has || cnt == 0) return;
+    for (uint32_t e = v0 + vslot; e < v1; e += V) {
+        const uint2 v = __ldg(visits + e);
         const uint32_t t = (v.x >> 24) & 15u, key = sh.key[t] ^ (v.x & 0xFFFFFFu);
-        if (cnt == kBlockOverflow) {
+        const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
+        const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+        if (sub == 0) visited++;
+        if (q1.y & 1u) {   // the bucket did not fit its block: contiguous copy
             const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
             const uint32_t start = __ldg(o), end = __ldg(o + 1);
-            triple_bucket(a, sh, guide, v, start, end, gl, LANES);
-            if (gl == 0) entries += end - start;
-            return;
+            triple_bucket(a, sh, guide, v, start, end, sub, SUBS);
+            if (sub == 0) entries += end - start;
+            continue;
         }
-        if (gl == 0) entries += cnt;
-        // slots gl*8 .. gl*8+7 of the block; slot 0 is the count, slots 1..cnt hold residuals
-        const int last = (int)cnt + 1 - (int)gl * 8;          // exclusive upper slot of this lane
-        if (last <= 0) return;
-        const uint32_t valid = ((1u << min(last, 8)) - 1u) & (gl == 0 ? ~1u : ~0u);
-        const uint32_t slot0 = gl * 8u;
-        triple_vector(a, sh, guide, v, sh.res[t], r, valid,
-                      [key, slot0](uint32_t i) { return key | ((slot0 + i) << 24); }, 256u);
-    };
-
-    const uint32_t nv = v1 > v0 ? v1 - v0 : 0u;
-    for (uint32_t e0 = v0; e0 < v0 + nv; e0 += 2 * G) {
-        const uint32_t ea = e0 + grp, eb = ea + G;
-        const bool hasA = ea < v1, hasB = eb < v1;
-        uint2 va = make_uint2(0, 0), vb = make_uint2(0, 0);
-        uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-        if (hasA) {
-            va = __ldg(visits + ea);
-            const uint32_t t = (va.x >> 24) & 15u;
-            ra = __ldg(blk + (((uint64_t)t << 24) | (sh.key[t] ^ (va.x & 0xFFFFFFu))) * LANES + gl);
+        const uint32_t cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
+        if (cnt == 0) continue;
+        entries += cnt;
+        const uint4 m0 = sh.mask[t][0], m1 = sh.mask[t][1], m2 = sh.mask[t][2], m3 = sh.mask[t][3];
+        const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
+        const uint32_t x2 = (q1.x ^ m1.x) | (q1.y ^ m1.y), x3 = (q1.z ^ m1.z) | (q1.w ^ m1.w);
+        const uint32_t x4 = (q2.x ^ m2.x) | (q2.y ^ m2.y), x5 = (q2.z ^ m2.z) | (q2.w ^ m2.w);
+        const uint32_t x6 = (q3.x ^ m3.x) | (q3.y ^ m3.y), x7 = (q3.z ^ m3.z) | (q3.w ^ m3.w);
+        uint32_t sa, ca, sb, cb, sc, cc, t1, u1;
+        bs_full_add(x0, x1, x2, sa, ca);
+        bs_full_add(x3, x4, x5, sb, cb);
+        bs_full_add(x6, x7, sa, sc, cc);
+        const uint32_t s0 = sb ^ sc, cd = sb & sc;          // count bit 0
+        bs_full_add(ca, cb, cc, t1, u1);
+        const uint32_t s1 = t1 ^ cd, u2 = t1 & cd;          // count bit 1
+        const uint32_t s2 = u1 ^ u2, s3 = u1 & u2;          // count bits 2, 3
+        uint32_t over;                                       // slots whose count exceeds the budget
+        switch (v.x >> 28) {
+        case 0: over = s0 | s1 | s2 | s3; break;
+        case 1: over = s1 | s2 | s3; break;
+        case 2: over = s2 | s3 | (s1 & s0); break;
+        case 3: over = s2 | s3; break;
+        case 4: over = s3 | (s2 & (s1 | s0)); break;
+        case 5: over = s3 | (s2 & s1); break;
+        case 6: over = s3 | (s2 & s1 & s0); break;
+        default: over = s3; break;
         }
-        if (hasB) {
-            vb = __ldg(visits + eb);
-            const uint32_t t = (vb.x >> 24) & 15u;
-            rb = __ldg(blk + (((uint64_t)t << 24) | (sh.key[t] ^ (vb.x & 0xFFFFFFu))) * LANES + gl);
+        uint32_t pass = ~over & ((2u << cnt) - 2u);          // slots 1..cnt hold residuals
+        if (pass) {
+            const uint32_t pEx = ~(x0 | x1 | x2 | x3), qEx = ~(x4 | x5 | x6 | x7);
+            do {
+                const uint32_t sl = __ffs(pass) - 1;
+                pass &= pass - 1;
+                // entry number sub*31 + sl - 1 of the bucket, stored as "slot" = entry + 1 (hit_position)
+                triple_push(a, sh, guide, v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, key | ((sub * kSubEntries + sl) << 24), 256u);
+            } while (pass);
         }
-        one(va, ra, hasA);
-        one(vb, rb, hasB);
-        if (gl == 0) visited += (hasA ? 1u : 0u) + (hasB ? 1u : 0u);
     }
     triple_epilogue(a, sh, guide, entries, visited);
 }
