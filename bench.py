@@ -17,9 +17,14 @@ is used only for the barrier and the max-over-ranks of the step time.
 `value`  : guides/s with guides and outputs resident in HBM (issl_score_device), CUDA events.
 `e2e`    : guides/s through issl_score with pinned HOST buffers (H2D of guides and D2H of both score
            columns inside the timed region), wall clock around the blocking calls.
-`roofline`: the candidate-scan kernel (k_scan): algorithmic bytes = bytes/candidate of the HBM layout
-           (4 B for the inline 32-bit residual layout) x list entries visited, over the kernel's own
-           CUDA-event time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`roofline`: the dominant kernel, timed by the library's own CUDA events on the launching stream, against the
+           measured HBM copy bandwidth in MEASURED_PEAKS.json.  Default layout (triple): the
+           bucket scan k_scan_triple_blocked; unit = one (guide, sub-bucket) visit = one aligned read of the
+           bucket's block (128 B at human scale), plus 28 B per hit (offset pair, id, 16-byte record).
+           `reference_equivalent` restates the same time as SURVEY.md 8d defines it: 4 B (inline-residual
+           layout) x list entries the reference's loop would visit -- far above the HBM peak, because the
+           sub-bucket index lets a guide skip ~99.6 % of its five slice lists.  With --layout res32|sig64|gather:
+           k_scan, bytes/candidate of the layout x list entries visited.
 `cpu_baseline`: the unmodified reference binary (oracle/_ref/isslScoreOfftargets, built from
            /root/reference by oracle/Makefile) on the same index written out as a real .issl file and
            a bounded prefix of the same guides, all host cores; scoring time = wall time minus the
@@ -309,7 +314,8 @@ def main() -> int:
               "max_group": args.max_group,
               "index_hbm_gb": round(info["hbm_bytes"] / 1e9, 2), "index_build_s": round(t_build, 2),
               "parallelism": f"replicated index, guides partitioned x{world}, no collective",
-              "l2": "inputs larger than L2 (each step streams ~45 MB of slice lists per guide)"}
+              "l2": ("inputs larger than L2 (126 MB): every step reads its sub-buckets (~180 KB per guide, random 128-byte blocks "
+                     "out of a 21 GB copy; ~45 MB of slice lists per guide with the list-scan layouts)")}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -405,37 +411,64 @@ def main() -> int:
 
     peak, peak_src = hbm_peak()
     bpc = info["bytes_per_candidate"]
-    per_launch_bytes = bpc * candidates / max(scan_launches, 1)
     per_launch_ms = scan_ms / max(scan_launches, 1)
-    achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
-    tpc = ncu_traffic_per_candidate(layout_name)
-    roofline = {"bound": "hbm", "kernel": f"k_scan<{layout_name}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_candidate": bpc, "candidates_per_launch": candidates / max(scan_launches, 1),
-                "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": scan_ms / ms_total,
-                "traffic": (tpc * streamed / max(scan_launches, 1)) if tpc else None,
-                "traffic_source": ("profiles/scan_traffic.json: ncu --set full dram bytes per list entry streamed x entries "
-                                   "streamed per launch (each chunk is read once per guide group)") if tpc else None,
-                "frac_of_nominal_8TBps": achieved / 8000.0}
-    # With list reuse (max_group > 1) a chunk read from HBM once serves up to 8 guides, so the figure above --
-    # algorithmic bytes of the reference's per-guide walk over time -- legitimately exceeds the HBM peak
-    # (SURVEY.md 8d).  What then bounds the kernel is the XU pipe: one POPC per (guide, candidate) pair at
-    # 16 lanes/clk/SM (measured: profiles/).  Both views are reported.
     clk = clocks.summary()
     sm_hz = (clk["sm_mhz"] or 1965.0) * 1e6
-    pairs_per_s = candidates / max(scan_launches, 1) / (per_launch_ms / 1e3)
-    streamed_gbs = bpc * streamed / max(scan_launches, 1) / (per_launch_ms / 1e3) / 1e9
-    if args.max_group == 32 and layout_name == "res32" and args.max_dist <= 7:
-        # bit-sliced path: 40 ALU-pipe instructions (16 nibble extractions + 24 adder/threshold LOP3) per 32 pairs,
-        # ALU pipe = 64 lanes/clk/SM  ->  51.2 pairs/clk/SM
-        pipe, per_clk = "alu (bit-sliced: 1.25 ALU-pipe instr per pair at 64 lanes/clk/SM x 148 SMs)", 64 / 1.25
+    triple_scan = layout_name == "triple" and bucket_visits > 0
+    if triple_scan:
+        # unit = one (guide, sub-bucket) visit.  Blocked copy: one aligned read of the bucket's block; otherwise an
+        # offset pair (8 B) + the bucket's residuals (2 B each).  Every hit adds an offset pair, an id and a 16-byte
+        # record.  
+        blk = info["triple_block_bytes"]
+        alg = (bucket_visits * blk if blk else bucket_visits * 8 + streamed * 2) + hits * 28
+        per_launch_bytes = alg / max(scan_launches, 1)
+        achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+        tpv = ncu_traffic_per_candidate("triple_per_visit")
+        ref_equiv = 4 * candidates / max(scan_launches, 1) / (per_launch_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_scan_triple_blocked" if blk else "k_scan_triple", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "unit_of_work": "bucket visit", "algorithmic_bytes_per_visit": blk if blk else None,
+                    "algorithmic_bytes_per_hit": 28, "visits_per_launch": bucket_visits / max(scan_launches, 1),
+                    "visits_per_guide": bucket_visits / max(args.steps * n, 1),
+                    "bucket_entries_per_guide": streamed / max(args.steps * n, 1),
+                    "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": scan_ms / ms_total,
+                    "traffic": (tpv * bucket_visits / max(scan_launches, 1)) if tpv else None,
+                    "traffic_source": ("profiles/scan_traffic.json: ncu --set full dram read+write bytes of one k_scan_triple "
+                                       "launch / its bucket visits, x visits per launch here") if tpv else None,
+                    "frac_of_nominal_8TBps": achieved / 8000.0,
+                    "reference_equivalent": {"GB/s": ref_equiv, "x_hbm_peak": ref_equiv / peak,
+                                             "definition": "4 B x list entries the reference's loop visits (SURVEY.md 8d, RES32 "
+                                                           "layout) over the same kernel time",
+                                             "candidates_per_launch": candidates / max(scan_launches, 1),
+                                             "entries_read_per_candidate": streamed / max(candidates, 1)}}
     else:
-        pipe, per_clk = "xu (one POPC per pair at 16 lanes/clk/SM x 148 SMs)", 16.0
-    roofline.update({"reuse": candidates / max(streamed, 1), "streamed_gbs": streamed_gbs,
-                     "streamed_frac_of_hbm_peak": streamed_gbs / peak,
-                     "pipe_bound": {"pipe": pipe, "achieved_pairs_per_s": pairs_per_s,
-                                    "peak_pairs_per_s": 148 * per_clk * sm_hz, "frac": pairs_per_s / (148 * per_clk * sm_hz),
-                                    "sm_mhz_used": sm_hz / 1e6}})
+        per_launch_bytes = bpc * candidates / max(scan_launches, 1)
+        achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+        tpc = ncu_traffic_per_candidate(layout_name)
+        roofline = {"bound": "hbm", "kernel": f"k_scan<{layout_name}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_candidate": bpc, "candidates_per_launch": candidates / max(scan_launches, 1),
+                    "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": scan_ms / ms_total,
+                    "traffic": (tpc * streamed / max(scan_launches, 1)) if tpc else None,
+                    "traffic_source": ("profiles/scan_traffic.json: ncu --set full dram bytes per list entry streamed x entries "
+                                       "streamed per launch (each chunk is read once per guide group)") if tpc else None,
+                    "frac_of_nominal_8TBps": achieved / 8000.0}
+        # With list reuse (max_group > 1) a chunk read from HBM once serves up to 32 guides, so the figure above --
+        # algorithmic bytes of the reference's per-guide walk over time -- legitimately exceeds the HBM peak
+        # (SURVEY.md 8d).  What then bounds the kernel is an integer pipe.  Both views are reported.
+        pairs_per_s = candidates / max(scan_launches, 1) / (per_launch_ms / 1e3)
+        streamed_gbs = bpc * streamed / max(scan_launches, 1) / (per_launch_ms / 1e3) / 1e9
+        if args.max_group == 32 and layout_name in ("res32", "triple") and args.max_dist <= 7:
+            # bit-sliced path: 40 ALU-pipe instructions (16 nibble extractions + 24 adder/threshold LOP3) per 32 pairs,
+            # ALU pipe = 64 lanes/clk/SM  ->  51.2 pairs/clk/SM
+            pipe, per_clk = "alu (bit-sliced: 1.25 ALU-pipe instr per pair at 64 lanes/clk/SM x 148 SMs)", 64 / 1.25
+        else:
+            pipe, per_clk = "xu (one POPC per pair at 16 lanes/clk/SM x 148 SMs)", 16.0
+        roofline.update({"reuse": candidates / max(streamed, 1), "streamed_gbs": streamed_gbs,
+                         "streamed_frac_of_hbm_peak": streamed_gbs / peak,
+                         "pipe_bound": {"pipe": pipe, "achieved_pairs_per_s": pairs_per_s,
+                                        "peak_pairs_per_s": 148 * per_clk * sm_hz, "frac": pairs_per_s / (148 * per_clk * sm_hz),
+                                        "sm_mhz_used": sm_hz / 1e6}})
 
     result = {"metric": "guides scored/sec (MIT+CFD, <=4 mm)", "value": value, "unit": "guides/s", "n_gpus": world,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -444,6 +477,7 @@ def main() -> int:
               "e2e": {"value": e2e_value, "unit": "guides/s", "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 16)},
               "gpu_launches": int(launches), "scan_launches": int(scan_launches),
               "hits_per_guide": hits / max(args.steps * n, 1), "candidates_per_guide": candidates / max(args.steps * n, 1),
+              "dtype_note": "u16 bit-sliced residual compare (LOP3), f64 scores" if triple_scan else "u32/u64 xor+popcount, f64 scores",
               "roofline": roofline}
 
     if world == 1 and not args.no_cpu_baseline:

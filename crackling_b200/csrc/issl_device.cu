@@ -50,7 +50,8 @@ struct issl_device {
     uint32_t maxGroup = kBigGroup;   // ISSL_MAX_GROUP: 32 bit-sliced blocks + register groups (default), 8/4/2 register groups only, 1 no list reuse
 
     // ISSL_LAYOUT_TRIPLE
-    DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt;
+    DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites;
+    uint64_t segCap = 0;
     DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
@@ -260,6 +261,7 @@ static int build_triple(issl_device *d)
         // stable: ids stay ascending inside a bucket, as inside the reference's lists (isslCreateIndex.cpp:225-233)
         CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(), ids, N, 0, 24, st));
         k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, d->tripleRes.as<uint16_t>() + t * stride);
+        if (N < (1ull << 31)) k_triple_flag_ids<<<blocks_for(N, 256), 256, 0, st>>>(d->occ.as<uint32_t>(), N, ids);
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
         if (pitch)
@@ -274,6 +276,7 @@ static int build_triple(issl_device *d)
     d->tv.ids = d->tripleIds.as<uint32_t>();
     d->tv.offs = d->tripleOffs.as<uint32_t>();
     d->tv.stride = stride;
+    d->tv.occFlag = N < (1ull << 31) ? 1u : 0u;
     d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = pitch;
     d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
@@ -319,7 +322,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk,
+                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites,
                     &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
@@ -688,6 +691,7 @@ extern "C" int issl_device_get_info(const issl_device *d, issl_device_info *out)
     out->hbm_bytes = d->hbmBytes;
     out->list_entries = d->info.sliceCount * d->info.offtargetsCount;
     out->info = d->info;
+    out->triple_block_bytes = d->layout == ISSL_LAYOUT_TRIPLE ? d->tv.pitch * 2 : 0;
     return ISSL_OK;
 }
 
@@ -830,10 +834,14 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
         chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
         chunks = std::min<uint32_t>(chunks, 65535u);
-        const bool fuse = ws.fuse && chunks == 1;   // per-guide key segments need all hits of a guide in one CTA
+        const bool fuse = ws.fuse && chunks == 1;   // per-guide segments need all hits of a guide in one CTA
         if (fuse) { CKR(d->segOff.ensure(n * 8ull)); CKR(d->segCnt.ensure(n * 4ull)); }
         for (;;) {
             CKR(ensure_hit_buffers(d, n));
+            if (fuse && d->segCap < d->hitCap) {
+                d->segCap = d->hitCap;
+                CKR(d->segKeys.ensure(d->segCap * 8)); CKR(d->segSites.ensure(d->segCap * 8));
+            }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
             CK(cudaMemsetAsync(dc + 4, 0, 24, st));
             if (fuse) CK(cudaMemsetAsync(d->segCnt.p, 0, n * 4ull, st));
@@ -842,8 +850,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             a.nVisits = nv; a.visitsPerCta = (nv + chunks - 1) / chunks;
             a.hitKeys = d->keysA.as<uint64_t>(); a.hitCount = dc + 1; a.hitCap = d->hitCap; a.streamed = dc + 4;
             a.maxDist = maxDist;
+            a.segKeys = d->segKeys.as<uint64_t>(); a.segSites = d->segSites.as<uint64_t>(); a.segCount = dc + 6; a.segCap = d->segCap;
             a.segOff = fuse ? d->segOff.as<uint64_t>() : nullptr; a.segCnt = fuse ? d->segCnt.as<uint32_t>() : nullptr;
-            a.overflowGuides = dc + 6;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
@@ -858,26 +866,32 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             CK(cudaStreamSynchronize(st));
             d->stats.scan_launches += 1;
             d->stats.launches += 1;
-            if (d->hCounters[1] <= d->hitCap) break;
-            d->hitCap = d->hCounters[1] + d->hCounters[1] / 4;
-            CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+            if (d->hCounters[1] <= d->hitCap && d->hCounters[6] <= d->segCap) break;
+            if (d->hCounters[1] > d->hitCap) {
+                d->hitCap = d->hCounters[1] + d->hCounters[1] / 4;
+                CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+            }
+            if (d->hCounters[6] > d->segCap) {
+                d->segCap = d->hCounters[6] + d->hCounters[6] / 4;
+                CKR(d->segKeys.ensure(d->segCap * 8)); CKR(d->segSites.ensure(d->segCap * 8));
+            }
         }
         *nHitsOut = d->hCounters[1];
         d->stats.streamed += d->hCounters[4];
         d->stats.bucket_visits += d->hCounters[5];
-        if (fuse && d->hCounters[6] == 0 && *nHitsOut) {
-            // every guide's hits lie in its own segment: finish them there, nothing is left for the global tail
+        if (fuse && d->hCounters[6]) {
+            // guides whose hits fit a segment are finished there; nHitsOut covers only the others
             SegmentArgs sa;
-            sa.keys = d->keysA.as<uint64_t>(); sa.segOff = d->segOff.as<uint64_t>(); sa.segCnt = d->segCnt.as<uint32_t>();
-            sa.guides = dGuides; sa.sig = d->iv.sig; sa.occ = d->iv.occ; sa.tb = score_tables(d);
+            sa.segKeys = d->segKeys.as<uint64_t>(); sa.segSites = d->segSites.as<uint64_t>();
+            sa.segOff = d->segOff.as<uint64_t>(); sa.segCnt = d->segCnt.as<uint32_t>();
+            sa.guides = dGuides; sa.sig = d->iv.sig; sa.occ = d->iv.occ; sa.occFlag = d->tv.occFlag; sa.tb = score_tables(d);
             sa.calcMit = ws.calcMit; sa.calcCfd = ws.calcCfd; sa.method = ws.method; sa.checkExit = ws.checkExit;
             sa.maximumSum = ws.maximumSum;
             sa.totMit = d->totMit.as<double>(); sa.totCfd = d->totCfd.as<double>(); sa.done = d->done.as<uint8_t>();
             k_score_segments<<<n, kTripleThreads, 0, st>>>(sa);
             CK(cudaGetLastError());
             d->stats.launches += 1;
-            d->stats.hits += *nHitsOut;
-            *nHitsOut = 0;
+            d->stats.hits += d->hCounters[6];
         }
     } else {
         CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));

@@ -30,7 +30,8 @@ __constant__ uint8_t c_tripleSlices[kTripleCount][5] = {
 
 struct TripleView {
     const uint16_t *res;    // [10][stride] residual bits (slice p | slice q << 8) per bucket entry
-    const uint32_t *ids;    // [10][stride] site id per bucket entry
+    const uint32_t *ids;    // [10][stride] site id per bucket entry; with occFlag, bit 31 = "occurs more than once"
+    uint32_t occFlag;       // 1 when offtargetsCount < 2^31, so that bit 31 of an id is free for that flag
     const uint32_t *offs;   // [10][2^24 + 1] first entry of every bucket
     uint64_t stride;        // entries reserved per triple (multiple of 8, >= N + 64)
     // blocked, bit-sliced copy of res (optional): bucket k of triple t owns pitch/32 sub-blocks of 64 bytes at
@@ -70,6 +71,15 @@ __global__ void k_triple_residuals(const uint64_t *sig, const uint32_t *sortedId
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     res[i] = (uint16_t)triple_res(sig[sortedIds[i]], c_tripleSlices[t][3], c_tripleSlices[t][4]);
+}
+
+// bit 31 of every stored id = the site occurs more than once (saves the occurrence lookup for all other hits)
+__global__ void k_triple_flag_ids(const uint32_t *occ, uint64_t n, uint32_t *ids)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = ids[i];
+    if (occ[id] > 1) ids[i] = id | 0x80000000u;
 }
 
 // offs[k] = number of entries with key < k, for k in [0, 2^24]
@@ -148,18 +158,23 @@ struct TripleArgs {
     const uint8_t *done;          // optional: guides that already left through the early exit
     const TripleVisit *visits;    // this wave's part of the table
     uint32_t nVisits, visitsPerCta;
+    // survivors for the general pipeline (radix sort -> k_contrib -> k_accumulate): key = guide << 35 | slice << 32 | id
     uint64_t *hitKeys;
     unsigned long long *hitCount;
     uint64_t hitCap;
-    unsigned long long *streamed; // [0] entries of visited buckets, [1] bucket visits, [2] hits scored in-CTA
+    unsigned long long *streamed; // [0] entries of visited buckets, [1] bucket visits
     int maxDist;
-    // per-guide segments of the key buffer (one CTA per guide only): lets k_score_segments finish each guide
-    // from its own contiguous keys instead of radix-sorting all survivors
-    uint64_t *segOff;             // [guides] first key of the guide, or nullptr
-    uint32_t *segCnt;             // [guides] number of keys (pre-zeroed); kSegOverflow: keys are scattered
-    unsigned long long *overflowGuides;
+    // per-guide segments (one CTA per guide only, else nullptr): a guide with at most kTripleHitCap survivors
+    // gets a contiguous range of segKeys/segSites and is finished there by k_score_segments; only the others
+    // go through the general pipeline
+    uint64_t *segKeys;            // slice << 32 | id (bit 31 of the id: occurrence flag when tv.occFlag)
+    uint64_t *segSites;           // the site's signature; kSiteUnknown: look it up in sig[]
+    unsigned long long *segCount;
+    uint64_t segCap;
+    uint64_t *segOff;             // [guides] first entry of the guide's segment
+    uint32_t *segCnt;             // [guides] entries (pre-zeroed; stays 0 for guides sent to the general pipeline)
 };
-constexpr uint32_t kSegOverflow = 0xFFFFFFFFu;
+constexpr uint64_t kSiteUnknown = ~0ull;
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
 __host__ __device__ constexpr uint32_t triple_resp_of(uint32_t E)
@@ -189,7 +204,8 @@ struct TripleShared {
     uint4 mask[kTripleCount][4];  // bit-sliced scan: word p = all ones when bit p of the guide's residual is set
     unsigned long long count[2];
     uint2 hits[kTripleHitCap];    // x: position in the triple's copy -- or key | slot << 24 when y bit 8 is set
-    uint32_t nHits;               // (blocked scan: position = offs[key] + slot - 1); y: triple | min(E) << 4
+    uint32_t nHits;               // (blocked scan: position = offs[key] + slot - 1, and y bits 16..31 = the
+                                  // residual, which with the key is the whole site); y: triple | min(E) << 4
     unsigned long long base;
 };
 
@@ -227,8 +243,8 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
     const uint32_t slot = atomicAdd(&sh.nHits, 1u);
     if (slot < kTripleHitCap) {
         sh.hits[slot] = h;
-    } else {   // rare (dense repeat families): straight to the global buffer
-        const uint32_t id = a.tv.ids[(uint64_t)t * a.tv.stride + hit_position(a.tv, h)];
+    } else {   // rare (dense repeat families): straight to the general pipeline's buffer
+        const uint32_t id = a.tv.ids[(uint64_t)t * a.tv.stride + hit_position(a.tv, h)] & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u);
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
         if (gs < a.hitCap) a.hitKeys[gs] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | id;
     }
@@ -289,19 +305,36 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleShare
     __syncthreads();
     const uint32_t nAll = sh.nHits, nLocal = min(nAll, kTripleHitCap);
     if (a.streamed && threadIdx.x < 2 && sh.count[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, sh.count[threadIdx.x]);
-    if (threadIdx.x == 0) {
-        if (nLocal) sh.base = atomicAdd(a.hitCount, (unsigned long long)nLocal);
-        if (a.segCnt) {
-            if (nAll > kTripleHitCap) { a.segCnt[guide] = kSegOverflow; atomicAdd(a.overflowGuides, 1ull); }
-            else if (nLocal) { a.segOff[guide] = sh.base; a.segCnt[guide] = nLocal; }
+    const bool segment = a.segCnt && nAll <= kTripleHitCap;
+    if (threadIdx.x == 0 && nLocal) {
+        if (segment) {
+            sh.base = atomicAdd(a.segCount, (unsigned long long)nLocal);
+            a.segOff[guide] = sh.base;
+            if (sh.base + nLocal <= a.segCap) a.segCnt[guide] = nLocal;   // else the launch is repeated with a larger buffer
+        } else {
+            sh.base = atomicAdd(a.hitCount, (unsigned long long)nLocal);
         }
     }
     __syncthreads();
+    const uint32_t idMask = a.tv.occFlag ? 0x7FFFFFFFu : ~0u;
     for (uint32_t j = threadIdx.x; j < nLocal; j += kTripleThreads) {
         const uint2 h = sh.hits[j];
-        const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+        const uint32_t t = h.y & 15u, minE = (h.y >> 4) & 7u;
+        const uint32_t id = __ldg(a.tv.ids + (uint64_t)t * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + j;
-        if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)((h.y >> 4) & 7u) << 32) | id;
+        if (!segment) {
+            if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | (id & idMask);
+        } else if (slot < a.segCap) {
+            a.segKeys[slot] = ((uint64_t)minE << 32) | id;
+            uint64_t site = kSiteUnknown;
+            if (h.y & 256u) {   // bucket key + residual = the site
+                const uint32_t key = h.x & 0xFFFFFFu, r = h.y >> 16;
+                site = ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
+                       ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
+                       ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
+            }
+            a.segSites[slot] = site;
+        }
     }
 }
 
@@ -422,8 +455,15 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const Tr
             do {
                 const uint32_t sl = __ffs(pass) - 1;
                 pass &= pass - 1;
+                // the slot's residual, gathered back from the 16 planes (with the bucket key it is the whole site)
+                const uint32_t r =
+                    ((q0.x >> sl) & 1u) | (((q0.y >> sl) & 1u) << 1) | (((q0.z >> sl) & 1u) << 2) | (((q0.w >> sl) & 1u) << 3) |
+                    (((q1.x >> sl) & 1u) << 4) | (((q1.y >> sl) & 1u) << 5) | (((q1.z >> sl) & 1u) << 6) | (((q1.w >> sl) & 1u) << 7) |
+                    (((q2.x >> sl) & 1u) << 8) | (((q2.y >> sl) & 1u) << 9) | (((q2.z >> sl) & 1u) << 10) | (((q2.w >> sl) & 1u) << 11) |
+                    (((q3.x >> sl) & 1u) << 12) | (((q3.y >> sl) & 1u) << 13) | (((q3.z >> sl) & 1u) << 14) | (((q3.w >> sl) & 1u) << 15);
                 // entry number sub*31 + sl - 1 of the bucket, stored as "slot" = entry + 1 (hit_position)
-                triple_push(a, sh, guide, v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, key | ((sub * kSubEntries + sl) << 24), 256u);
+                triple_push(a, sh, guide, v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, key | ((sub * kSubEntries + sl) << 24),
+                            256u | (r << 16));
             } while (pass);
         }
     }
@@ -438,12 +478,13 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const Tr
 // when every guide's hits fit a segment.
 // ------------------------------------------------------------------------------------------------
 struct SegmentArgs {
-    const uint64_t *keys;
+    const uint64_t *segKeys, *segSites;
     const uint64_t *segOff;
     const uint32_t *segCnt;
     const uint64_t *guides;
     const uint64_t *sig;          // [N] site signatures
     const uint32_t *occ;          // [N] occurrences
+    uint32_t occFlag;
     ScoreTables tb;
     int calcMit, calcCfd, method, checkExit;
     double maximumSum;
@@ -455,27 +496,38 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
 {
     const uint32_t guide = blockIdx.x;
     const uint32_t n = a.segCnt[guide];
-    if (n == 0 || n == kSegOverflow) return;
-    // The order wanted is (slice, id).  Keys are first split by slice (5 groups, a counting pass), then every
-    // group's ids are sorted by ONE warp with a bitonic network over its own power-of-two region (__syncwarp
-    // only): ~55 ids per group on a uniform genome, 21 rounds, instead of 45 block-wide rounds over 512 keys.
+    if (n == 0) return;
+    // Every hit is scored where it lies (the record carries the site; occurrences are looked up only for the few
+    // sites flagged as repeated).  The accumulation order wanted is (slice, id): hits are split by slice (5 groups,
+    // a counting pass), then every group's (id, hit index) pairs are sorted by ONE warp with a bitonic network
+    // over its own power-of-two region (__syncwarp only): ~55 per group on a uniform genome, 21 rounds.
     constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
-    __shared__ uint32_t sIds[2 * kTripleHitCap + 8];      // group g occupies [sStart[g], sStart[g] + pow2(count g))
+    __shared__ unsigned long long sSort[2 * kTripleHitCap + 8];   // group g occupies [sStart[g], sStart[g] + pow2(count g))
     __shared__ double sMit[kTripleHitCap], sCfd[kTripleHitCap];
     __shared__ uint32_t sCnt[5], sFill[5], sStart[6], sOut[6];
+    __shared__ uint16_t sRank[kTripleHitCap];
     const uint64_t g = a.guides[guide];
-    const uint64_t *__restrict__ keys = a.keys + a.segOff[guide];
+    const uint64_t off = a.segOff[guide];
     if (threadIdx.x < 5) { sCnt[threadIdx.x] = 0; sFill[threadIdx.x] = 0; }
     __syncthreads();
     uint32_t myId[kPerThread], mySlice[kPerThread];
+    const uint32_t idMask = a.occFlag ? 0x7FFFFFFFu : ~0u;
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         const uint32_t j = threadIdx.x + k * kTripleThreads;
         mySlice[k] = 7;
         if (j < n) {
-            const uint64_t key = keys[j];
-            myId[k] = (uint32_t)key; mySlice[k] = (uint32_t)(key >> 32) & 7u;
+            const uint64_t key = a.segKeys[off + j];
+            uint64_t site = a.segSites[off + j];
+            const uint32_t idRaw = (uint32_t)key, id = idRaw & idMask;
+            myId[k] = id; mySlice[k] = (uint32_t)(key >> 32) & 7u;
             atomicAdd(&sCnt[mySlice[k]], 1u);
+            if (site == kSiteUnknown) site = __ldg(a.sig + id);
+            const uint32_t occ = (a.occFlag && !(idRaw & 0x80000000u)) ? 1u : __ldg(a.occ + id);
+            double cm, cc;
+            int dist;
+            hit_contrib(a.tb, g, site, occ, a.calcMit, a.calcCfd, cm, cc, dist);
+            sMit[j] = cm; sCfd[j] = cc;
         }
     }
     __syncthreads();
@@ -490,11 +542,13 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
         sStart[5] = at; sOut[5] = out;
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < sStart[5]; j += kTripleThreads) sIds[j] = 0xFFFFFFFFu;   // padding sorts last
+    for (uint32_t j = threadIdx.x; j < sStart[5]; j += kTripleThreads) sSort[j] = ~0ull;   // padding sorts last
     __syncthreads();
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++)
-        if (mySlice[k] < 5) sIds[sStart[mySlice[k]] + atomicAdd(&sFill[mySlice[k]], 1u)] = myId[k];
+        if (mySlice[k] < 5)
+            sSort[sStart[mySlice[k]] + atomicAdd(&sFill[mySlice[k]], 1u)] =
+                ((unsigned long long)myId[k] << 32) | (threadIdx.x + k * kTripleThreads);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (uint32_t s = warp; s < 5; s += kTripleThreads / 32) {
@@ -502,12 +556,12 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
         if (cnt < 2) continue;
         uint32_t m = 1;
         while (m < cnt) m <<= 1;
-        uint32_t *v = sIds + sStart[s];
+        unsigned long long *v = sSort + sStart[s];
         for (uint32_t size = 2; size <= m; size <<= 1)
             for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
                 for (uint32_t i = lane; i < (m >> 1); i += 32) {
                     const uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1)), hi = lo | stride;
-                    const uint32_t x = v[lo], y = v[hi];
+                    const unsigned long long x = v[lo], y = v[hi];
                     const bool up = (lo & size) == 0;
                     if ((x > y) == up) { v[lo] = y; v[hi] = x; }
                 }
@@ -515,25 +569,39 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
             }
     }
     __syncthreads();
-    // contributions in the final order: hit j of slice s sits at sStart[s] + j and goes to slot sOut[s] + j
-    for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
-        uint32_t s = 0;
-        while (j >= sOut[s + 1]) s++;
-        const uint32_t id = sIds[sStart[s] + (j - sOut[s])];
-        double cm, cc;
-        int dist;
-        hit_contrib(a.tb, g, __ldg(a.sig + id), __ldg(a.occ + id), a.calcMit, a.calcCfd, cm, cc, dist);
-        sMit[j] = cm; sCfd[j] = cc;
+    // move the contributions into accumulation order, so that the serial part below is nothing but a stream of
+    // shared-memory loads feeding two dependent add chains
+    for (uint32_t s = 0; s < 5; s++) {
+        const unsigned long long *v = sSort + sStart[s];
+        for (uint32_t i = threadIdx.x; i < sCnt[s]; i += kTripleThreads) sRank[(uint32_t)v[i]] = (uint16_t)(sOut[s] + i);
     }
     __syncthreads();
-    // ordered accumulation with the reference's early exit (ref :394, :460, :466-502)
+    double pm[kPerThread], pc[kPerThread];
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        if (j < n) { pm[k] = sMit[j]; pc[k] = sCfd[j]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        if (j < n) { const uint32_t r = sRank[j]; sMit[r] = pm[k]; sCfd[r] = pc[k]; }
+    }
+    __syncthreads();
+    // ordered accumulation with the reference's early exit (ref :394, :460, :466-502): slice by slice, ascending id
     if (threadIdx.x == 0) {
         double mit = a.totMit[guide], cfd = a.totCfd[guide];
         bool stop = false;
-        for (uint32_t j = 0; j < n && !stop; j++) {
-            mit = __dadd_rn(mit, sMit[j]);
-            cfd = __dadd_rn(cfd, sCfd[j]);
-            if (a.checkExit) stop = exit_predicate(a.method, mit, cfd, a.maximumSum);
+        if (!a.checkExit) {
+#pragma unroll 8
+            for (uint32_t i = 0; i < n; i++) { mit = __dadd_rn(mit, sMit[i]); cfd = __dadd_rn(cfd, sCfd[i]); }
+        } else {
+            for (uint32_t i = 0; i < n && !stop; i++) {
+                mit = __dadd_rn(mit, sMit[i]);
+                cfd = __dadd_rn(cfd, sCfd[i]);
+                stop = exit_predicate(a.method, mit, cfd, a.maximumSum);
+            }
         }
         a.totMit[guide] = mit; a.totCfd[guide] = cfd;
         if (stop) a.done[guide] = 1;

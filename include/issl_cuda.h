@@ -83,10 +83,12 @@ typedef enum issl_layout {
 typedef struct issl_device_info {
     int cuda_device;
     int layout;                    /* issl_layout actually in use                          */
-    uint32_t bytes_per_candidate;  /* algorithmic bytes streamed per list entry visited    */
+    uint32_t bytes_per_candidate;  /* algorithmic bytes streamed per list entry read (TRIPLE: 2, of the sub-buckets) */
     uint64_t hbm_bytes;            /* bytes of HBM held by the index                       */
     uint64_t list_entries;         /* sliceCount * offtargetsCount                          */
     issl_info info;
+    uint32_t triple_block_bytes;   /* TRIPLE: bytes of one bucket's block in the blocked copy (one read per
+                                      bucket visit); 0 = no blocked copy, buckets are read through their offsets */
 } issl_device_info;
 
 /* Counters of the last issl_score* call on a device handle. */
