@@ -50,12 +50,13 @@ struct issl_device {
     uint32_t maxGroup = kBigGroup;   // ISSL_MAX_GROUP: 32 bit-sliced blocks + register groups (default), 8/4/2 register groups only, 1 no list reuse
 
     // ISSL_LAYOUT_TRIPLE
-    DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites;
+    DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites, totMit2, totCfd2, done2;
     uint64_t segCap = 0;
     DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
-    bool tripleFuse = true;          // ISSL_TRIPLE_FUSE=0: survivors go through the global sort/score/accumulate kernels
+    int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments
+                                     // from per-guide segments, 0 = everything through the general sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
     int visitsDist = -100;           // maxDist the resident visit table was built for
     uint32_t waveStart[6] = {0, 0, 0, 0, 0, 0};
@@ -296,7 +297,7 @@ static int new_device(int cuda_device, issl_device **out)
         const long v = atol(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
     }
-    if (const char *e = getenv("ISSL_TRIPLE_FUSE")) d->tripleFuse = atoi(e) != 0;
+    if (const char *e = getenv("ISSL_TRIPLE_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->tripleFuse = v; }
     if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
         const long v = atol(e);
         if (v >= -1 && v <= 7) d->tripleMaxDist = (int)v;
@@ -322,7 +323,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites,
+                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
                     &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
@@ -794,8 +795,9 @@ static int ensure_hit_buffers(issl_device *d, uint32_t n)
 }
 
 // ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
-struct WaveScoring {   // what k_score_segments needs to finish the guides
-    bool fuse, calcMit, calcCfd, checkExit;
+struct WaveScoring {   // what the fused tail / k_score_segments need to finish the guides
+    int fuse;              // 0, 1, 2 as ISSL_TRIPLE_FUSE
+    bool calcMit, calcCfd, checkExit;
     int method;
     double maximumSum;
 };
@@ -834,8 +836,15 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
         chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
         chunks = std::min<uint32_t>(chunks, 65535u);
-        const bool fuse = ws.fuse && chunks == 1;   // per-guide segments need all hits of a guide in one CTA
+        // finishing a guide where its hits are needs all of them in one CTA
+        const bool inScan = ws.fuse == 2 && chunks == 1, fuse = ws.fuse == 1 && chunks == 1;
         if (fuse) { CKR(d->segOff.ensure(n * 8ull)); CKR(d->segCnt.ensure(n * 4ull)); }
+        if (inScan) { CKR(d->totMit2.ensure(n * 8ull)); CKR(d->totCfd2.ensure(n * 8ull)); CKR(d->done2.ensure(n)); }
+        ScoreParams sp;
+        sp.sig = d->iv.sig; sp.occ = d->iv.occ; sp.occFlag = d->tv.occFlag; sp.tb = score_tables(d);
+        sp.calcMit = ws.calcMit; sp.calcCfd = ws.calcCfd; sp.method = ws.method; sp.checkExit = ws.checkExit;
+        sp.maximumSum = ws.maximumSum;
+        sp.totMit = d->totMit.as<double>(); sp.totCfd = d->totCfd.as<double>(); sp.done = d->done.as<uint8_t>();
         for (;;) {
             CKR(ensure_hit_buffers(d, n));
             if (fuse && d->segCap < d->hitCap) {
@@ -843,7 +852,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
                 CKR(d->segKeys.ensure(d->segCap * 8)); CKR(d->segSites.ensure(d->segCap * 8));
             }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
-            CK(cudaMemsetAsync(dc + 4, 0, 24, st));
+            CK(cudaMemsetAsync(dc + 4, 0, 32, st));
             if (fuse) CK(cudaMemsetAsync(d->segCnt.p, 0, n * 4ull, st));
             TripleArgs a;
             a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<TripleVisit>() + v0;
@@ -852,6 +861,9 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             a.maxDist = maxDist;
             a.segKeys = d->segKeys.as<uint64_t>(); a.segSites = d->segSites.as<uint64_t>(); a.segCount = dc + 6; a.segCap = d->segCap;
             a.segOff = fuse ? d->segOff.as<uint64_t>() : nullptr; a.segCnt = fuse ? d->segCnt.as<uint32_t>() : nullptr;
+            a.fuse = inScan ? 1 : 0; a.sp = sp;
+            a.totMitOut = d->totMit2.as<double>(); a.totCfdOut = d->totCfd2.as<double>(); a.doneOut = d->done2.as<uint8_t>();
+            a.fusedHits = dc + 7;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
@@ -862,7 +874,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             else k_scan_triple<<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
-            CK(cudaMemcpyAsync(d->hCounters, dc, 7 * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(d->hCounters, dc, 8 * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             d->stats.scan_launches += 1;
             d->stats.launches += 1;
@@ -884,14 +896,15 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             SegmentArgs sa;
             sa.segKeys = d->segKeys.as<uint64_t>(); sa.segSites = d->segSites.as<uint64_t>();
             sa.segOff = d->segOff.as<uint64_t>(); sa.segCnt = d->segCnt.as<uint32_t>();
-            sa.guides = dGuides; sa.sig = d->iv.sig; sa.occ = d->iv.occ; sa.occFlag = d->tv.occFlag; sa.tb = score_tables(d);
-            sa.calcMit = ws.calcMit; sa.calcCfd = ws.calcCfd; sa.method = ws.method; sa.checkExit = ws.checkExit;
-            sa.maximumSum = ws.maximumSum;
-            sa.totMit = d->totMit.as<double>(); sa.totCfd = d->totCfd.as<double>(); sa.done = d->done.as<uint8_t>();
+            sa.guides = dGuides; sa.sp = sp;
             k_score_segments<<<n, kTripleThreads, 0, st>>>(sa);
             CK(cudaGetLastError());
             d->stats.launches += 1;
             d->stats.hits += d->hCounters[6];
+        }
+        if (inScan) {   // the scan kernel wrote every guide's state of after this wave
+            std::swap(d->totMit, d->totMit2); std::swap(d->totCfd, d->totCfd2); std::swap(d->done, d->done2);
+            d->stats.hits += d->hCounters[7];
         }
     } else {
         CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
@@ -937,7 +950,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         uint64_t nHits = 0;
         if (useTriple) {
             WaveScoring ws;
-            ws.fuse = sink == nullptr && d->tripleFuse; ws.calcMit = calcMit; ws.calcCfd = calcCfd; ws.checkExit = checkExit;
+            ws.fuse = sink == nullptr ? d->tripleFuse : 0; ws.calcMit = calcMit; ws.calcCfd = calcCfd; ws.checkExit = checkExit;
             ws.method = method; ws.maximumSum = maximumSum;
             CKR(triple_wave(d, st, dGuides, n, s0, ns, doneMask, maxDist, ws, timer, &nHits));
         } else {

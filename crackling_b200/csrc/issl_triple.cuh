@@ -144,8 +144,140 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint3
 // key buffer with one atomic, resolves the site ids with all threads and writes
 // key = guide << 35 | min(E) << 32 | id, which sorts back into the reference's visiting order.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kTripleHitCap = 768;   // per CTA; further hits are emitted straight to the global buffer
-constexpr uint32_t kTripleSortCap = 1024; // next power of two: the in-CTA bitonic sort works on a padded array
+constexpr uint32_t kTripleHitCap = 512;   // per CTA; a guide with more hits goes through the general pipeline
+
+// ------------------------------------------------------------------------------------------------
+// Finishing one guide inside a CTA (used by the fused tail of the bucket scan and by k_score_segments):
+// every hit is scored where it lies (ref :392-461); the accumulation order wanted is (slice, id) -- the
+// reference's visiting order, ref :330-344 -- so hits are split by slice (5 groups, a counting pass), every
+// group's (id, hit index) pairs are sorted by ONE warp with a bitonic network over its own power-of-two region
+// (__syncwarp only: ~55 per group on a uniform genome, 21 rounds), the contributions are moved into that order,
+// and one thread adds them up one rounded sum at a time with the reference's early exit (ref :394, :460, :466-502).
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kSiteUnknown = ~0ull;   // a hit record without the site's signature: look it up in sig[]
+
+struct ScoreParams {
+    const uint64_t *sig;          // [N] site signatures
+    const uint32_t *occ;          // [N] occurrences
+    uint32_t occFlag;             // ids carry "occurs more than once" in bit 31
+    ScoreTables tb;
+    int calcMit, calcCfd, method, checkExit;
+    double maximumSum;
+    double *totMit, *totCfd;      // running sums, carried across slice waves
+    uint8_t *done;
+};
+
+struct ScoreShared {
+    double mit[kTripleHitCap], cfd[kTripleHitCap];
+    uint32_t cnt[5], fill[5], start[6], out[6];
+    uint16_t rank[kTripleHitCap];
+};
+constexpr uint32_t kScoreSortSlots = 2 * kTripleHitCap + 8;   // group g occupies [start[g], start[g] + pow2(count g))
+
+// load(j, idRaw, slice, site): hit j of the guide.  sort[] may alias whatever load() reads: it is first written
+// after a barrier that follows the last load.  Results go to totMitOut/totCfdOut/doneOut[guide].
+template <class Load>
+__device__ __forceinline__ void score_guide(ScoreShared &ss, unsigned long long *sort, uint32_t n, uint32_t guide, uint64_t g,
+                                            const ScoreParams &sp, double *totMitOut, double *totCfdOut, uint8_t *doneOut, Load load)
+{
+    constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
+    if (threadIdx.x < 5) { ss.cnt[threadIdx.x] = 0; ss.fill[threadIdx.x] = 0; }
+    __syncthreads();
+    uint32_t myId[kPerThread], mySlice[kPerThread];
+    const uint32_t idMask = sp.occFlag ? 0x7FFFFFFFu : ~0u;
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        mySlice[k] = 7;
+        if (j < n) {
+            uint32_t idRaw, slice;
+            uint64_t site;
+            load(j, idRaw, slice, site);
+            const uint32_t id = idRaw & idMask;
+            myId[k] = id; mySlice[k] = slice;
+            atomicAdd(&ss.cnt[slice], 1u);
+            if (site == kSiteUnknown) site = __ldg(sp.sig + id);
+            const uint32_t occ = (sp.occFlag && !(idRaw & 0x80000000u)) ? 1u : __ldg(sp.occ + id);
+            double cm, cc;
+            int dist;
+            hit_contrib(sp.tb, g, site, occ, sp.calcMit, sp.calcCfd, cm, cc, dist);
+            ss.mit[j] = cm; ss.cfd[j] = cc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t at = 0, out = 0;
+        for (uint32_t s = 0; s < 5; s++) {
+            uint32_t m = 1;
+            while (m < ss.cnt[s]) m <<= 1;
+            ss.start[s] = at; ss.out[s] = out;
+            at += ss.cnt[s] ? m : 0; out += ss.cnt[s];
+        }
+        ss.start[5] = at; ss.out[5] = out;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < ss.start[5]; j += kTripleThreads) sort[j] = ~0ull;   // padding sorts last
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++)
+        if (mySlice[k] < 5)
+            sort[ss.start[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u)] =
+                ((unsigned long long)myId[k] << 32) | (threadIdx.x + k * kTripleThreads);
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t s = warp; s < 5; s += kTripleThreads / 32) {
+        const uint32_t cnt = ss.cnt[s];
+        if (cnt < 2) continue;
+        uint32_t m = 1;
+        while (m < cnt) m <<= 1;
+        unsigned long long *v = sort + ss.start[s];
+        for (uint32_t size = 2; size <= m; size <<= 1)
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = lane; i < (m >> 1); i += 32) {
+                    const uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1)), hi = lo | stride;
+                    const unsigned long long x = v[lo], y = v[hi];
+                    const bool up = (lo & size) == 0;
+                    if ((x > y) == up) { v[lo] = y; v[hi] = x; }
+                }
+                __syncwarp();
+            }
+    }
+    __syncthreads();
+    for (uint32_t s = 0; s < 5; s++) {
+        const unsigned long long *v = sort + ss.start[s];
+        for (uint32_t i = threadIdx.x; i < ss.cnt[s]; i += kTripleThreads) ss.rank[(uint32_t)v[i]] = (uint16_t)(ss.out[s] + i);
+    }
+    __syncthreads();
+    double pm[kPerThread], pc[kPerThread];
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        if (j < n) { pm[k] = ss.mit[j]; pc[k] = ss.cfd[j]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        if (j < n) { const uint32_t r = ss.rank[j]; ss.mit[r] = pm[k]; ss.cfd[r] = pc[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mit = sp.totMit[guide], cfd = sp.totCfd[guide];
+        bool stop = false;
+        if (!sp.checkExit) {
+#pragma unroll 8
+            for (uint32_t i = 0; i < n; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
+        } else {
+            for (uint32_t i = 0; i < n && !stop; i++) {
+                mit = __dadd_rn(mit, ss.mit[i]);
+                cfd = __dadd_rn(cfd, ss.cfd[i]);
+                stop = exit_predicate(sp.method, mit, cfd, sp.maximumSum);
+            }
+        }
+        totMitOut[guide] = mit; totCfdOut[guide] = cfd;
+        if (stop) doneOut[guide] = 1;
+    }
+}
 
 struct TripleVisit {
     uint32_t x;   // pattern24 | triple << 24 | budget << 28   (issl_triple_visits)
@@ -173,8 +305,14 @@ struct TripleArgs {
     uint64_t segCap;
     uint64_t *segOff;             // [guides] first entry of the guide's segment
     uint32_t *segCnt;             // [guides] entries (pre-zeroed; stays 0 for guides sent to the general pipeline)
+    // fused scoring (one CTA per guide only): a guide with at most kTripleHitCap survivors is sorted, scored and
+    // accumulated by the CTA that found them, straight from shared memory; nothing of it reaches global memory
+    int fuse;
+    ScoreParams sp;               // sp.totMit/totCfd/done: state before this wave (read only)
+    double *totMitOut, *totCfdOut;   // state after it, written for EVERY guide (a re-launch after a buffer overflow
+    uint8_t *doneOut;                // must start from the same state)
+    unsigned long long *fusedHits;
 };
-constexpr uint64_t kSiteUnknown = ~0ull;
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
 __host__ __device__ constexpr uint32_t triple_resp_of(uint32_t E)
@@ -294,10 +432,32 @@ __device__ __forceinline__ void triple_bucket(const TripleArgs &a, TripleShared 
     }
 }
 
-// end of the scan: reserve a contiguous range of the key buffer, publish the guide's segment, resolve ids
-__device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleShared &sh, uint32_t guide,
+// site of a hit of the blocked scan: bucket key + residual
+__device__ __forceinline__ uint64_t hit_site(uint2 h)
+{
+    if (!(h.y & 256u)) return kSiteUnknown;
+    const uint32_t t = h.y & 15u, key = h.x & 0xFFFFFFu, r = h.y >> 16;
+    return ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
+           ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
+           ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
+}
+
+// Shared memory of the scan kernels: the scan state; the sort region of the fused tail reuses it once every
+// thread has taken its hits out.
+struct TripleSmem {
+    union {
+        TripleShared scan;
+        unsigned long long sort[kScoreSortSlots];
+    };
+    ScoreShared score;
+};
+
+// end of the scan: finish the guide here (fused), or hand its hits on -- as a segment for k_score_segments or as
+// keys for the general pipeline
+__device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleSmem &sm, uint32_t guide, uint64_t g,
                                                 unsigned long long entries, unsigned long long visited)
 {
+    TripleShared &sh = sm.scan;
     if (a.streamed) {
         if (entries) atomicAdd(&sh.count[0], entries);
         if (visited) atomicAdd(&sh.count[1], visited);
@@ -305,6 +465,22 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleShare
     __syncthreads();
     const uint32_t nAll = sh.nHits, nLocal = min(nAll, kTripleHitCap);
     if (a.streamed && threadIdx.x < 2 && sh.count[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, sh.count[threadIdx.x]);
+    if (a.fuse && threadIdx.x == 0) {   // state after this wave unless the fused tail below changes it
+        a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 0;
+    }
+    if (a.fuse && nAll <= kTripleHitCap) {
+        if (nAll == 0) return;
+        if (threadIdx.x == 0) atomicAdd(a.fusedHits, (unsigned long long)nAll);
+        __syncthreads();   // the defaults above are in place before score_guide's writer thread runs
+        score_guide(sm.score, sm.sort, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
+                    [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
+                        const uint2 h = sh.hits[j];
+                        idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+                        slice = (h.y >> 4) & 7u;
+                        site = hit_site(h);
+                    });
+        return;
+    }
     const bool segment = a.segCnt && nAll <= kTripleHitCap;
     if (threadIdx.x == 0 && nLocal) {
         if (segment) {
@@ -326,14 +502,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleShare
             if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | (id & idMask);
         } else if (slot < a.segCap) {
             a.segKeys[slot] = ((uint64_t)minE << 32) | id;
-            uint64_t site = kSiteUnknown;
-            if (h.y & 256u) {   // bucket key + residual = the site
-                const uint32_t key = h.x & 0xFFFFFFu, r = h.y >> 16;
-                site = ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
-                       ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
-                       ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
-            }
-            a.segSites[slot] = site;
+            a.segSites[slot] = hit_site(h);
         }
     }
 }
@@ -343,8 +512,14 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleShare
 __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
-    if (a.done && a.done[guide]) return;
-    __shared__ TripleShared sh;
+    if (a.done && a.done[guide]) {
+        if (a.fuse && threadIdx.x == 0) {
+            a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 1;
+        }
+        return;
+    }
+    __shared__ TripleSmem sm;
+    TripleShared &sh = sm.scan;
     const uint64_t g = a.guides[guide];
     triple_prologue(a, sh, g);
 
@@ -380,7 +555,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
         if (lane8 == 0) visited++;
         e = en; v = vn; start = startn; end = endn;
     }
-    triple_epilogue(a, sh, guide, entries, visited);
+    triple_epilogue(a, sm, guide, g, entries, visited);
 }
 
 // blocked, bit-sliced copy: ONE aligned read per visit.  SUBS lanes share a visit, each owning a 64-byte
@@ -398,8 +573,14 @@ template <int SUBS>
 __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
-    if (a.done && a.done[guide]) return;
-    __shared__ TripleShared sh;
+    if (a.done && a.done[guide]) {
+        if (a.fuse && threadIdx.x == 0) {
+            a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 1;
+        }
+        return;
+    }
+    __shared__ TripleSmem sm;
+    TripleShared &sh = sm.scan;
     const uint64_t g = a.guides[guide];
     triple_prologue(a, sh, g);
 
@@ -467,7 +648,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const Tr
             } while (pass);
         }
     }
-    triple_epilogue(a, sh, guide, entries, visited);
+    triple_epilogue(a, sm, guide, g, entries, visited);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -482,14 +663,7 @@ struct SegmentArgs {
     const uint64_t *segOff;
     const uint32_t *segCnt;
     const uint64_t *guides;
-    const uint64_t *sig;          // [N] site signatures
-    const uint32_t *occ;          // [N] occurrences
-    uint32_t occFlag;
-    ScoreTables tb;
-    int calcMit, calcCfd, method, checkExit;
-    double maximumSum;
-    double *totMit, *totCfd;      // running sums, carried across slice waves
-    uint8_t *done;
+    ScoreParams sp;
 };
 
 __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const SegmentArgs a)
@@ -497,115 +671,15 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
     const uint32_t guide = blockIdx.x;
     const uint32_t n = a.segCnt[guide];
     if (n == 0) return;
-    // Every hit is scored where it lies (the record carries the site; occurrences are looked up only for the few
-    // sites flagged as repeated).  The accumulation order wanted is (slice, id): hits are split by slice (5 groups,
-    // a counting pass), then every group's (id, hit index) pairs are sorted by ONE warp with a bitonic network
-    // over its own power-of-two region (__syncwarp only): ~55 per group on a uniform genome, 21 rounds.
-    constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
-    __shared__ unsigned long long sSort[2 * kTripleHitCap + 8];   // group g occupies [sStart[g], sStart[g] + pow2(count g))
-    __shared__ double sMit[kTripleHitCap], sCfd[kTripleHitCap];
-    __shared__ uint32_t sCnt[5], sFill[5], sStart[6], sOut[6];
-    __shared__ uint16_t sRank[kTripleHitCap];
-    const uint64_t g = a.guides[guide];
+    __shared__ ScoreShared ss;
+    __shared__ unsigned long long sort[kScoreSortSlots];
     const uint64_t off = a.segOff[guide];
-    if (threadIdx.x < 5) { sCnt[threadIdx.x] = 0; sFill[threadIdx.x] = 0; }
-    __syncthreads();
-    uint32_t myId[kPerThread], mySlice[kPerThread];
-    const uint32_t idMask = a.occFlag ? 0x7FFFFFFFu : ~0u;
-#pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++) {
-        const uint32_t j = threadIdx.x + k * kTripleThreads;
-        mySlice[k] = 7;
-        if (j < n) {
-            const uint64_t key = a.segKeys[off + j];
-            uint64_t site = a.segSites[off + j];
-            const uint32_t idRaw = (uint32_t)key, id = idRaw & idMask;
-            myId[k] = id; mySlice[k] = (uint32_t)(key >> 32) & 7u;
-            atomicAdd(&sCnt[mySlice[k]], 1u);
-            if (site == kSiteUnknown) site = __ldg(a.sig + id);
-            const uint32_t occ = (a.occFlag && !(idRaw & 0x80000000u)) ? 1u : __ldg(a.occ + id);
-            double cm, cc;
-            int dist;
-            hit_contrib(a.tb, g, site, occ, a.calcMit, a.calcCfd, cm, cc, dist);
-            sMit[j] = cm; sCfd[j] = cc;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t at = 0, out = 0;
-        for (uint32_t s = 0; s < 5; s++) {
-            uint32_t m = 1;
-            while (m < sCnt[s]) m <<= 1;
-            sStart[s] = at; sOut[s] = out;
-            at += sCnt[s] ? m : 0; out += sCnt[s];
-        }
-        sStart[5] = at; sOut[5] = out;
-    }
-    __syncthreads();
-    for (uint32_t j = threadIdx.x; j < sStart[5]; j += kTripleThreads) sSort[j] = ~0ull;   // padding sorts last
-    __syncthreads();
-#pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++)
-        if (mySlice[k] < 5)
-            sSort[sStart[mySlice[k]] + atomicAdd(&sFill[mySlice[k]], 1u)] =
-                ((unsigned long long)myId[k] << 32) | (threadIdx.x + k * kTripleThreads);
-    __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    for (uint32_t s = warp; s < 5; s += kTripleThreads / 32) {
-        const uint32_t cnt = sCnt[s];
-        if (cnt < 2) continue;
-        uint32_t m = 1;
-        while (m < cnt) m <<= 1;
-        unsigned long long *v = sSort + sStart[s];
-        for (uint32_t size = 2; size <= m; size <<= 1)
-            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                for (uint32_t i = lane; i < (m >> 1); i += 32) {
-                    const uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1)), hi = lo | stride;
-                    const unsigned long long x = v[lo], y = v[hi];
-                    const bool up = (lo & size) == 0;
-                    if ((x > y) == up) { v[lo] = y; v[hi] = x; }
-                }
-                __syncwarp();
-            }
-    }
-    __syncthreads();
-    // move the contributions into accumulation order, so that the serial part below is nothing but a stream of
-    // shared-memory loads feeding two dependent add chains
-    for (uint32_t s = 0; s < 5; s++) {
-        const unsigned long long *v = sSort + sStart[s];
-        for (uint32_t i = threadIdx.x; i < sCnt[s]; i += kTripleThreads) sRank[(uint32_t)v[i]] = (uint16_t)(sOut[s] + i);
-    }
-    __syncthreads();
-    double pm[kPerThread], pc[kPerThread];
-#pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++) {
-        const uint32_t j = threadIdx.x + k * kTripleThreads;
-        if (j < n) { pm[k] = sMit[j]; pc[k] = sCfd[j]; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++) {
-        const uint32_t j = threadIdx.x + k * kTripleThreads;
-        if (j < n) { const uint32_t r = sRank[j]; sMit[r] = pm[k]; sCfd[r] = pc[k]; }
-    }
-    __syncthreads();
-    // ordered accumulation with the reference's early exit (ref :394, :460, :466-502): slice by slice, ascending id
-    if (threadIdx.x == 0) {
-        double mit = a.totMit[guide], cfd = a.totCfd[guide];
-        bool stop = false;
-        if (!a.checkExit) {
-#pragma unroll 8
-            for (uint32_t i = 0; i < n; i++) { mit = __dadd_rn(mit, sMit[i]); cfd = __dadd_rn(cfd, sCfd[i]); }
-        } else {
-            for (uint32_t i = 0; i < n && !stop; i++) {
-                mit = __dadd_rn(mit, sMit[i]);
-                cfd = __dadd_rn(cfd, sCfd[i]);
-                stop = exit_predicate(a.method, mit, cfd, a.maximumSum);
-            }
-        }
-        a.totMit[guide] = mit; a.totCfd[guide] = cfd;
-        if (stop) a.done[guide] = 1;
-    }
+    score_guide(ss, sort, n, guide, a.guides[guide], a.sp, a.sp.totMit, a.sp.totCfd, a.sp.done,
+                [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
+                    const uint64_t key = a.segKeys[off + j];
+                    idRaw = (uint32_t)key; slice = (uint32_t)(key >> 32) & 7u;
+                    site = a.segSites[off + j];
+                });
 }
 
 // candidates of one wave = list entries the reference would visit (ref :330-344): the unit of work
