@@ -149,10 +149,10 @@ constexpr uint32_t kTripleHitCap = 512;   // per CTA; a guide with more hits goe
 // ------------------------------------------------------------------------------------------------
 // Finishing one guide inside a CTA (used by the fused tail of the bucket scan and by k_score_segments):
 // every hit is scored where it lies (ref :392-461); the accumulation order wanted is (slice, id) -- the
-// reference's visiting order, ref :330-344 -- so hits are split by slice (5 groups, a counting pass), every
-// group's (id, hit index) pairs are sorted by ONE warp with a bitonic network over its own power-of-two region
-// (__syncwarp only: ~55 per group on a uniform genome, 21 rounds), the contributions are moved into that order,
-// and one thread adds them up one rounded sum at a time with the reference's early exit (ref :394, :460, :466-502).
+// reference's visiting order, ref :330-344 -- so hits are split by slice (5 groups, a counting pass), every hit's
+// rank inside its group is counted by one warp per group (~55 ids per group on a uniform genome), the
+// contributions are moved into that order, and one thread adds them up one rounded sum at a time with the
+// reference's early exit (ref :394, :460, :466-502).
 // ------------------------------------------------------------------------------------------------
 constexpr uint64_t kSiteUnknown = ~0ull;   // a hit record without the site's signature: look it up in sig[]
 
@@ -169,15 +169,15 @@ struct ScoreParams {
 
 struct ScoreShared {
     double mit[kTripleHitCap], cfd[kTripleHitCap];
-    uint32_t cnt[5], fill[5], start[6], out[6];
+    uint32_t cnt[5], fill[5], out[6];
     uint16_t rank[kTripleHitCap];
 };
-constexpr uint32_t kScoreSortSlots = 2 * kTripleHitCap + 8;   // group g occupies [start[g], start[g] + pow2(count g))
+constexpr uint32_t kScoreGroupWords = kTripleHitCap + kTripleHitCap / 2;   // u32 id + u16 hit index per hit
 
-// load(j, idRaw, slice, site): hit j of the guide.  sort[] may alias whatever load() reads: it is first written
+// load(j, idRaw, slice, site): hit j of the guide.  group[] may alias whatever load() reads: it is first written
 // after a barrier that follows the last load.  Results go to totMitOut/totCfdOut/doneOut[guide].
 template <class Load>
-__device__ __forceinline__ void score_guide(ScoreShared &ss, unsigned long long *sort, uint32_t n, uint32_t guide, uint64_t g,
+__device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, uint32_t n, uint32_t guide, uint64_t g,
                                             const ScoreParams &sp, double *totMitOut, double *totCfdOut, uint8_t *doneOut, Load load)
 {
     constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
@@ -206,46 +206,31 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, unsigned long long 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t at = 0, out = 0;
-        for (uint32_t s = 0; s < 5; s++) {
-            uint32_t m = 1;
-            while (m < ss.cnt[s]) m <<= 1;
-            ss.start[s] = at; ss.out[s] = out;
-            at += ss.cnt[s] ? m : 0; out += ss.cnt[s];
-        }
-        ss.start[5] = at; ss.out[5] = out;
+        uint32_t out = 0;
+        for (uint32_t s = 0; s < 5; s++) { ss.out[s] = out; out += ss.cnt[s]; }
+        ss.out[5] = out;
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < ss.start[5]; j += kTripleThreads) sort[j] = ~0ull;   // padding sorts last
-    __syncthreads();
+    uint32_t *gid = reinterpret_cast<uint32_t *>(group);                       // ids, grouped by slice
+    uint16_t *gidx = reinterpret_cast<uint16_t *>(gid + kTripleHitCap);        // the hit each one belongs to
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++)
-        if (mySlice[k] < 5)
-            sort[ss.start[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u)] =
-                ((unsigned long long)myId[k] << 32) | (threadIdx.x + k * kTripleThreads);
+        if (mySlice[k] < 5) {
+            const uint32_t p = ss.out[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u);
+            gid[p] = myId[k]; gidx[p] = (uint16_t)(threadIdx.x + k * kTripleThreads);
+        }
     __syncthreads();
+    // rank of every hit inside its slice group = number of smaller ids (ids of one guide are distinct): one warp per
+    // group, every lane counts for its own hits over the whole group (broadcast reads); groups are small (~55)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (uint32_t s = warp; s < 5; s += kTripleThreads / 32) {
-        const uint32_t cnt = ss.cnt[s];
-        if (cnt < 2) continue;
-        uint32_t m = 1;
-        while (m < cnt) m <<= 1;
-        unsigned long long *v = sort + ss.start[s];
-        for (uint32_t size = 2; size <= m; size <<= 1)
-            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                for (uint32_t i = lane; i < (m >> 1); i += 32) {
-                    const uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1)), hi = lo | stride;
-                    const unsigned long long x = v[lo], y = v[hi];
-                    const bool up = (lo & size) == 0;
-                    if ((x > y) == up) { v[lo] = y; v[hi] = x; }
-                }
-                __syncwarp();
-            }
-    }
-    __syncthreads();
-    for (uint32_t s = 0; s < 5; s++) {
-        const unsigned long long *v = sort + ss.start[s];
-        for (uint32_t i = threadIdx.x; i < ss.cnt[s]; i += kTripleThreads) ss.rank[(uint32_t)v[i]] = (uint16_t)(ss.out[s] + i);
+        const uint32_t c = ss.cnt[s], base = ss.out[s];
+        for (uint32_t i = lane; i < c; i += 32) {
+            const uint32_t mine = gid[base + i];
+            uint32_t r = 0;
+            for (uint32_t q = 0; q < c; q++) r += (uint32_t)(gid[base + q] < mine);
+            ss.rank[gidx[base + i]] = (uint16_t)(base + r);
+        }
     }
     __syncthreads();
     double pm[kPerThread], pc[kPerThread];
@@ -442,12 +427,12 @@ __device__ __forceinline__ uint64_t hit_site(uint2 h)
            ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
 }
 
-// Shared memory of the scan kernels: the scan state; the sort region of the fused tail reuses it once every
+// Shared memory of the scan kernels: the scan state; the grouping arrays of the fused tail reuse it once every
 // thread has taken its hits out.
 struct TripleSmem {
     union {
         TripleShared scan;
-        unsigned long long sort[kScoreSortSlots];
+        uint32_t group[kScoreGroupWords];
     };
     ScoreShared score;
 };
@@ -472,7 +457,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleSmem 
         if (nAll == 0) return;
         if (threadIdx.x == 0) atomicAdd(a.fusedHits, (unsigned long long)nAll);
         __syncthreads();   // the defaults above are in place before score_guide's writer thread runs
-        score_guide(sm.score, sm.sort, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
+        score_guide(sm.score, sm.group, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
                     [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
                         const uint2 h = sh.hits[j];
                         idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
@@ -570,7 +555,7 @@ __device__ __forceinline__ void bs_full_add(uint32_t a, uint32_t b, uint32_t c, 
 }
 
 template <int SUBS>
-__global__ void __launch_bounds__(kTripleThreads) k_scan_triple_blocked(const TripleArgs a)
+__global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
     if (a.done && a.done[guide]) {
@@ -672,9 +657,9 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
     const uint32_t n = a.segCnt[guide];
     if (n == 0) return;
     __shared__ ScoreShared ss;
-    __shared__ unsigned long long sort[kScoreSortSlots];
+    __shared__ uint32_t group[kScoreGroupWords];
     const uint64_t off = a.segOff[guide];
-    score_guide(ss, sort, n, guide, a.guides[guide], a.sp, a.sp.totMit, a.sp.totCfd, a.sp.done,
+    score_guide(ss, group, n, guide, a.guides[guide], a.sp, a.sp.totMit, a.sp.totCfd, a.sp.done,
                 [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
                     const uint64_t key = a.segKeys[off + j];
                     idRaw = (uint32_t)key; slice = (uint32_t)(key >> 32) & 7u;
