@@ -55,8 +55,8 @@ struct issl_device {
     DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
-    int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments
-                                     // from per-guide segments, 0 = everything through the general sort/score/accumulate kernels
+    int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments from
+                                     // per-guide segments, 0 = everything through the general sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
     int visitsDist = -100;           // maxDist the resident visit table was built for
     uint32_t waveStart[6] = {0, 0, 0, 0, 0, 0};
@@ -794,18 +794,8 @@ static int ensure_hit_buffers(issl_device *d, uint32_t n)
     return ISSL_OK;
 }
 
-// ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
-struct WaveScoring {   // what the fused tail / k_score_segments need to finish the guides
-    int fuse;              // 0, 1, 2 as ISSL_TRIPLE_FUSE
-    bool calcMit, calcCfd, checkExit;
-    int method;
-    double maximumSum;
-};
-
-static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint32_t s0, uint32_t ns,
-                       const uint8_t *doneMask, int maxDist, const WaveScoring &ws, EventTimer &timer, uint64_t *nHitsOut)
+static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
 {
-    unsigned long long *dc = d->counters.as<unsigned long long>();
     if (d->visitsDist != maxDist) {   // the visit table depends on maxDist only
         std::vector<uint32_t> raw(issl_triple_visits(maxDist, nullptr, 0, nullptr));
         issl_triple_visits(maxDist, raw.data(), raw.size(), d->waveStart);
@@ -825,6 +815,37 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         CK(cudaStreamSynchronize(st));   // v is a local
         d->visitsDist = maxDist;
     }
+    return ISSL_OK;
+}
+
+// ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
+static void launch_triple_scan(const issl_device *d, const TripleArgs &a, dim3 grid, bool fused, cudaStream_t st)
+{
+    if (fused) {
+        if (d->tv.pitch == 32) k_scan_triple_blocked<1, true><<<grid, kTripleThreads, 0, st>>>(a);
+        else if (d->tv.pitch == 64) k_scan_triple_blocked<2, true><<<grid, kTripleThreads, 0, st>>>(a);
+        else if (d->tv.pitch == 128) k_scan_triple_blocked<4, true><<<grid, kTripleThreads, 0, st>>>(a);
+        else k_scan_triple<true><<<grid, kTripleThreads, 0, st>>>(a);
+    } else {
+        if (d->tv.pitch == 32) k_scan_triple_blocked<1, false><<<grid, kTripleThreads, 0, st>>>(a);
+        else if (d->tv.pitch == 64) k_scan_triple_blocked<2, false><<<grid, kTripleThreads, 0, st>>>(a);
+        else if (d->tv.pitch == 128) k_scan_triple_blocked<4, false><<<grid, kTripleThreads, 0, st>>>(a);
+        else k_scan_triple<false><<<grid, kTripleThreads, 0, st>>>(a);
+    }
+}
+
+struct WaveScoring {   // what the fused tail / k_score_segments need to finish the guides
+    int fuse;              // 0, 1, 2 as ISSL_TRIPLE_FUSE
+    bool calcMit, calcCfd, checkExit;
+    int method;
+    double maximumSum;
+};
+
+static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint32_t s0, uint32_t ns,
+                       const uint8_t *doneMask, int maxDist, const WaveScoring &ws, EventTimer &timer, uint64_t *nHitsOut)
+{
+    unsigned long long *dc = d->counters.as<unsigned long long>();
+    CKR(ensure_visits(d, maxDist, st));
     const uint32_t v0 = d->waveStart[s0], v1 = d->waveStart[s0 + ns], nv = v1 - v0;
     CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
     k_wave_candidates<<<blocks_for((uint64_t)n * ns, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
@@ -863,15 +884,12 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             a.segOff = fuse ? d->segOff.as<uint64_t>() : nullptr; a.segCnt = fuse ? d->segCnt.as<uint32_t>() : nullptr;
             a.fuse = inScan ? 1 : 0; a.sp = sp;
             a.totMitOut = d->totMit2.as<double>(); a.totCfdOut = d->totCfd2.as<double>(); a.doneOut = d->done2.as<uint8_t>();
-            a.fusedHits = dc + 7;
+            a.fusedHits = dc + 7; a.maxRecords = dc + 2;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
             CK(cudaEventRecord(e0, st));
-            if (d->tv.pitch == 32) k_scan_triple_blocked<1><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
-            else if (d->tv.pitch == 64) k_scan_triple_blocked<2><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
-            else if (d->tv.pitch == 128) k_scan_triple_blocked<4><<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
-            else k_scan_triple<<<dim3(n, chunks), kTripleThreads, 0, st>>>(a);
+            launch_triple_scan(d, a, dim3(n, chunks), inScan, st);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
             CK(cudaMemcpyAsync(d->hCounters, dc, 8 * 8, cudaMemcpyDeviceToHost, st));
@@ -889,6 +907,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             }
         }
         *nHitsOut = d->hCounters[1];
+        if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] wave %u+%u: max records per guide %llu, general-pipeline hits %llu, fused hits %llu\n",
+                                          s0, ns, d->hCounters[2], d->hCounters[1], d->hCounters[7]);
         d->stats.streamed += d->hCounters[4];
         d->stats.bucket_visits += d->hCounters[5];
         if (fuse && d->hCounters[6]) {

@@ -14,6 +14,8 @@
 // unchanged.  "ref:" = /root/reference/src/ISSL/.
 #pragma once
 
+#include <type_traits>
+
 #include "issl_kernels.cuh"
 
 namespace issl {
@@ -144,7 +146,10 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint3
 // key buffer with one atomic, resolves the site ids with all threads and writes
 // key = guide << 35 | min(E) << 32 | id, which sorts back into the reference's visiting order.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kTripleHitCap = 512;   // per CTA; a guide with more hits goes through the general pipeline
+#ifndef ISSL_TRIPLE_HIT_CAP
+#define ISSL_TRIPLE_HIT_CAP 512
+#endif
+constexpr uint32_t kTripleHitCap = ISSL_TRIPLE_HIT_CAP;   // per CTA; a guide with more hits goes through the general pipeline
 
 // ------------------------------------------------------------------------------------------------
 // Finishing one guide inside a CTA (used by the fused tail of the bucket scan and by k_score_segments):
@@ -190,9 +195,10 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
         const uint32_t j = threadIdx.x + k * kTripleThreads;
         mySlice[k] = 7;
         if (j < n) {
-            uint32_t idRaw, slice;
-            uint64_t site;
+            uint32_t idRaw = 0, slice = 7;
+            uint64_t site = kSiteUnknown;
             load(j, idRaw, slice, site);
+            if (slice >= 5) continue;   // not a hit in this triple (the triple responsible for it reports it)
             const uint32_t id = idRaw & idMask;
             myId[k] = id; mySlice[k] = slice;
             atomicAdd(&ss.cnt[slice], 1u);
@@ -237,23 +243,24 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         const uint32_t j = threadIdx.x + k * kTripleThreads;
-        if (j < n) { pm[k] = ss.mit[j]; pc[k] = ss.cfd[j]; }
+        if (j < n && mySlice[k] < 5) { pm[k] = ss.mit[j]; pc[k] = ss.cfd[j]; }
     }
     __syncthreads();
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         const uint32_t j = threadIdx.x + k * kTripleThreads;
-        if (j < n) { const uint32_t r = ss.rank[j]; ss.mit[r] = pm[k]; ss.cfd[r] = pc[k]; }
+        if (j < n && mySlice[k] < 5) { const uint32_t r = ss.rank[j]; ss.mit[r] = pm[k]; ss.cfd[r] = pc[k]; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         double mit = sp.totMit[guide], cfd = sp.totCfd[guide];
         bool stop = false;
+        const uint32_t kept = ss.out[5];
         if (!sp.checkExit) {
 #pragma unroll 8
-            for (uint32_t i = 0; i < n; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
+            for (uint32_t i = 0; i < kept; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
         } else {
-            for (uint32_t i = 0; i < n && !stop; i++) {
+            for (uint32_t i = 0; i < kept && !stop; i++) {
                 mit = __dadd_rn(mit, ss.mit[i]);
                 cfd = __dadd_rn(cfd, ss.cfd[i]);
                 stop = exit_predicate(sp.method, mit, cfd, sp.maximumSum);
@@ -297,6 +304,7 @@ struct TripleArgs {
     double *totMitOut, *totCfdOut;   // state after it, written for EVERY guide (a re-launch after a buffer overflow
     uint8_t *doneOut;                // must start from the same state)
     unsigned long long *fusedHits;
+    unsigned long long *maxRecords;   // largest number of candidate records of one guide (diagnostics)
 };
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
@@ -326,9 +334,8 @@ struct TripleShared {
     uint32_t key[kTripleCount], res[kTripleCount];   // the guide's bucket key / residual (both halves) per triple
     uint4 mask[kTripleCount][4];  // bit-sliced scan: word p = all ones when bit p of the guide's residual is set
     unsigned long long count[2];
-    uint2 hits[kTripleHitCap];    // x: position in the triple's copy -- or key | slot << 24 when y bit 8 is set
-    uint32_t nHits;               // (blocked scan: position = offs[key] + slot - 1, and y bits 16..31 = the
-                                  // residual, which with the key is the whole site); y: triple | min(E) << 4
+    uint2 hits[kTripleHitCap];    // candidate records (record_y)
+    uint32_t nHits, nKept;
     unsigned long long base;
 };
 
@@ -343,31 +350,69 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
         for (int p = 0; p < 16; p++) m[p] = 0u - ((r >> p) & 1u);
     }
     if (threadIdx.x < 2) sh.count[threadIdx.x] = 0;
-    if (threadIdx.x == 0) sh.nHits = 0;
+    if (threadIdx.x == 0) { sh.nHits = 0; sh.nKept = 0; }
     __syncthreads();
+}
+
+// A hit record: an entry within its bucket's budget, i.e. a site within maxDist of the guide, found in the triple
+// responsible for it (record_keep).  The scan only notes where it is and which of the two residual slices match
+// exactly; id, site and scores are worked out later, for all records of the guide in parallel.
+//   x: blocked scan: bucket key | (entry + 1) << 24;  contiguous scan: position in the triple's copy
+//   y: triple (0..3) | exact slices of the visit's pattern (4..8) | slice p (9..11) | slice q (12..14) |
+//      residual matches on p (15), on q (16) | blocked scan (17)
+constexpr uint32_t kRecBlocked = 1u << 17;
+
+__device__ __forceinline__ uint32_t record_y(uint2 v, uint32_t pExact, uint32_t qExact, uint32_t flag)
+{
+    return ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | (((v.y >> 8) & 7u) << 9) | (((v.y >> 12) & 7u) << 12) |
+           (pExact << 15) | (qExact << 16) | flag;
+}
+
+// E = slices on which site and guide agree exactly; the record is a hit only in the triple responsible for E
+__device__ __forceinline__ bool record_keep(uint2 h, uint32_t &minE)
+{
+    const uint32_t E = ((h.y >> 4) & 31u) | (((h.y >> 15) & 1u) << ((h.y >> 9) & 7u)) | (((h.y >> 16) & 1u) << ((h.y >> 12) & 7u));
+    const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
+    minE = __ffs(E) - 1;
+    return resp == (h.y & 15u);
 }
 
 __device__ __forceinline__ uint32_t hit_position(const TripleView &tv, uint2 h)
 {
-    if (!(h.y & 256u)) return h.x;
+    if (!(h.y & kRecBlocked)) return h.x;
     return __ldg(tv.offs + (uint64_t)(h.y & 15u) * (kTripleBuckets + 1) + (h.x & 0xFFFFFFu)) + (h.x >> 24) - 1u;
 }
 
-// A residual within the bucket's budget: derive E, keep the hit only in the triple responsible for it.
-__device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t pExact,
-                                            uint32_t qExact, uint32_t recX, uint32_t recFlag)
+// site of a record of the blocked scan: bucket key + the entry's residual, read back from its sub-block (one
+// 64-byte line the scan touched a moment ago) and gathered from the 16 planes
+__device__ __forceinline__ uint64_t hit_site(const TripleView &tv, uint2 h)
 {
-    const uint32_t t = (v.x >> 24) & 15u;
-    const uint32_t E = (v.y & 31u) | (pExact << ((v.y >> 8) & 7u)) | (qExact << ((v.y >> 12) & 7u));
-    const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
-    if (resp != t) return;
-    const uint32_t minE = __ffs(E) - 1;
-    const uint2 h = make_uint2(recX, t | (minE << 4) | recFlag);
+    if (!(h.y & kRecBlocked)) return kSiteUnknown;
+    const uint32_t t = h.y & 15u, key = h.x & 0xFFFFFFu, entry = (h.x >> 24) - 1u, subs = tv.pitch / 32;
+    const uint32_t sub = entry / kSubEntries, sl = entry - sub * kSubEntries + 1u;
+    const uint4 *__restrict__ p = tv.blk + ((((uint64_t)t << 24) | key) * subs + sub) * 4;
+    const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    const uint32_t r =
+        ((q0.x >> sl) & 1u) | (((q0.y >> sl) & 1u) << 1) | (((q0.z >> sl) & 1u) << 2) | (((q0.w >> sl) & 1u) << 3) |
+        (((q1.x >> sl) & 1u) << 4) | (((q1.y >> sl) & 1u) << 5) | (((q1.z >> sl) & 1u) << 6) | (((q1.w >> sl) & 1u) << 7) |
+        (((q2.x >> sl) & 1u) << 8) | (((q2.y >> sl) & 1u) << 9) | (((q2.z >> sl) & 1u) << 10) | (((q2.w >> sl) & 1u) << 11) |
+        (((q3.x >> sl) & 1u) << 12) | (((q3.y >> sl) & 1u) << 13) | (((q3.z >> sl) & 1u) << 14) | (((q3.w >> sl) & 1u) << 15);
+    return ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
+           ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
+           ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
+}
+
+__device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 h)
+{
+    uint32_t slice;
+    if (!record_keep(h, slice)) return;   // found again, and reported, through the triple responsible for it
     const uint32_t slot = atomicAdd(&sh.nHits, 1u);
     if (slot < kTripleHitCap) {
         sh.hits[slot] = h;
     } else {   // rare (dense repeat families): straight to the general pipeline's buffer
-        const uint32_t id = a.tv.ids[(uint64_t)t * a.tv.stride + hit_position(a.tv, h)] & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u);
+        uint32_t minE;
+        if (!record_keep(h, minE)) return;
+        const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)] & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u);
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
         if (gs < a.hitCap) a.hitKeys[gs] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | id;
     }
@@ -396,7 +441,7 @@ __device__ __forceinline__ void triple_vector(const TripleArgs &a, TripleShared 
         pass &= pass - 1;
         const uint32_t ws = (i & 4u) ? ((i & 2u) ? w3 : w2) : ((i & 2u) ? w1 : w0);
         const uint32_t x16 = (ws >> ((i & 1u) * 16u)) & 0xFFFFu;
-        triple_push(a, sh, guide, v, (uint32_t)((x16 & 0xFFu) == 0), (uint32_t)((x16 >> 8) == 0), recX(i), recFlag);
+        triple_push(a, sh, guide, make_uint2(recX(i), record_y(v, (uint32_t)((x16 & 0xFFu) == 0), (uint32_t)((x16 >> 8) == 0), recFlag)));
     }
 }
 
@@ -417,16 +462,6 @@ __device__ __forceinline__ void triple_bucket(const TripleArgs &a, TripleShared 
     }
 }
 
-// site of a hit of the blocked scan: bucket key + residual
-__device__ __forceinline__ uint64_t hit_site(uint2 h)
-{
-    if (!(h.y & 256u)) return kSiteUnknown;
-    const uint32_t t = h.y & 15u, key = h.x & 0xFFFFFFu, r = h.y >> 16;
-    return ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
-           ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
-           ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
-}
-
 // Shared memory of the scan kernels: the scan state; the grouping arrays of the fused tail reuse it once every
 // thread has taken its hits out.
 struct TripleSmem {
@@ -436,10 +471,16 @@ struct TripleSmem {
     };
     ScoreShared score;
 };
+// ... without the fused tail: the scan state alone.  Less shared memory per SM is more L1, and the L1 holds the lines
+// of the loads in flight: the scan is measurably faster with it.
+struct TripleSmemScan {
+    TripleShared scan;
+};
 
 // end of the scan: finish the guide here (fused), or hand its hits on -- as a segment for k_score_segments or as
 // keys for the general pipeline
-__device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleSmem &sm, uint32_t guide, uint64_t g,
+template <bool FUSED, class Smem>
+__device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, uint32_t guide, uint64_t g,
                                                 unsigned long long entries, unsigned long long visited)
 {
     TripleShared &sh = sm.scan;
@@ -450,50 +491,64 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, TripleSmem 
     __syncthreads();
     const uint32_t nAll = sh.nHits, nLocal = min(nAll, kTripleHitCap);
     if (a.streamed && threadIdx.x < 2 && sh.count[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, sh.count[threadIdx.x]);
+    if (a.maxRecords && threadIdx.x == 0) atomicMax(a.maxRecords, (unsigned long long)nAll);
     if (a.fuse && threadIdx.x == 0) {   // state after this wave unless the fused tail below changes it
         a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 0;
     }
-    if (a.fuse && nAll <= kTripleHitCap) {
+    if constexpr (FUSED) if (a.fuse && nAll <= kTripleHitCap) {
         if (nAll == 0) return;
-        if (threadIdx.x == 0) atomicAdd(a.fusedHits, (unsigned long long)nAll);
         __syncthreads();   // the defaults above are in place before score_guide's writer thread runs
         score_guide(sm.score, sm.group, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
                     [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
                         const uint2 h = sh.hits[j];
+                        if (!record_keep(h, slice)) { slice = 7; return; }
                         idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
-                        slice = (h.y >> 4) & 7u;
-                        site = hit_site(h);
+                        site = hit_site(a.tv, h);
                     });
+        if (threadIdx.x == 0 && sm.score.out[5]) atomicAdd(a.fusedHits, (unsigned long long)sm.score.out[5]);
         return;
     }
+    // hand the hits on: de-duplicate, compact, reserve a range of the segment / key buffer, resolve ids
+    constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
     const bool segment = a.segCnt && nAll <= kTripleHitCap;
-    if (threadIdx.x == 0 && nLocal) {
+    uint32_t myPos[kPerThread], myMinE[kPerThread];
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        const uint32_t j = threadIdx.x + k * kTripleThreads;
+        myPos[k] = 0xFFFFFFFFu;
+        if (j < nLocal && record_keep(sh.hits[j], myMinE[k])) myPos[k] = atomicAdd(&sh.nKept, 1u);
+    }
+    __syncthreads();
+    const uint32_t nKept = sh.nKept;
+    if (threadIdx.x == 0 && nKept) {
         if (segment) {
-            sh.base = atomicAdd(a.segCount, (unsigned long long)nLocal);
+            sh.base = atomicAdd(a.segCount, (unsigned long long)nKept);
             a.segOff[guide] = sh.base;
-            if (sh.base + nLocal <= a.segCap) a.segCnt[guide] = nLocal;   // else the launch is repeated with a larger buffer
+            if (sh.base + nKept <= a.segCap) a.segCnt[guide] = nKept;   // else the launch is repeated with a larger buffer
         } else {
-            sh.base = atomicAdd(a.hitCount, (unsigned long long)nLocal);
+            sh.base = atomicAdd(a.hitCount, (unsigned long long)nKept);
         }
     }
     __syncthreads();
     const uint32_t idMask = a.tv.occFlag ? 0x7FFFFFFFu : ~0u;
-    for (uint32_t j = threadIdx.x; j < nLocal; j += kTripleThreads) {
-        const uint2 h = sh.hits[j];
-        const uint32_t t = h.y & 15u, minE = (h.y >> 4) & 7u;
-        const uint32_t id = __ldg(a.tv.ids + (uint64_t)t * a.tv.stride + hit_position(a.tv, h));
-        const unsigned long long slot = sh.base + j;
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        if (myPos[k] == 0xFFFFFFFFu) continue;
+        const uint2 h = sh.hits[threadIdx.x + k * kTripleThreads];
+        const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+        const unsigned long long slot = sh.base + myPos[k];
         if (!segment) {
-            if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | (id & idMask);
+            if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)myMinE[k] << 32) | (id & idMask);
         } else if (slot < a.segCap) {
-            a.segKeys[slot] = ((uint64_t)minE << 32) | id;
-            a.segSites[slot] = hit_site(h);
+            a.segKeys[slot] = ((uint64_t)myMinE[k] << 32) | id;
+            a.segSites[slot] = hit_site(a.tv, h);
         }
     }
 }
 
 // contiguous copy: offsets, then the bucket (two dependent round trips; the next visit's offsets are requested
 // before the current bucket is processed)
+template <bool FUSED>
 __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
@@ -503,7 +558,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
         }
         return;
     }
-    __shared__ TripleSmem sm;
+    __shared__ typename std::conditional<FUSED, TripleSmem, TripleSmemScan>::type sm;
     TripleShared &sh = sm.scan;
     const uint64_t g = a.guides[guide];
     triple_prologue(a, sh, g);
@@ -540,7 +595,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
         if (lane8 == 0) visited++;
         e = en; v = vn; start = startn; end = endn;
     }
-    triple_epilogue(a, sm, guide, g, entries, visited);
+    triple_epilogue<FUSED>(a, sm, guide, g, entries, visited);
 }
 
 // blocked, bit-sliced copy: ONE aligned read per visit.  SUBS lanes share a visit, each owning a 64-byte
@@ -554,7 +609,7 @@ __device__ __forceinline__ void bs_full_add(uint32_t a, uint32_t b, uint32_t c, 
     carry = (a & b) | (c & (a ^ b));
 }
 
-template <int SUBS>
+template <int SUBS, bool FUSED>
 __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
@@ -564,7 +619,7 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
         }
         return;
     }
-    __shared__ TripleSmem sm;
+    __shared__ typename std::conditional<FUSED, TripleSmem, TripleSmemScan>::type sm;
     TripleShared &sh = sm.scan;
     const uint64_t g = a.guides[guide];
     triple_prologue(a, sh, g);
@@ -579,7 +634,8 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
         const uint2 v = __ldg(visits + e);
         const uint32_t t = (v.x >> 24) & 15u, key = sh.key[t] ^ (v.x & 0xFFFFFFu);
         const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
-        const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+        // read once: streaming loads, so that the visit table and the offsets keep their place in L1
+        const uint4 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2), q3 = __ldcs(p + 3);
         if (sub == 0) visited++;
         if (q1.y & 1u) {   // the bucket did not fit its block: contiguous copy
             const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
@@ -621,19 +677,13 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
             do {
                 const uint32_t sl = __ffs(pass) - 1;
                 pass &= pass - 1;
-                // the slot's residual, gathered back from the 16 planes (with the bucket key it is the whole site)
-                const uint32_t r =
-                    ((q0.x >> sl) & 1u) | (((q0.y >> sl) & 1u) << 1) | (((q0.z >> sl) & 1u) << 2) | (((q0.w >> sl) & 1u) << 3) |
-                    (((q1.x >> sl) & 1u) << 4) | (((q1.y >> sl) & 1u) << 5) | (((q1.z >> sl) & 1u) << 6) | (((q1.w >> sl) & 1u) << 7) |
-                    (((q2.x >> sl) & 1u) << 8) | (((q2.y >> sl) & 1u) << 9) | (((q2.z >> sl) & 1u) << 10) | (((q2.w >> sl) & 1u) << 11) |
-                    (((q3.x >> sl) & 1u) << 12) | (((q3.y >> sl) & 1u) << 13) | (((q3.z >> sl) & 1u) << 14) | (((q3.w >> sl) & 1u) << 15);
-                // entry number sub*31 + sl - 1 of the bucket, stored as "slot" = entry + 1 (hit_position)
-                triple_push(a, sh, guide, v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, key | ((sub * kSubEntries + sl) << 24),
-                            256u | (r << 16));
+                // entry number sub*31 + sl - 1 of the bucket, recorded as entry + 1
+                triple_push(a, sh, guide, make_uint2(key | ((sub * kSubEntries + sl) << 24),
+                                                     record_y(v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, kRecBlocked)));
             } while (pass);
         }
     }
-    triple_epilogue(a, sm, guide, g, entries, visited);
+    triple_epilogue<FUSED>(a, sm, guide, g, entries, visited);
 }
 
 // ------------------------------------------------------------------------------------------------
