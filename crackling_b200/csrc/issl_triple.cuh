@@ -39,8 +39,8 @@ struct TripleView {
     // blocked, bit-sliced copy of res (optional): bucket k of triple t owns pitch/32 sub-blocks of 64 bytes at
     // ((t << 24) | k) * pitch * 2 bytes.  A sub-block holds up to 31 residuals TRANSPOSED: word p (p = 0..15) is
     // bit p of the residuals of its 32 slots; slot 0 is not a residual: its column holds the number of
-    // residuals in the sub-block (bits 0..4) and the flag "this bucket does not fit, read res/offs" (bit 5).
-    // A bucket fills sub-block 0 first.  One aligned read per visit, no offset lookup in front of it, and 32
+    // residuals in the sub-block (bits 0..4) and the flag "the bucket has more entries than its block holds: the
+    // rest is in res/offs" (bit 5).  A bucket fills sub-block 0 first.  One aligned read per visit, no offset lookup in front of it, and 32
     // residuals are tested with ~30 bitwise instructions.
     const uint4 *blk;
     uint32_t pitch;         // 16-bit slots per bucket: 0 (no blocked copy), 32, 64 or 128
@@ -107,19 +107,17 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint3
     uint32_t w[16];
 #pragma unroll
     for (int p = 0; p < 16; p++) w[p] = 0;
-    if (count > subs * kSubEntries) {
-        w[5] = 1u;                                   // does not fit: every sub-block carries the flag
-    } else {
-        const uint32_t first = sub * kSubEntries;
-        const uint32_t n = count > first ? min(count - first, kSubEntries) : 0u;
-        for (uint32_t e = 0; e < n; e++) {
-            const uint32_t r = res[start + first + e];
+    // the block holds the bucket's first subs*31 entries; the flag says that more follow in the contiguous copy
+    const uint32_t first = sub * kSubEntries;
+    const uint32_t n = count > first ? min(count - first, kSubEntries) : 0u;
+    for (uint32_t e = 0; e < n; e++) {
+        const uint32_t r = res[start + first + e];
 #pragma unroll
-            for (int p = 0; p < 16; p++) w[p] |= ((r >> p) & 1u) << (e + 1);
-        }
-#pragma unroll
-        for (int p = 0; p < 5; p++) w[p] |= (n >> p) & 1u;
+        for (int p = 0; p < 16; p++) w[p] |= ((r >> p) & 1u) << (e + 1);
     }
+#pragma unroll
+    for (int p = 0; p < 5; p++) w[p] |= (n >> p) & 1u;
+    if (count > subs * kSubEntries) w[5] |= 1u;
     uint4 *o = blk + i * 4;
     o[0] = make_uint4(w[0], w[1], w[2], w[3]);
     o[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -333,7 +331,7 @@ constexpr uint64_t kRespLo = triple_resp_pack(0), kRespHi = triple_resp_pack(16)
 struct TripleShared {
     uint32_t key[kTripleCount], res[kTripleCount];   // the guide's bucket key / residual (both halves) per triple
     uint4 mask[kTripleCount][4];  // bit-sliced scan: word p = all ones when bit p of the guide's residual is set
-    unsigned long long count[2];
+    uint32_t count[2];            // entries / visits of this CTA (native 32-bit shared-memory atomics)
     uint2 hits[kTripleHitCap];    // candidate records (record_y)
     uint32_t nHits, nKept;
     unsigned long long base;
@@ -481,16 +479,19 @@ struct TripleSmemScan {
 // keys for the general pipeline
 template <bool FUSED, class Smem>
 __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, uint32_t guide, uint64_t g,
-                                                unsigned long long entries, unsigned long long visited)
+                                                uint32_t entries, uint32_t visited)
 {
     TripleShared &sh = sm.scan;
     if (a.streamed) {
-        if (entries) atomicAdd(&sh.count[0], entries);
-        if (visited) atomicAdd(&sh.count[1], visited);
+        for (int o = 16; o > 0; o >>= 1) {
+            entries += __shfl_down_sync(0xffffffffu, entries, o);
+            visited += __shfl_down_sync(0xffffffffu, visited, o);
+        }
+        if ((threadIdx.x & 31u) == 0) { atomicAdd(&sh.count[0], entries); atomicAdd(&sh.count[1], visited); }
     }
     __syncthreads();
     const uint32_t nAll = sh.nHits, nLocal = min(nAll, kTripleHitCap);
-    if (a.streamed && threadIdx.x < 2 && sh.count[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, sh.count[threadIdx.x]);
+    if (a.streamed && threadIdx.x < 2 && sh.count[threadIdx.x]) atomicAdd(a.streamed + threadIdx.x, (unsigned long long)sh.count[threadIdx.x]);
     if (a.maxRecords && threadIdx.x == 0) atomicMax(a.maxRecords, (unsigned long long)nAll);
     if (a.fuse && threadIdx.x == 0) {   // state after this wave unless the fused tail below changes it
         a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 0;
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
     const uint32_t octet = threadIdx.x >> 3, lane8 = threadIdx.x & 7u;
     constexpr uint32_t kOctets = kTripleThreads / 8;
     const uint32_t v0 = blockIdx.y * a.visitsPerCta, v1 = min(a.nVisits, v0 + a.visitsPerCta);
-    unsigned long long entries = 0, visited = 0;
+    uint32_t entries = 0, visited = 0;
     const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
 
     uint32_t e = v0 + octet;
@@ -637,12 +638,11 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
         // read once: streaming loads, so that the visit table and the offsets keep their place in L1
         const uint4 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2), q3 = __ldcs(p + 3);
         if (sub == 0) visited++;
-        if (q1.y & 1u) {   // the bucket did not fit its block: contiguous copy
+        if (q1.y & 1u) {   // more entries than the block holds (~1 % of the visits at human scale): the rest is contiguous
             const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
-            const uint32_t start = __ldg(o), end = __ldg(o + 1);
+            const uint32_t start = __ldg(o) + SUBS * kSubEntries, end = __ldg(o + 1);
             triple_bucket(a, sh, guide, v, start, end, sub, SUBS);
             if (sub == 0) entries += end - start;
-            continue;
         }
         const uint32_t cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
         if (cnt == 0) continue;
