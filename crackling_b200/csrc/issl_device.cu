@@ -55,6 +55,8 @@ struct issl_device {
     DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
+    int tripleFlush = -1;            // ISSL_TRIPLE_FLUSH: 1 / 0 force the scan variant that flushes full record lists; -1 automatic
+    double lastHitsPerGuide = 0;     // of the previous scoring call on this handle
     int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments from
                                      // per-guide segments, 0 = everything through the general sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
@@ -297,6 +299,7 @@ static int new_device(int cuda_device, issl_device **out)
         const long v = atol(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
     }
+    if (const char *e = getenv("ISSL_TRIPLE_FLUSH")) d->tripleFlush = atoi(e) != 0;
     if (const char *e = getenv("ISSL_TRIPLE_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->tripleFuse = v; }
     if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
         const long v = atol(e);
@@ -819,19 +822,21 @@ static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
 }
 
 // ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
-static void launch_triple_scan(const issl_device *d, const TripleArgs &a, dim3 grid, bool fused, cudaStream_t st)
+template <bool FUSED, bool FLUSH>
+static void launch_triple_scan_t(const issl_device *d, const TripleArgs &a, dim3 grid, cudaStream_t st)
 {
-    if (fused) {
-        if (d->tv.pitch == 32) k_scan_triple_blocked<1, true><<<grid, kTripleThreads, 0, st>>>(a);
-        else if (d->tv.pitch == 64) k_scan_triple_blocked<2, true><<<grid, kTripleThreads, 0, st>>>(a);
-        else if (d->tv.pitch == 128) k_scan_triple_blocked<4, true><<<grid, kTripleThreads, 0, st>>>(a);
-        else k_scan_triple<true><<<grid, kTripleThreads, 0, st>>>(a);
-    } else {
-        if (d->tv.pitch == 32) k_scan_triple_blocked<1, false><<<grid, kTripleThreads, 0, st>>>(a);
-        else if (d->tv.pitch == 64) k_scan_triple_blocked<2, false><<<grid, kTripleThreads, 0, st>>>(a);
-        else if (d->tv.pitch == 128) k_scan_triple_blocked<4, false><<<grid, kTripleThreads, 0, st>>>(a);
-        else k_scan_triple<false><<<grid, kTripleThreads, 0, st>>>(a);
-    }
+    if (d->tv.pitch == 32) k_scan_triple_blocked<1, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 64) k_scan_triple_blocked<2, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 128) k_scan_triple_blocked<4, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
+    else k_scan_triple<FUSED><<<grid, kTripleThreads, 0, st>>>(a);
+}
+
+// flush: the variant that empties a full record list into the general pipeline's buffer in the middle of the scan
+// (one barrier per round of visits) -- chosen when guides are expected to have more hits than a CTA can hold
+static void launch_triple_scan(const issl_device *d, const TripleArgs &a, dim3 grid, bool fused, bool flush, cudaStream_t st)
+{
+    if (fused) { if (flush) launch_triple_scan_t<true, true>(d, a, grid, st); else launch_triple_scan_t<true, false>(d, a, grid, st); }
+    else { if (flush) launch_triple_scan_t<false, true>(d, a, grid, st); else launch_triple_scan_t<false, false>(d, a, grid, st); }
 }
 
 struct WaveScoring {   // what the fused tail / k_score_segments need to finish the guides
@@ -859,6 +864,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         chunks = std::min<uint32_t>(chunks, 65535u);
         // finishing a guide where its hits are needs all of them in one CTA
         const bool inScan = ws.fuse == 2 && chunks == 1, fuse = ws.fuse == 1 && chunks == 1;
+        // many hits per guide expected (large maxDist; the previous call saw repeat families): flush variant
+        const bool flush = d->tripleFlush == 1 || (d->tripleFlush < 0 && (maxDist >= 5 || d->lastHitsPerGuide > 0.6 * kTripleHitCap));
         if (fuse) { CKR(d->segOff.ensure(n * 8ull)); CKR(d->segCnt.ensure(n * 4ull)); }
         if (inScan) { CKR(d->totMit2.ensure(n * 8ull)); CKR(d->totCfd2.ensure(n * 8ull)); CKR(d->done2.ensure(n)); }
         ScoreParams sp;
@@ -889,7 +896,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
             CK(cudaEventRecord(e0, st));
-            launch_triple_scan(d, a, dim3(n, chunks), inScan, st);
+            launch_triple_scan(d, a, dim3(n, chunks), inScan, flush, st);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
             CK(cudaMemcpyAsync(d->hCounters, dc, 8 * 8, cudaMemcpyDeviceToHost, st));
@@ -1161,6 +1168,7 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, t0, t1));
     d->stats.total_ms = ms;
+    d->lastHitsPerGuide = n ? (double)d->stats.hits / (double)n : 0.0;
     for (auto &pr : timer.scanPairs) {
         CK(cudaEventElapsedTime(&ms, d->evPool[pr.first], d->evPool[pr.second]));
         d->stats.scan_ms += ms;

@@ -334,6 +334,7 @@ struct TripleShared {
     uint32_t count[2];            // entries / visits of this CTA (native 32-bit shared-memory atomics)
     uint2 hits[kTripleHitCap];    // candidate records (record_y)
     uint32_t nHits, nKept;
+    uint32_t flushed;             // the guide's records were flushed to the general pipeline's buffer at least once
     unsigned long long base;
 };
 
@@ -348,7 +349,7 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
         for (int p = 0; p < 16; p++) m[p] = 0u - ((r >> p) & 1u);
     }
     if (threadIdx.x < 2) sh.count[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { sh.nHits = 0; sh.nKept = 0; }
+    if (threadIdx.x == 0) { sh.nHits = 0; sh.nKept = 0; sh.flushed = 0; }
     __syncthreads();
 }
 
@@ -414,6 +415,30 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
         if (gs < a.hitCap) a.hitKeys[gs] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | id;
     }
+}
+
+// Guides with thousands of hits (maxDist 5 and 6, dense repeat families): when the CTA's record list is nearly full,
+// all threads empty it into the general pipeline's key buffer (one reservation, ids resolved in parallel) and the
+// scan goes on; such a guide is finished by the general pipeline.  Called by all threads of the CTA.
+constexpr uint32_t kTripleFlushAt = kTripleHitCap - 128;
+
+__device__ __forceinline__ void triple_flush(const TripleArgs &a, TripleShared &sh, uint32_t guide)
+{
+    const uint32_t n = min(sh.nHits, kTripleHitCap);
+    if (threadIdx.x == 0) sh.base = atomicAdd(a.hitCount, (unsigned long long)n);
+    __syncthreads();
+    const uint32_t idMask = a.tv.occFlag ? 0x7FFFFFFFu : ~0u;
+    for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
+        const uint2 h = sh.hits[j];
+        uint32_t minE;
+        record_keep(h, minE);
+        const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+        const unsigned long long slot = sh.base + j;
+        if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | (id & idMask);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { sh.nHits = 0; sh.flushed = 1; }
+    __syncthreads();
 }
 
 // 8 residuals of one 16-byte vector against the guide's; `valid` masks the slots that belong to the bucket
@@ -496,7 +521,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
     if (a.fuse && threadIdx.x == 0) {   // state after this wave unless the fused tail below changes it
         a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 0;
     }
-    if constexpr (FUSED) if (a.fuse && nAll <= kTripleHitCap) {
+    if constexpr (FUSED) if (a.fuse && nAll <= kTripleHitCap && !sh.flushed) {
         if (nAll == 0) return;
         __syncthreads();   // the defaults above are in place before score_guide's writer thread runs
         score_guide(sm.score, sm.group, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
@@ -511,7 +536,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
     }
     // hand the hits on: de-duplicate, compact, reserve a range of the segment / key buffer, resolve ids
     constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
-    const bool segment = a.segCnt && nAll <= kTripleHitCap;
+    const bool segment = a.segCnt && nAll <= kTripleHitCap && !sh.flushed;
     uint32_t myPos[kPerThread], myMinE[kPerThread];
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
@@ -610,7 +635,7 @@ __device__ __forceinline__ void bs_full_add(uint32_t a, uint32_t b, uint32_t c, 
     carry = (a & b) | (c & (a ^ b));
 }
 
-template <int SUBS, bool FUSED>
+template <int SUBS, bool FUSED, bool FLUSH>
 __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(const TripleArgs a)
 {
     const uint32_t guide = blockIdx.x;
@@ -631,7 +656,7 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
     uint32_t entries = 0, visited = 0;
     const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
 
-    for (uint32_t e = v0 + vslot; e < v1; e += V) {
+    auto visit = [&](uint32_t e) {
         const uint2 v = __ldg(visits + e);
         const uint32_t t = (v.x >> 24) & 15u, key = sh.key[t] ^ (v.x & 0xFFFFFFu);
         const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
@@ -645,7 +670,7 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
             if (sub == 0) entries += end - start;
         }
         const uint32_t cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
-        if (cnt == 0) continue;
+        if (cnt == 0) return;
         entries += cnt;
         const uint4 m0 = sh.mask[t][0], m1 = sh.mask[t][1], m2 = sh.mask[t][2], m3 = sh.mask[t][3];
         const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
@@ -682,6 +707,11 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
                                                      record_y(v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, kRecBlocked)));
             } while (pass);
         }
+    };
+    for (uint32_t e0 = v0; e0 < v1; e0 += V) {   // the same number of rounds for every thread of the CTA
+        if (e0 + vslot < v1) visit(e0 + vslot);
+        if constexpr (FLUSH)
+            if (__syncthreads_or(sh.nHits > kTripleFlushAt)) triple_flush(a, sh, guide);
     }
     triple_epilogue<FUSED>(a, sm, guide, g, entries, visited);
 }

@@ -236,14 +236,15 @@ def test_triple_layout_sub_bucket_scan(triple_max):
     dev.close()
 
 
-@pytest.mark.parametrize("fuse,blocks", [(2, "64"), (2, "32"), (1, "64"), (0, "0"), (2, "0")])
-def test_triple_large_batch_tails(fuse, blocks):
+@pytest.mark.parametrize("fuse,blocks,flush", [(2, "64", "0"), (2, "32", "0"), (1, "64", "0"), (0, "0", "0"), (2, "0", "0"),
+                                               (2, "64", "1"), (1, "32", "1"), (0, "64", "1")])
+def test_triple_large_batch_tails(fuse, blocks, flush):
     """With at least 148 x 16 guides in a batch every guide gets one CTA, and the scan's tails come into play: 2 = the
     CTA sorts, scores and accumulates the guide's hits itself (fused), 1 = per-guide segments finished by
     k_score_segments, 0 = general pipeline; guides with more than 512 hits (dense families here) always take the
-    general pipeline, mixed with the others in one batch.  Blocked (bit-sliced sub-blocks of 31/62 entries, with
-    buckets that do not fit) and contiguous copies.  Everything must stay bit-identical to the oracle, early exits
-    included."""
+    general pipeline, mixed with the others in one batch -- with flush = 1 through the scan variant that empties a
+    full record list in the middle of the scan.  Blocked (bit-sliced sub-blocks of 31/62 entries, with buckets that
+    do not fit) and contiguous copies.  Everything must stay bit-identical to the oracle, early exits included."""
     text = td.make_offtargets(51, n_random=120_000, n_families=30, family_size=900, max_sub_rate=0.12)
     img = oracle.create_index(text, 20, 8)
     rng = np.random.default_rng(52)
@@ -259,19 +260,20 @@ def test_triple_large_batch_tails(fuse, blocks):
     assert guides.size >= 148 * 16
     os.environ["ISSL_TRIPLE_FUSE"] = str(fuse)
     os.environ["ISSL_TRIPLE_BLOCKS"] = blocks
+    os.environ["ISSL_TRIPLE_FLUSH"] = flush
     try:
         dev = cb.Device.from_index(cb.Index(img), 0, "triple")
     finally:
-        del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"]
+        del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"], os.environ["ISSL_TRIPLE_FLUSH"]
     assert dev.info["triple_block_bytes"] == 2 * int(blocks)
     seen_big = False
     for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 5), ("mit", 0, 2), ("cfd", 20, 4)):
         want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
         mit, cfd = dev.score(guides, md, thr, method)
         if method != "cfd":
-            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (fuse, blocks, method, thr, md)
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (fuse, blocks, flush, method, thr, md)
         if method != "mit":
-            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (fuse, blocks, method, thr, md)
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (fuse, blocks, flush, method, thr, md)
         st = dev.stats
         if thr == 0:
             assert st["candidates"] == int(want["candidates"].sum())
