@@ -357,23 +357,23 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
 // responsible for it (record_keep).  The scan only notes where it is and which of the two residual slices match
 // exactly; id, site and scores are worked out later, for all records of the guide in parallel.
 //   x: blocked scan: bucket key | (entry + 1) << 24;  contiguous scan: position in the triple's copy
-//   y: triple (0..3) | exact slices of the visit's pattern (4..8) | slice p (9..11) | slice q (12..14) |
-//      residual matches on p (15), on q (16) | blocked scan (17)
-constexpr uint32_t kRecBlocked = 1u << 17;
+//   y: triple (0..3) | exact slices of the visit's pattern (4..8) | residual matches on slice p (9), on q (10) |
+//      blocked scan (11) | blocked scan: the entry's residual (16..31) -- with the bucket key, the whole site
+constexpr uint32_t kRecBlocked = 1u << 11;
 
 __device__ __forceinline__ uint32_t record_y(uint2 v, uint32_t pExact, uint32_t qExact, uint32_t flag)
 {
-    return ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | (((v.y >> 8) & 7u) << 9) | (((v.y >> 12) & 7u) << 12) |
-           (pExact << 15) | (qExact << 16) | flag;
+    return ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | (pExact << 9) | (qExact << 10) | flag;
 }
 
 // E = slices on which site and guide agree exactly; the record is a hit only in the triple responsible for E
 __device__ __forceinline__ bool record_keep(uint2 h, uint32_t &minE)
 {
-    const uint32_t E = ((h.y >> 4) & 31u) | (((h.y >> 15) & 1u) << ((h.y >> 9) & 7u)) | (((h.y >> 16) & 1u) << ((h.y >> 12) & 7u));
+    const uint32_t t = h.y & 15u;
+    const uint32_t E = ((h.y >> 4) & 31u) | (((h.y >> 9) & 1u) << c_tripleSlices[t][3]) | (((h.y >> 10) & 1u) << c_tripleSlices[t][4]);
     const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
     minE = __ffs(E) - 1;
-    return resp == (h.y & 15u);
+    return resp == t;
 }
 
 __device__ __forceinline__ uint32_t hit_position(const TripleView &tv, uint2 h)
@@ -382,29 +382,21 @@ __device__ __forceinline__ uint32_t hit_position(const TripleView &tv, uint2 h)
     return __ldg(tv.offs + (uint64_t)(h.y & 15u) * (kTripleBuckets + 1) + (h.x & 0xFFFFFFu)) + (h.x >> 24) - 1u;
 }
 
-// site of a record of the blocked scan: bucket key + the entry's residual, read back from its sub-block (one
-// 64-byte line the scan touched a moment ago) and gathered from the 16 planes
+// site of a record of the blocked scan: bucket key + the entry's residual
 __device__ __forceinline__ uint64_t hit_site(const TripleView &tv, uint2 h)
 {
     if (!(h.y & kRecBlocked)) return kSiteUnknown;
-    const uint32_t t = h.y & 15u, key = h.x & 0xFFFFFFu, entry = (h.x >> 24) - 1u, subs = tv.pitch / 32;
-    const uint32_t sub = entry / kSubEntries, sl = entry - sub * kSubEntries + 1u;
-    const uint4 *__restrict__ p = tv.blk + ((((uint64_t)t << 24) | key) * subs + sub) * 4;
-    const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
-    const uint32_t r =
-        ((q0.x >> sl) & 1u) | (((q0.y >> sl) & 1u) << 1) | (((q0.z >> sl) & 1u) << 2) | (((q0.w >> sl) & 1u) << 3) |
-        (((q1.x >> sl) & 1u) << 4) | (((q1.y >> sl) & 1u) << 5) | (((q1.z >> sl) & 1u) << 6) | (((q1.w >> sl) & 1u) << 7) |
-        (((q2.x >> sl) & 1u) << 8) | (((q2.y >> sl) & 1u) << 9) | (((q2.z >> sl) & 1u) << 10) | (((q2.w >> sl) & 1u) << 11) |
-        (((q3.x >> sl) & 1u) << 12) | (((q3.y >> sl) & 1u) << 13) | (((q3.z >> sl) & 1u) << 14) | (((q3.w >> sl) & 1u) << 15);
+    const uint32_t t = h.y & 15u, key = h.x & 0xFFFFFFu, r = h.y >> 16;
     return ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
            ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
            ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
 }
 
+template <bool CHECKED = false>
 __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 h)
 {
     uint32_t slice;
-    if (!record_keep(h, slice)) return;   // found again, and reported, through the triple responsible for it
+    if (!CHECKED && !record_keep(h, slice)) return;   // found again, and reported, through the triple responsible for it
     const uint32_t slot = atomicAdd(&sh.nHits, 1u);
     if (slot < kTripleHitCap) {
         sh.hits[slot] = h;
@@ -702,9 +694,17 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
             do {
                 const uint32_t sl = __ffs(pass) - 1;
                 pass &= pass - 1;
+                const uint32_t y = record_y(v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, kRecBlocked);
+                uint32_t minE;
+                if (!record_keep(make_uint2(0u, y), minE)) continue;   // reported through the triple responsible for it
+                // the entry's residual, gathered back from the 16 planes (issue slots are free, DRAM lines are not)
+                const uint32_t r =
+                    ((q0.x >> sl) & 1u) | (((q0.y >> sl) & 1u) << 1) | (((q0.z >> sl) & 1u) << 2) | (((q0.w >> sl) & 1u) << 3) |
+                    (((q1.x >> sl) & 1u) << 4) | (((q1.y >> sl) & 1u) << 5) | (((q1.z >> sl) & 1u) << 6) | (((q1.w >> sl) & 1u) << 7) |
+                    (((q2.x >> sl) & 1u) << 8) | (((q2.y >> sl) & 1u) << 9) | (((q2.z >> sl) & 1u) << 10) | (((q2.w >> sl) & 1u) << 11) |
+                    (((q3.x >> sl) & 1u) << 12) | (((q3.y >> sl) & 1u) << 13) | (((q3.z >> sl) & 1u) << 14) | (((q3.w >> sl) & 1u) << 15);
                 // entry number sub*31 + sl - 1 of the bucket, recorded as entry + 1
-                triple_push(a, sh, guide, make_uint2(key | ((sub * kSubEntries + sl) << 24),
-                                                     record_y(v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, kRecBlocked)));
+                triple_push<true>(a, sh, guide, make_uint2(key | ((sub * kSubEntries + sl) << 24), y | (r << 16)));
             } while (pass);
         }
     };
