@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
             "issl_score_device": ([vp, vp, sz, i, d, i, vp, vp, vp], i),
             "issl_score_hits": ([vp, vp, sz, i, d, i, vp, vp, vp, vp, vp, vp, sz, C.POINTER(sz)], i),
             "issl_last_stats": ([vp, C.POINTER(_Stats)], i),
+            "issl_guide_filters": ([vp, C.c_char_p, sz, vp, vp, vp], i),
             "issl_local_mit_score": ([u64, sz], d),
             "issl_mit_table": ([sz, sz, vp, vp, sz, C.POINTER(u64)], sz),
             "issl_triple_visits": ([C.c_int, vp, sz, vp], sz),
@@ -254,6 +255,15 @@ class Device:
              "triple_block_bytes": int(s.triple_block_bytes)}
         d.update(_info_dict(s.info))
         return d
+
+    def guide_filters(self, text23: bytes):
+        """(flags, AT %, packed 20-mers) of n lines of 23 characters + LF (issl_guide_filters)."""
+        n = len(text23) // 24
+        flags = np.zeros(n, dtype=np.uint8)
+        at = np.zeros(n, dtype=np.float64)
+        packed = np.zeros(n, dtype=np.uint64)
+        _check(lib().issl_guide_filters(self._h, text23, len(text23), flags.ctypes.data, at.ctypes.data, packed.ctypes.data))
+        return flags, at, packed
 
     @property
     def stats(self) -> dict:

@@ -1210,6 +1210,37 @@ extern "C" int issl_score_hits(issl_device *d, const uint64_t *guides, size_t n,
     return ISSL_OK;
 }
 
+extern "C" int issl_guide_filters(issl_device *d, const char *text, size_t bytes, uint8_t *flags_out, double *at_out,
+                                  uint64_t *packed_out)
+{
+    if (!d || (bytes && !text)) return issl_set_error(ISSL_ERR_ARG, "issl_guide_filters: null argument");
+    if (bytes % 24 != 0) return issl_set_error(ISSL_ERR_ARG, "issl_guide_filters: input is not a multiple of 24 bytes (23 characters + LF)");
+    const uint64_t n = bytes / 24;
+    if (n == 0) return ISSL_OK;
+    CK(cudaSetDevice(d->dev));
+    DBuf dText, dFlags, dAt, dPacked;
+    int rc = dText.ensure(bytes);
+    if (rc == ISSL_OK && flags_out) rc = dFlags.ensure(n);
+    if (rc == ISSL_OK && at_out) rc = dAt.ensure(n * 8);
+    if (rc == ISSL_OK && packed_out) rc = dPacked.ensure(n * 8);
+    cudaError_t e = cudaSuccess;
+    if (rc == ISSL_OK) {
+        e = cudaMemcpyAsync(dText.p, text, bytes, cudaMemcpyHostToDevice, d->stream);
+        k_guide_filters<<<blocks_for(n, 256), 256, 0, d->stream>>>(dText.as<char>(), n, flags_out ? dFlags.as<uint8_t>() : nullptr,
+                                                                  at_out ? dAt.as<double>() : nullptr,
+                                                                  packed_out ? dPacked.as<uint64_t>() : nullptr);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess && flags_out) e = cudaMemcpyAsync(flags_out, dFlags.p, n, cudaMemcpyDeviceToHost, d->stream);
+        if (e == cudaSuccess && at_out) e = cudaMemcpyAsync(at_out, dAt.p, n * 8, cudaMemcpyDeviceToHost, d->stream);
+        if (e == cudaSuccess && packed_out) e = cudaMemcpyAsync(packed_out, dPacked.p, n * 8, cudaMemcpyDeviceToHost, d->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    }
+    for (DBuf *b : {&dText, &dFlags, &dAt, &dPacked}) b->release();
+    if (rc != ISSL_OK) return rc;
+    if (e != cudaSuccess) return issl_set_error(ISSL_ERR_CUDA, "issl_guide_filters: %s", cudaGetErrorString(e));
+    return ISSL_OK;
+}
+
 extern "C" int issl_last_stats(const issl_device *d, issl_stats *out)
 {
     if (!d || !out) return issl_set_error(ISSL_ERR_ARG, "issl_last_stats: null argument");

@@ -935,6 +935,35 @@ __global__ void k_place_slice(IndexView iv, const uint8_t *sortedValues, const u
         const_cast<uint64_t *>(iv.sig64)[p] = s;
 }
 
+// Guide-side pre-filters of the pipeline (ref src/crackling/Crackling.py:312-384) + packing of target23[0:20]
+// (ref :747-752 and isslScoreOfftargets.cpp:63-71, :99-102), one thread per 24-byte line.
+__global__ void k_guide_filters(const char *text, uint64_t n, uint8_t *flags, double *at, uint64_t *packed)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const char *t = text + i * 24;
+    uint32_t f = 0, atCount = 0, run = 0;
+    uint64_t sig = 0;
+    bool tttt = false;
+    for (int j = 0; j < 23; j++) {
+        const char c = t[j];
+        if (j < 20) {
+            atCount += (c == 'A' || c == 'T');
+            sig |= (uint64_t)(c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0) << (2 * j);
+        }
+        run = (c == 'T') ? run + 1 : 0;
+        tttt |= run >= 4;
+    }
+    if (t[19] != 'G') f |= ISSL_FILTER_G20;
+    if ((t[21] == 'G' && t[22] == 'G' && t[0] == 'T') || (t[0] == 'C' && t[1] == 'C' && t[22] == 'A')) f |= ISSL_FILTER_LEADING_T;
+    const double pct = __ddiv_rn(__dmul_rn(100.0, (double)atCount), 20.0);
+    if (pct < 20.0 || pct > 65.0) f |= ISSL_FILTER_AT;
+    if (tttt) f |= ISSL_FILTER_TTTT;
+    if (flags) flags[i] = (uint8_t)f;
+    if (at) at[i] = pct;
+    if (packed) packed[i] = sig;
+}
+
 __global__ void k_gather_sites(const uint64_t *sig, uint64_t N, const uint64_t *siteIds, uint64_t n, uint64_t *out)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

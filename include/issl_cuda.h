@@ -233,6 +233,23 @@ int issl_score_hits(issl_device *dev, const uint64_t *guides, size_t n, int maxD
 
 int issl_last_stats(const issl_device *dev, issl_stats *out);
 
+/* ---- guide-side pre-filters of the pipeline (the step before the scorer) ------------------- */
+
+/* Crackling's sequence-only consensus filters, /root/reference/src/crackling/Crackling.py:312-384, and the packing
+ * of the 20-mer the scorer is given (:747-752 writes target23[0:20] to the guide file), in one pass on the device.
+ * text: n lines of 23 characters + LF (target23 as produced at :151-165: 20-mer + PAM on the forward strand, or the
+ * reverse complement of a CC... match).  Per target:
+ *   flags_out (optional): ISSL_FILTER_* bits of the filters the target FAILS;
+ *   at_out (optional):    AT_percentage(target23[0:20]) = 100.0 * count(A, T) / 20.0 (Helpers.py:21-27);
+ *   packed_out (optional): the 20-mer 2-bit packed as issl_pack_guides does, ready for issl_score.
+ * bytes must be a multiple of 24 (ISSL_ERR_ARG otherwise). */
+#define ISSL_FILTER_G20 1u        /* CHOPCHOP: target23[19] != 'G'                                   (:318-326)  */
+#define ISSL_FILTER_LEADING_T 2u  /* mm10db: (ends "GG" and starts 'T') or (starts "CC" and ends 'A') (:336-346) */
+#define ISSL_FILTER_AT 4u         /* mm10db: AT % of the 20-mer < 20 or > 65                          (:356-368) */
+#define ISSL_FILTER_TTTT 8u       /* mm10db: "TTTT" in target23                                       (:378-384) */
+int issl_guide_filters(issl_device *dev, const char *text, size_t bytes, uint8_t *flags_out, double *at_out,
+                       uint64_t *packed_out);
+
 /* ---- builder-side arithmetic (used by the synthetic builder; exposed for parity tests) ---- */
 
 /* Local MIT score of a mismatch mask (bit 2*pos set per mismatching position).
