@@ -22,7 +22,7 @@ namespace issl {
 
 constexpr uint32_t kTripleCount = 10;
 constexpr uint32_t kTripleBuckets = 1u << 24;
-constexpr int kTripleThreads = 128;              // 16 octets; one octet (8 lanes x 16 B) reads one bucket
+constexpr int kTripleThreads = 128;              // per CTA = per guide
 constexpr int kTripleKeyBits = 35;               // survivor key = guide << 35 | lowest exact slice << 32 | site id
 
 // slices of triple t: a, b, c (key bytes 0..2) then p, q (residual bytes 0..1)
@@ -40,8 +40,8 @@ struct TripleView {
     // ((t << 24) | k) * pitch * 2 bytes.  A sub-block holds up to 31 residuals TRANSPOSED: word p (p = 0..15) is
     // bit p of the residuals of its 32 slots; slot 0 is not a residual: its column holds the number of
     // residuals in the sub-block (bits 0..4) and the flag "the bucket has more entries than its block holds: the
-    // rest is in res/offs" (bit 5).  A bucket fills sub-block 0 first.  One aligned read per visit, no offset lookup in front of it, and 32
-    // residuals are tested with ~30 bitwise instructions.
+    // rest is in res/offs" (bit 5).  A bucket fills sub-block 0 first.  One aligned read per visit, no offset
+    // lookup in front of it, and 31 residuals are tested with ~30 bitwise instructions.
     const uint4 *blk;
     uint32_t pitch;         // 16-bit slots per bucket: 0 (no blocked copy), 32, 64 or 128
 };
@@ -126,23 +126,24 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint3
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1t: bucket scan.  ref isslScoreOfftargets.cpp:344-390 for one guide, restricted to the buckets
-// that can hold a site within maxDist.
+// K1t: bucket scan.  ref isslScoreOfftargets.cpp:344-390 (+ :392-502 in the fused tail) for one guide,
+// restricted to the buckets that can hold a site within maxDist.
 //
-// grid = (guides, visit chunks); one CTA = one guide x a range of the visit table; an octet of lanes
-// takes one bucket at a time: two 4-byte offsets (one sector), then the bucket's residuals as 16-byte
-// vectors (8 entries per lane, 64 per octet step; a bucket holds ~35 at human scale).  Per 32-bit word
-// (two entries): XOR with the guide's residual, fold to per-base flags, two POPC, two compares with the
-// bucket's budget -> an 8-bit pass mask per vector.  The offsets of the next visit are requested before
-// the current bucket is processed, so that two dependent round trips per octet are in flight.
-//
-// A passing entry is within maxDist of the guide (bucket mismatches + residual mismatches); what is
-// left is the de-duplication -- the stateless replacement for the reference's toggle bitset (:385-390,
-// :463): E = slices matching exactly (from the visit's pattern and the residual's two bytes), and the
-// hit is kept only if this triple is resp(E), so each hit is produced exactly once.  Kept hits go to a
-// shared-memory list (position, triple, min(E)); when the CTA is done it reserves a range of the global
-// key buffer with one atomic, resolves the site ids with all threads and writes
-// key = guide << 35 | min(E) << 32 | id, which sorts back into the reference's visiting order.
+// grid = (guides, visit chunks); one CTA = one guide x a range of the visit table.  Two kernels share the
+// helpers below:
+//   k_scan_triple_blocked  reads the blocked, bit-sliced copy: one aligned read per visit, 31 residuals
+//                          per 64-byte sub-block compared with ~30 LOP3 (the default);
+//   k_scan_triple          reads the contiguous copy through the bucket offsets: an octet of lanes per
+//                          bucket, 16-byte vectors, XOR / fold / POPC per entry (indexes too small for
+//                          blocks, or when the blocked copy does not fit the HBM).
+// An entry within its bucket's budget is within maxDist of the guide (bucket mismatches + residual
+// mismatches); what is left is the de-duplication -- the stateless replacement for the reference's toggle
+// bitset (:385-390, :463): E = slices matching exactly (from the visit's pattern and the residual's two
+// bytes), and the hit is kept only if this triple is resp(E), so each hit is produced exactly once.
+// Kept hits go to a shared-memory list of 8-byte records; when the scan is done the CTA either finishes
+// the guide itself (fused tail, score_guide), or hands the hits on: as a per-guide segment for
+// k_score_segments, or as keys  guide << 35 | min(E) << 32 | id  for the general pipeline (radix sort ->
+// k_contrib -> k_accumulate), which sort back into the reference's visiting order.
 // ------------------------------------------------------------------------------------------------
 #ifndef ISSL_TRIPLE_HIT_CAP
 #define ISSL_TRIPLE_HIT_CAP 512
