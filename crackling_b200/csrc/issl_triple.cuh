@@ -176,7 +176,7 @@ struct ScoreShared {
     uint32_t cnt[5], fill[5], out[6];
     uint16_t rank[kTripleHitCap];
 };
-constexpr uint32_t kScoreGroupWords = kTripleHitCap + kTripleHitCap / 2;   // u32 id + u16 hit index per hit
+constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one u32 id per hit
 
 // load(j, idRaw, slice, site): hit j of the guide.  group[] may alias whatever load() reads: it is first written
 // after a barrier that follows the last load.  Results go to totMitOut/totCfdOut/doneOut[guide].
@@ -217,26 +217,20 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
     }
     __syncthreads();
     uint32_t *gid = reinterpret_cast<uint32_t *>(group);                       // ids, grouped by slice
-    uint16_t *gidx = reinterpret_cast<uint16_t *>(gid + kTripleHitCap);        // the hit each one belongs to
+#pragma unroll
+    for (uint32_t k = 0; k < kPerThread; k++)
+        if (mySlice[k] < 5) gid[ss.out[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u)] = myId[k];
+    __syncthreads();
+    // rank of every hit inside its slice group = number of smaller ids (ids of one guide are distinct): every thread
+    // counts for its own hits over the whole group (broadcast reads); groups are small (~55 ids)
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++)
         if (mySlice[k] < 5) {
-            const uint32_t p = ss.out[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u);
-            gid[p] = myId[k]; gidx[p] = (uint16_t)(threadIdx.x + k * kTripleThreads);
-        }
-    __syncthreads();
-    // rank of every hit inside its slice group = number of smaller ids (ids of one guide are distinct): one warp per
-    // group, every lane counts for its own hits over the whole group (broadcast reads); groups are small (~55)
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    for (uint32_t s = warp; s < 5; s += kTripleThreads / 32) {
-        const uint32_t c = ss.cnt[s], base = ss.out[s];
-        for (uint32_t i = lane; i < c; i += 32) {
-            const uint32_t mine = gid[base + i];
+            const uint32_t c = ss.cnt[mySlice[k]], base = ss.out[mySlice[k]], mine = myId[k];
             uint32_t r = 0;
             for (uint32_t q = 0; q < c; q++) r += (uint32_t)(gid[base + q] < mine);
-            ss.rank[gidx[base + i]] = (uint16_t)(base + r);
+            ss.rank[threadIdx.x + k * kTripleThreads] = (uint16_t)(base + r);
         }
-    }
     __syncthreads();
     double pm[kPerThread], pc[kPerThread];
 #pragma unroll
