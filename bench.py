@@ -367,7 +367,7 @@ def main() -> int:
 
     for _ in range(args.warmup):
         step_device()
-    scan_ms, scan_launches, launches, candidates, hits, streamed, bucket_visits = 0.0, 0, 0, 0, 0, 0, 0
+    scan_ms, scan_launches, launches, candidates, hits, streamed, bucket_visits, early_exits = 0.0, 0, 0, 0, 0, 0, 0, 0
     barrier()
     with ClockSampler(local_rank) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,7 +377,7 @@ def main() -> int:
             st = dev.stats
             scan_ms += st["scan_ms"]; scan_launches += st["scan_launches"]; launches += st["launches"]
             candidates += st["candidates"]; hits += st["hits"]; streamed += st["streamed"]
-            bucket_visits += st["bucket_visits"]
+            bucket_visits += st["bucket_visits"]; early_exits += st["early_exits"]
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -477,6 +477,7 @@ def main() -> int:
               "e2e": {"value": e2e_value, "unit": "guides/s", "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 16)},
               "gpu_launches": int(launches), "scan_launches": int(scan_launches),
               "hits_per_guide": hits / max(args.steps * n, 1), "candidates_per_guide": candidates / max(args.steps * n, 1),
+              "early_exit_fraction": early_exits / max(args.steps * n, 1),
               "dtype_note": "u16 bit-sliced residual compare (LOP3), f64 scores" if triple_scan else "u32/u64 xor+popcount, f64 scores",
               "roofline": roofline}
 

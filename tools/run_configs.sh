@@ -24,3 +24,5 @@ run --layout gather --guides 20000 --steps 2 --warmup 1
 run --layout sig64 --guides 20000 --steps 2 --warmup 1
 # config 3 flavour: 1 M guides in one call, method and
 run --guides 1000000 --steps 2 --warmup 1
+# config 3: 10 M guides, method and (ten internal batches of 2^20 guides)
+run --guides 10000000 --steps 1 --warmup 1
