@@ -17,11 +17,11 @@ CXXFLAGS  := -O3 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Iinclude -I$(CSRC)
 
 all: $(LIBDIR)/libissl_cuda.so bin/isslScoreOfftargets bin/isslCreateIndex bin/isslScoreServer bin/extractOfftargets
 
-$(LIBDIR)/issl_host.o: $(CSRC)/issl_host.cpp $(CSRC)/issl_internal.h include/issl_cuda.h
+$(LIBDIR)/issl_host.o: $(CSRC)/issl_host.cpp $(CSRC)/issl_internal.h $(CSRC)/issl_triple_tables.h include/issl_cuda.h
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) -c -o $@ $<
 
-$(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_device_common.cuh $(CSRC)/issl_kernels.cuh $(CSRC)/issl_triple.cuh $(CSRC)/issl_internal.h $(CSRC)/cfd_tables.h include/issl_cuda.h
+$(LIBDIR)/issl_device.o: $(CSRC)/issl_device.cu $(CSRC)/issl_device_common.cuh $(CSRC)/issl_kernels.cuh $(CSRC)/issl_triple.cuh $(CSRC)/issl_triple_tables.h $(CSRC)/issl_internal.h $(CSRC)/cfd_tables.h include/issl_cuda.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o $@ $< 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 

@@ -7,5 +7,5 @@ tests and by bench.py; it adds no compute of its own and has no CPU fallback.
 """
 from .binding import (  # noqa: F401
     IsslError, Index, Device, Sites, lib, lib_path, build, pack_guides, unpack_guide, method_code,
-    local_mit_score, mit_table, triple_visits, device_count, cli_path, create_cli_path, extract_cli_path, LAYOUTS, METHODS,
+    local_mit_score, mit_table, triple_visits, triple_layout, device_count, cli_path, create_cli_path, extract_cli_path, LAYOUTS, METHODS,
 )

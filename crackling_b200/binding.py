@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
             "issl_local_mit_score": ([u64, sz], d),
             "issl_mit_table": ([sz, sz, vp, vp, sz, C.POINTER(u64)], sz),
             "issl_triple_visits": ([C.c_int, vp, sz, vp], sz),
+            "issl_triple_layout": ([vp, vp], None),
             "issl_last_error": ([], C.c_char_p),
             "issl_abi_version": ([], i),
         }
@@ -166,6 +167,14 @@ def triple_visits(max_dist: int):
     out = np.zeros(max(n, 1), dtype=np.uint32)
     n = lib().issl_triple_visits(int(max_dist), out.ctypes.data, n, wave.ctypes.data)
     return out[:n], wave
+
+
+def triple_layout():
+    """(slices[10][5], resp[32]) of issl_triple_layout."""
+    sl = np.zeros(50, dtype=np.uint8)
+    resp = np.zeros(32, dtype=np.uint8)
+    lib().issl_triple_layout(sl.ctypes.data, resp.ctypes.data)
+    return sl.reshape(10, 5), resp
 
 
 def _info_dict(s) -> dict:

@@ -802,8 +802,7 @@ static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
     if (d->visitsDist != maxDist) {   // the visit table depends on maxDist only
         std::vector<uint32_t> raw(issl_triple_visits(maxDist, nullptr, 0, nullptr));
         issl_triple_visits(maxDist, raw.data(), raw.size(), d->waveStart);
-        static const uint8_t slices[10][5] = {{0, 1, 2, 3, 4}, {0, 1, 3, 2, 4}, {0, 1, 4, 2, 3}, {0, 2, 3, 1, 4}, {0, 2, 4, 1, 3},
-                                              {0, 3, 4, 1, 2}, {1, 2, 3, 0, 4}, {1, 2, 4, 0, 3}, {1, 3, 4, 0, 2}, {2, 3, 4, 0, 1}};
+        static const uint8_t slices[10][5] = ISSL_TRIPLE_LAYOUT_INIT;
         std::vector<TripleVisit> v(raw.size());
         for (size_t i = 0; i < raw.size(); i++) {
             const uint32_t t = (raw[i] >> 24) & 15u;

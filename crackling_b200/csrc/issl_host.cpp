@@ -15,6 +15,7 @@
 #include <unistd.h>
 
 #include "issl_internal.h"
+#include "issl_triple_tables.h"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -282,32 +283,29 @@ extern "C" size_t issl_mit_table(size_t seqLength, size_t sliceWidth, uint64_t *
 // The reference scores a site iff it lies in at least one of the guide's five looked-up lists -- i.e. the set E of
 // slices on which site and guide agree exactly is non-empty -- and dist <= maxDist, and it meets the site first
 // in slice min(E) (ref isslScoreOfftargets.cpp:330-390).  Every slice outside E carries at least one mismatch.
-// Each such site is made the responsibility of exactly one slice triple T = resp(E):
-//   |E| >= 3: the three lowest slices of E;  |E| == 2: E plus the lowest slice outside E;
-//   |E| == 1: E plus the two lowest slices outside E,
-// and within that triple's copy of the index it can only sit in a bucket whose key differs from the guide's on
-// the slices of T \ E, by 1..(maxDist - #other non-exact slices) mismatches each.  Enumerating those XOR
-// patterns gives the table below; the scan kernel re-derives E for every survivor and keeps it only when
-// resp(E) is the triple it was found in, so every hit is produced exactly once.
+// Each such site is made the responsibility of exactly one slice triple T = resp(E) (issl_triple_tables.h), which
+// contains E when |E| <= 3 and is the three lowest slices of E otherwise; within that triple's copy of the index it can
+// only sit in a bucket whose key differs from the guide's on the slices of T \ E, by 1..(maxDist - #other non-exact
+// slices) mismatches each.  Enumerating those XOR patterns gives the table below; the scan kernel re-derives E for
+// every survivor and keeps it only when resp(E) is the triple it was found in, so every hit is produced exactly once.
 namespace {
-const int kTriples[10][3] = {{0, 1, 2}, {0, 1, 3}, {0, 1, 4}, {0, 2, 3}, {0, 2, 4}, {0, 3, 4}, {1, 2, 3}, {1, 2, 4}, {1, 3, 4}, {2, 3, 4}};
+const uint8_t kLayout[10][5] = ISSL_TRIPLE_LAYOUT_INIT;
 
-int triple_index(int a, int b, int c)
-{
-    int s[3] = {a, b, c};
-    std::sort(s, s + 3);
-    for (int t = 0; t < 10; t++)
-        if (kTriples[t][0] == s[0] && kTriples[t][1] == s[1] && kTriples[t][2] == s[2]) return t;
-    return -1;
-}
 int byte_pos(int t, int slice)
 {
     for (int k = 0; k < 3; k++)
-        if (kTriples[t][k] == slice) return k;
+        if (kLayout[t][k] == slice) return k;
     return -1;
 }
 int ham4(uint32_t x) { return ((x & 3u) != 0) + ((x & 12u) != 0) + ((x & 48u) != 0) + ((x & 192u) != 0); }
 }  // namespace
+
+extern "C" void issl_triple_layout(uint8_t slices_out[50], uint8_t resp_out[32])
+{
+    if (slices_out) memcpy(slices_out, kLayout, 50);
+    if (resp_out)
+        for (uint32_t E = 0; E < 32; E++) resp_out[E] = (uint8_t)issl_triple_resp(E);
+}
 
 extern "C" size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6])
 {
@@ -318,21 +316,18 @@ extern "C" size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uin
         v.push_back({(uint32_t)wave, pattern | ((uint32_t)t << 24) | ((uint32_t)budget << 28)});
     };
     if (D >= 0) {
-        for (int t = 0; t < 10; t++) add(kTriples[t][0], t, 0, D);                       // E contains the whole triple
+        for (int t = 0; t < 10; t++)                                                     // E contains the whole triple
+            add(std::min({kLayout[t][0], kLayout[t][1], kLayout[t][2]}), t, 0, D);
         for (int i = 0; i < 5; i++)                                                      // |E| == 2
             for (int j = i + 1; j < 5; j++) {
-                int k = 0;
-                while (k == i || k == j) k++;
-                const int t = triple_index(i, j, k), pos = byte_pos(t, k);
+                const int t = (int)issl_triple_resp((1u << i) | (1u << j));
+                const int k = kLayout[t][0], pos = byte_pos(t, k);                       // the third slice: the low key byte
                 for (uint32_t x = 1; x < 256; x++)
                     if (ham4(x) <= D - 2) add(i, t, x << (8 * pos), D - ham4(x));
             }
         for (int e = 0; e < 5; e++) {                                                    // |E| == 1
-            int j = 0;
-            while (j == e) j++;
-            int k = j + 1;
-            while (k == e) k++;
-            const int t = triple_index(e, j, k), pj = byte_pos(t, j), pk = byte_pos(t, k);
+            const int t = (int)issl_triple_resp(1u << e);
+            const int j = kLayout[t][0], k = kLayout[t][1], pj = byte_pos(t, j), pk = byte_pos(t, k);
             for (uint32_t xj = 1; xj < 256; xj++)
                 for (uint32_t xk = 1; xk < 256; xk++)
                     if (ham4(xj) + ham4(xk) <= D - 2) add(e, t, (xj << (8 * pj)) | (xk << (8 * pk)), D - ham4(xj) - ham4(xk));

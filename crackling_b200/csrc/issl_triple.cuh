@@ -17,6 +17,7 @@
 #include <type_traits>
 
 #include "issl_kernels.cuh"
+#include "issl_triple_tables.h"
 
 namespace issl {
 
@@ -25,10 +26,8 @@ constexpr uint32_t kTripleBuckets = 1u << 24;
 constexpr int kTripleThreads = 128;              // per CTA = per guide
 constexpr int kTripleKeyBits = 35;               // survivor key = guide << 35 | lowest exact slice << 32 | site id
 
-// slices of triple t: a, b, c (key bytes 0..2) then p, q (residual bytes 0..1)
-__constant__ uint8_t c_tripleSlices[kTripleCount][5] = {
-    {0, 1, 2, 3, 4}, {0, 1, 3, 2, 4}, {0, 1, 4, 2, 3}, {0, 2, 3, 1, 4}, {0, 2, 4, 1, 3},
-    {0, 3, 4, 1, 2}, {1, 2, 3, 0, 4}, {1, 2, 4, 0, 3}, {1, 3, 4, 0, 2}, {2, 3, 4, 0, 1}};
+// slices of triple t: key bytes 0..2 (L, M, H), then p < q (residual bytes 0..1) -- issl_triple_tables.h
+__constant__ uint8_t c_tripleSlices[kTripleCount][5] = ISSL_TRIPLE_LAYOUT_INIT;
 
 struct TripleView {
     const uint16_t *res;    // [10][stride] residual bits (slice p | slice q << 8) per bucket entry
@@ -301,23 +300,10 @@ struct TripleArgs {
 };
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
-__host__ __device__ constexpr uint32_t triple_resp_of(uint32_t E)
-{
-    int pick[3] = {0, 0, 0}, np = 0;
-    for (int s = 0; s < 5 && np < 3; s++) if (E & (1u << s)) pick[np++] = s;
-    for (int s = 0; s < 5 && np < 3; s++) if (!(E & (1u << s))) pick[np++] = s;
-    for (int a = 0; a < 2; a++)
-        for (int b = 0; b < 2 - a; b++)
-            if (pick[b] > pick[b + 1]) { const int t = pick[b]; pick[b] = pick[b + 1]; pick[b + 1] = t; }
-    const int T[10][3] = {{0, 1, 2}, {0, 1, 3}, {0, 1, 4}, {0, 2, 3}, {0, 2, 4}, {0, 3, 4}, {1, 2, 3}, {1, 2, 4}, {1, 3, 4}, {2, 3, 4}};
-    for (int t = 0; t < 10; t++)
-        if (T[t][0] == pick[0] && T[t][1] == pick[1] && T[t][2] == pick[2]) return (uint32_t)t;
-    return 15u;
-}
 __host__ __device__ constexpr uint64_t triple_resp_pack(uint32_t e0)
 {
     uint64_t v = 0;
-    for (uint32_t e = 0; e < 16; e++) v |= (uint64_t)triple_resp_of(e0 + e) << (4 * e);
+    for (uint32_t e = 0; e < 16; e++) v |= (uint64_t)issl_triple_resp(e0 + e) << (4 * e);
     return v;
 }
 constexpr uint64_t kRespLo = triple_resp_pack(0), kRespHi = triple_resp_pack(16);

@@ -262,14 +262,19 @@ size_t issl_mit_table(size_t seqLength, size_t sliceWidth, uint64_t *masks, doub
                       uint64_t *scoresCount);
 
 /* ISSL_LAYOUT_TRIPLE: the sub-buckets one guide has to read for a given maxDist, as XOR patterns relative to
- * the guide's own bucket.  Entry = pattern24 | triple << 24 | budget << 28: `triple` indexes the slice triples
- * (a<b<c) of {0..4} in lexicographic order; pattern24 is XORed onto the guide's bucket key
- * (slice a | slice b << 8 | slice c << 16); an entry of that bucket can only be a hit if its 16 residual bits
+ * the guide's own bucket.  Entry = pattern24 | triple << 24 | budget << 28: `triple` indexes the ten slice triples
+ * (issl_triple_layout); pattern24 is XORed onto the guide's bucket key (the triple's three slices in key bytes
+ * 0..2); an entry of that bucket can only be a hit if its 16 residual bits
  * differ from the guide's in at most `budget` bases.  Entries are ordered by the lowest slice on which their hits
  * match the guide exactly -- the slice through which the reference meets them first
  * (isslScoreOfftargets.cpp:330-390) -- and waveStart[s] .. waveStart[s+1] delimits slice s.
  * Returns the number of entries (written up to cap); out may be NULL to size the table.  0 <= maxDist <= 7. */
 size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6]);
+
+/* The fixed tables behind it: slices_out[t*5 + 0..2] = the slices in key bytes 0..2 of triple t, [t*5 + 3..4] the two
+ * residual slices; resp_out[E] = the triple responsible for a site whose exactly matching slices are the set E
+ * (bit s = slice s; resp_out[0] = 15).  Either pointer may be NULL. */
+void issl_triple_layout(uint8_t slices_out[50], uint8_t resp_out[32]);
 
 const char *issl_last_error(void);
 int issl_abi_version(void);

@@ -132,14 +132,29 @@ def test_product_never_touches_the_oracle():
 
 # --- ISSL_LAYOUT_TRIPLE: the sub-bucket visit table (host arithmetic, no GPU) -------------------------------
 
-_TRIPLES = [(0, 1, 2), (0, 1, 3), (0, 1, 4), (0, 2, 3), (0, 2, 4), (0, 3, 4), (1, 2, 3), (1, 2, 4), (1, 3, 4), (2, 3, 4)]
 _HAM4 = np.array([sum(1 for f in range(4) if (x >> (2 * f)) & 3) for x in range(256)])
 
 
-def _resp(E):
-    E = sorted(E)
-    rest = [s for s in range(5) if s not in E]
-    return tuple(sorted((E + rest)[:3] if len(E) < 3 else E[:3]))
+def test_triple_layout_tables():
+    """The ten triples are all 3-subsets of the five slices; resp(E) always contains E (|E| <= 3) or is contained in
+    it; every pair is the {M, H} of exactly one triple and every single slice the H of its triple, which is what puts
+    the sub-buckets a guide reads next to each other (issl_triple_tables.h)."""
+    import itertools
+    lay, resp = cb.triple_layout()
+    sets = [frozenset(int(x) for x in row[:3]) for row in lay]
+    assert sorted(map(sorted, sets)) == [list(c) for c in itertools.combinations(range(5), 3)]
+    for t, row in enumerate(lay):
+        assert sorted(int(x) for x in row) == [0, 1, 2, 3, 4] and row[3] < row[4]
+    assert resp[0] == 15
+    for E in range(1, 32):
+        Eset = frozenset(s for s in range(5) if E >> s & 1)
+        T = sets[resp[E]]
+        assert Eset <= T if len(Eset) <= 3 else T <= Eset
+        if len(Eset) == 1:
+            assert lay[resp[E]][2] in Eset                       # the exact slice is the high key byte
+        if len(Eset) == 2:
+            assert Eset == {int(lay[resp[E]][1]), int(lay[resp[E]][2])}   # the varied slice is the low key byte
+    assert len({int(resp[(1 << i) | (1 << j)]) for i in range(5) for j in range(i + 1, 5)}) == 10
 
 
 def test_triple_visit_table_counts():
@@ -159,10 +174,14 @@ def test_triple_visits_cover_every_reference_hit_exactly_once(max_dist):
     attributed to the lowest matching slice."""
     rng = np.random.default_rng(100 + max_dist)
     visits, wave = cb.triple_visits(max_dist)
+    lay, resp = cb.triple_layout()
     by_wave = np.searchsorted(wave[1:], np.arange(visits.size), side="right")
 
     def slices(s):
         return [(s >> (8 * k)) & 0xFF for k in range(5)]
+
+    def key_of(sl, t):
+        return sl[lay[t][0]] | sl[lay[t][1]] << 8 | sl[lay[t][2]] << 16
 
     for g in (int(x) for x in rng.integers(0, 1 << 40, 4)):
         sites = {g}
@@ -172,11 +191,11 @@ def test_triple_visits_cover_every_reference_hit_exactly_once(max_dist):
                 s ^= int(rng.integers(1, 4)) << (2 * int(p))
             sites.add(s)
         gs = slices(g)
-        buckets = [dict() for _ in _TRIPLES]
+        buckets = [dict() for _ in range(10)]
         for s in sites:
             sl = slices(s)
-            for t, T in enumerate(_TRIPLES):
-                buckets[t].setdefault(sl[T[0]] | sl[T[1]] << 8 | sl[T[2]] << 16, []).append(s)
+            for t in range(10):
+                buckets[t].setdefault(key_of(sl, t), []).append(s)
         want = {}
         for s in sites:
             sl = slices(s)
@@ -186,16 +205,14 @@ def test_triple_visits_cover_every_reference_hit_exactly_once(max_dist):
         got = {}
         for e, w in zip(visits.tolist(), by_wave.tolist()):
             t, budget, pat = (e >> 24) & 15, e >> 28, e & 0xFFFFFF
-            T = _TRIPLES[t]
-            comp = [k for k in range(5) if k not in T]
-            key = (gs[T[0]] | gs[T[1]] << 8 | gs[T[2]] << 16) ^ pat
-            for s in buckets[t].get(key, []):
+            comp = [int(lay[t][3]), int(lay[t][4])]
+            for s in buckets[t].get(key_of(gs, t) ^ pat, []):
                 sl = slices(s)
                 if sum(_HAM4[sl[c] ^ gs[c]] for c in comp) > budget:
                     continue   # the kernel's fast-path filter must never drop a true hit (checked by got == want)
-                E = [k for k in range(5) if sl[k] == gs[k]]
-                if E and sum(_HAM4[a ^ b] for a, b in zip(sl, gs)) <= max_dist and _resp(E) == T:
+                E = sum(1 << k for k in range(5) if sl[k] == gs[k])
+                if E and sum(_HAM4[a ^ b] for a, b in zip(sl, gs)) <= max_dist and resp[E] == t:
                     assert s not in got, "hit produced twice"
-                    assert min(E) == w, "hit attributed to the wrong slice wave"
+                    assert (E & -E).bit_length() - 1 == w, "hit attributed to the wrong slice wave"
                     got[s] = w
         assert got == want
