@@ -171,9 +171,8 @@ struct ScoreParams {
 };
 
 struct ScoreShared {
-    double mit[kTripleHitCap], cfd[kTripleHitCap];
+    double mit[kTripleThreads], cfd[kTripleThreads];   // a window of contributions in accumulation order
     uint32_t cnt[5], fill[5], out[6];
-    uint16_t rank[kTripleHitCap];
 };
 constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one u32 id per hit
 
@@ -187,6 +186,7 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
     if (threadIdx.x < 5) { ss.cnt[threadIdx.x] = 0; ss.fill[threadIdx.x] = 0; }
     __syncthreads();
     uint32_t myId[kPerThread], mySlice[kPerThread];
+    double myMit[kPerThread], myCfd[kPerThread];   // shared memory per SM is L1 the scan cannot use: contributions stay in registers
     const uint32_t idMask = sp.occFlag ? 0x7FFFFFFFu : ~0u;
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
             double cm, cc;
             int dist;
             hit_contrib(sp.tb, g, site, occ, sp.calcMit, sp.calcCfd, cm, cc, dist);
-            ss.mit[j] = cm; ss.cfd[j] = cc;
+            myMit[k] = cm; myCfd[k] = cc;
         }
     }
     __syncthreads();
@@ -222,42 +222,44 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
     __syncthreads();
     // rank of every hit inside its slice group = number of smaller ids (ids of one guide are distinct): every thread
     // counts for its own hits over the whole group (broadcast reads); groups are small (~55 ids)
+    uint32_t myRank[kPerThread];
 #pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++)
+    for (uint32_t k = 0; k < kPerThread; k++) {
+        myRank[k] = 0xFFFFFFFFu;
         if (mySlice[k] < 5) {
             const uint32_t c = ss.cnt[mySlice[k]], base = ss.out[mySlice[k]], mine = myId[k];
             uint32_t r = 0;
             for (uint32_t q = 0; q < c; q++) r += (uint32_t)(gid[base + q] < mine);
-            ss.rank[threadIdx.x + k * kTripleThreads] = (uint16_t)(base + r);
+            myRank[k] = base + r;
         }
-    __syncthreads();
-    double pm[kPerThread], pc[kPerThread];
-#pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++) {
-        const uint32_t j = threadIdx.x + k * kTripleThreads;
-        if (j < n && mySlice[k] < 5) { pm[k] = ss.mit[j]; pc[k] = ss.cfd[j]; }
     }
-    __syncthreads();
+    // ordered accumulation with the reference's early exit (ref :394, :460, :466-502): the contributions pass through
+    // a window of shared memory in rank order, kTripleThreads at a time, and one thread adds them up
+    const uint32_t kept = ss.out[5];
+    double mit = 0.0, cfd = 0.0;
+    bool stop = false;
+    if (threadIdx.x == 0) { mit = sp.totMit[guide]; cfd = sp.totCfd[guide]; }
+    for (uint32_t w0 = 0; w0 < kept; w0 += kTripleThreads) {
 #pragma unroll
-    for (uint32_t k = 0; k < kPerThread; k++) {
-        const uint32_t j = threadIdx.x + k * kTripleThreads;
-        if (j < n && mySlice[k] < 5) { const uint32_t r = ss.rank[j]; ss.mit[r] = pm[k]; ss.cfd[r] = pc[k]; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double mit = sp.totMit[guide], cfd = sp.totCfd[guide];
-        bool stop = false;
-        const uint32_t kept = ss.out[5];
-        if (!sp.checkExit) {
+        for (uint32_t k = 0; k < kPerThread; k++)
+            if (myRank[k] - w0 < (uint32_t)kTripleThreads) { ss.mit[myRank[k] - w0] = myMit[k]; ss.cfd[myRank[k] - w0] = myCfd[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0 && !stop) {
+            const uint32_t m = min((uint32_t)kTripleThreads, kept - w0);
+            if (!sp.checkExit) {
 #pragma unroll 8
-            for (uint32_t i = 0; i < kept; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
-        } else {
-            for (uint32_t i = 0; i < kept && !stop; i++) {
-                mit = __dadd_rn(mit, ss.mit[i]);
-                cfd = __dadd_rn(cfd, ss.cfd[i]);
-                stop = exit_predicate(sp.method, mit, cfd, sp.maximumSum);
+                for (uint32_t i = 0; i < m; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
+            } else {
+                for (uint32_t i = 0; i < m && !stop; i++) {
+                    mit = __dadd_rn(mit, ss.mit[i]);
+                    cfd = __dadd_rn(cfd, ss.cfd[i]);
+                    stop = exit_predicate(sp.method, mit, cfd, sp.maximumSum);
+                }
             }
         }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
         totMitOut[guide] = mit; totCfdOut[guide] = cfd;
         if (stop) doneOut[guide] = 1;
     }
