@@ -43,7 +43,7 @@ struct issl_device {
     DBuf guides, totMit, totCfd, done, pairKeys, pairVals, pairKeysSorted, pairValsSorted, pairCounts, pairOffsets, items, keysA, keysB, sortTemp, scanTemp,
         contribMit, contribCfd, counters, outMit, outCfd, hitId, hitDist, hitOcc, scoredEnd, segBegin;
     unsigned long long *hCounters = nullptr;   // pinned: [0] total candidates, [1] hit count, [2] items, [3] done
-    uint64_t hitCap = 0, hitCapAuto = 0;
+    uint64_t hitCap = 0, hitCapAuto = 0, firstHitCap = 0;
     std::vector<cudaEvent_t> evPool;
     issl_stats stats{};
     uint32_t maxBatch = 1u << 20;
@@ -299,6 +299,7 @@ static int new_device(int cuda_device, issl_device **out)
         const long v = atol(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
     }
+    if (const char *e = getenv("ISSL_HIT_CAP")) { const long v = atol(e); if (v > 0) d->firstHitCap = (uint64_t)v; }
     if (const char *e = getenv("ISSL_TRIPLE_FLUSH")) d->tripleFlush = atoi(e) != 0;
     if (const char *e = getenv("ISSL_TRIPLE_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->tripleFuse = v; }
     if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
@@ -789,7 +790,8 @@ struct EventTimer {
 
 static int ensure_hit_buffers(issl_device *d, uint32_t n)
 {
-    const uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, 384ull * n), 1ull << 28);
+    uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, 384ull * n), 1ull << 28);
+    if (d->firstHitCap) wantCap = d->firstHitCap;   // ISSL_HIT_CAP: start small, so that tests reach the re-launch after an overflow
     if (d->hitCap < wantCap && d->hitCap == d->hitCapAuto) {   // first sizing for this batch size (uniform genomes: ~275 survivors per guide)
         d->hitCap = d->hitCapAuto = wantCap;
         CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));

@@ -236,15 +236,19 @@ def test_triple_layout_sub_bucket_scan(triple_max):
     dev.close()
 
 
-@pytest.mark.parametrize("fuse,blocks,flush", [(2, "64", "0"), (2, "32", "0"), (1, "64", "0"), (0, "0", "0"), (2, "0", "0"),
-                                               (2, "64", "1"), (1, "32", "1"), (0, "64", "1")])
-def test_triple_large_batch_tails(fuse, blocks, flush):
+@pytest.mark.parametrize("fuse,blocks,flush,hit_cap", [(2, "64", "0", None), (2, "32", "0", None), (1, "64", "0", None),
+                                                       (0, "0", "0", None), (2, "0", "0", None), (2, "64", "1", None),
+                                                       (1, "32", "1", None), (0, "64", "1", None),
+                                                       (2, "64", "0", "3000"), (1, "64", "1", "3000"), (0, "32", "0", "3000")])
+def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     """With at least 148 x 16 guides in a batch every guide gets one CTA, and the scan's tails come into play: 2 = the
     CTA sorts, scores and accumulates the guide's hits itself (fused), 1 = per-guide segments finished by
     k_score_segments, 0 = general pipeline; guides with more than 512 hits (dense families here) always take the
     general pipeline, mixed with the others in one batch -- with flush = 1 through the scan variant that empties a
     full record list in the middle of the scan.  Blocked (bit-sliced sub-blocks of 31/62 entries, with buckets that
-    do not fit) and contiguous copies.  Everything must stay bit-identical to the oracle, early exits included."""
+    do not fit) and contiguous copies; with hit_cap the survivor buffers start far too small, so that every call is
+    launched again after an overflow (the fused tail must then start from the same per-guide state).  Everything
+    must stay bit-identical to the oracle, early exits included."""
     text = td.make_offtargets(51, n_random=120_000, n_families=30, family_size=900, max_sub_rate=0.12)
     img = oracle.create_index(text, 20, 8)
     rng = np.random.default_rng(52)
@@ -261,10 +265,13 @@ def test_triple_large_batch_tails(fuse, blocks, flush):
     os.environ["ISSL_TRIPLE_FUSE"] = str(fuse)
     os.environ["ISSL_TRIPLE_BLOCKS"] = blocks
     os.environ["ISSL_TRIPLE_FLUSH"] = flush
+    if hit_cap:
+        os.environ["ISSL_HIT_CAP"] = hit_cap
     try:
         dev = cb.Device.from_index(cb.Index(img), 0, "triple")
     finally:
         del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"], os.environ["ISSL_TRIPLE_FLUSH"]
+        os.environ.pop("ISSL_HIT_CAP", None)
     assert dev.info["triple_block_bytes"] == 2 * int(blocks)
     seen_big = False
     for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 5), ("mit", 0, 2), ("cfd", 20, 4)):
