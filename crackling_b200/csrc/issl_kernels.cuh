@@ -608,6 +608,8 @@ __device__ __forceinline__ void hit_contrib(const ScoreTables &tb, uint64_t g, u
     }
 }
 
+constexpr uint64_t kKeyOccursOnce = 1ull << 63;   // survivor key flag, above every sorted bit: occurrences = 1
+
 struct ContribArgs {
     IndexView iv;
     const uint64_t *keys;     // sorted
@@ -630,10 +632,10 @@ __global__ void __launch_bounds__(256) k_contrib(const ContribArgs a)
     if (j >= a.nHits) return;
     const uint64_t key = a.keys[j];
     const uint64_t pos = key & ((1ull << a.pbits) - 1ull);
-    const uint64_t g = a.guides[key >> a.pbits];
+    const uint64_t g = a.guides[(key & ~kKeyOccursOnce) >> a.pbits];
     const uint32_t id = a.idInKey ? (uint32_t)pos : a.iv.ids[pos];
     const uint64_t site = a.iv.sig[id];
-    const uint32_t occ = a.iv.occ[id];
+    const uint32_t occ = (key & kKeyOccursOnce) ? 1u : a.iv.occ[id];
     double cm, cc;
     int dist;
     hit_contrib(a.tb, g, site, occ, a.calcMit, a.calcCfd, cm, cc, dist);
@@ -668,7 +670,7 @@ __device__ __forceinline__ uint64_t lower_bound_key(const uint64_t *keys, uint64
     uint64_t lo = 0, hi = n;
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
-        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+        if ((keys[mid] & ~kKeyOccursOnce) < key) lo = mid + 1; else hi = mid;
     }
     return lo;
 }

@@ -359,6 +359,14 @@ __device__ __forceinline__ bool record_keep(uint2 h, uint32_t &minE)
     return resp == t;
 }
 
+// key of the general pipeline: guide << 35 | slice << 32 | id, plus -- outside the bits that are sorted -- "occurs
+// once" when the stored id says so, which saves k_contrib the occurrence lookup
+__device__ __forceinline__ uint64_t general_key(const TripleView &tv, uint32_t guide, uint32_t minE, uint32_t idRaw)
+{
+    const uint64_t once = (tv.occFlag && !(idRaw & 0x80000000u)) ? kKeyOccursOnce : 0ull;
+    return once | ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | (idRaw & (tv.occFlag ? 0x7FFFFFFFu : ~0u));
+}
+
 __device__ __forceinline__ uint32_t hit_position(const TripleView &tv, uint2 h)
 {
     if (!(h.y & kRecBlocked)) return h.x;
@@ -386,9 +394,9 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
     } else {   // rare (dense repeat families): straight to the general pipeline's buffer
         uint32_t minE;
         if (!record_keep(h, minE)) return;
-        const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)] & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u);
+        const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)];
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
-        if (gs < a.hitCap) a.hitKeys[gs] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | id;
+        if (gs < a.hitCap) a.hitKeys[gs] = general_key(a.tv, guide, minE, id);
     }
 }
 
@@ -402,14 +410,13 @@ __device__ __forceinline__ void triple_flush(const TripleArgs &a, TripleShared &
     const uint32_t n = min(sh.nHits, kTripleHitCap);
     if (threadIdx.x == 0) sh.base = atomicAdd(a.hitCount, (unsigned long long)n);
     __syncthreads();
-    const uint32_t idMask = a.tv.occFlag ? 0x7FFFFFFFu : ~0u;
     for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
         const uint2 h = sh.hits[j];
         uint32_t minE;
         record_keep(h, minE);
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + j;
-        if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)minE << 32) | (id & idMask);
+        if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, minE, id);
     }
     __syncthreads();
     if (threadIdx.x == 0) { sh.nHits = 0; sh.flushed = 1; }
@@ -531,7 +538,6 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         }
     }
     __syncthreads();
-    const uint32_t idMask = a.tv.occFlag ? 0x7FFFFFFFu : ~0u;
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         if (myPos[k] == 0xFFFFFFFFu) continue;
@@ -539,7 +545,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + myPos[k];
         if (!segment) {
-            if (slot < a.hitCap) a.hitKeys[slot] = ((uint64_t)guide << kTripleKeyBits) | ((uint64_t)myMinE[k] << 32) | (id & idMask);
+            if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, myMinE[k], id);
         } else if (slot < a.segCap) {
             a.segKeys[slot] = ((uint64_t)myMinE[k] << 32) | id;
             a.segSites[slot] = hit_site(a.tv, h);
