@@ -111,12 +111,12 @@ static int choose_layout(const issl_info &f, int requested, int *out)
 {
     const uint32_t w = (uint32_t)f.sliceWidth, kb = std::min<uint32_t>(w, 8);
     const bool res32ok = (w % 2 == 0) && (2 * f.seqLength >= kb) && (2 * f.seqLength - kb <= 32);
-    const bool tripleok = f.seqLength == 20 && w == 8 && f.sliceCount == 5;
+    const bool tripleok = f.seqLength == 20 && ((w == 8 && f.sliceCount == 5) || (w == 4 && f.sliceCount == 10));
     if (requested == ISSL_LAYOUT_AUTO) requested = tripleok ? ISSL_LAYOUT_TRIPLE : res32ok ? ISSL_LAYOUT_RES32 : ISSL_LAYOUT_SIG64;
     if (requested == ISSL_LAYOUT_RES32 && !res32ok)
         return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout RES32 needs an even slice width and 2*seqLength - min(width,8) <= 32");
     if (requested == ISSL_LAYOUT_TRIPLE && !tripleok)
-        return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout TRIPLE needs seqLength 20 and sliceWidth 8");
+        return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout TRIPLE needs seqLength 20 and sliceWidth 8 or 4");
     if (requested != ISSL_LAYOUT_RES32 && requested != ISSL_LAYOUT_SIG64 && requested != ISSL_LAYOUT_GATHER &&
         requested != ISSL_LAYOUT_TRIPLE)
         return issl_set_error(ISSL_ERR_ARG, "unknown layout %d", requested);
@@ -152,7 +152,9 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     CKR(d->occ.ensure(N * 4));
     CKR(d->ids.ensure(P * 4));
     CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
-    const bool res32 = layout == ISSL_LAYOUT_RES32 || layout == ISSL_LAYOUT_TRIPLE;   // TRIPLE keeps the RES32 lists (maxDist > tripleMaxDist, .issl export)
+    // TRIPLE keeps slice lists too (maxDist beyond what the sub-bucket scan serves, .issl export): RES32 for sliceWidth 8,
+    // ids only (GATHER) for sliceWidth 4
+    const bool res32 = layout == ISSL_LAYOUT_RES32 || (layout == ISSL_LAYOUT_TRIPLE && f.sliceWidth == 8);
     if (res32) { CKR(d->res32.ensure(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
     if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.ensure(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
     CKR(d->listStart.ensure(d->nLists * 8));
@@ -175,7 +177,7 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     v.sliceCount = (uint32_t)f.sliceCount; v.sliceLimit = (uint32_t)sliceLimit;
     v.sliceMask = (uint32_t)(sliceLimit - 1);
     v.knownBits = std::min<uint32_t>((uint32_t)f.sliceWidth, 8);
-    v.layout = res32 ? (int)ISSL_LAYOUT_RES32 : layout;
+    v.layout = res32 ? (int)ISSL_LAYOUT_RES32 : layout == ISSL_LAYOUT_TRIPLE ? (int)ISSL_LAYOUT_GATHER : layout;
 
     d->hbmBytes = N * 12 + P * 4 + (res32 ? P * 4 : 0) + (layout == ISSL_LAYOUT_SIG64 ? P * 8 : 0) +
                   d->nLists * 24;
@@ -280,6 +282,7 @@ static int build_triple(issl_device *d)
     d->tv.offs = d->tripleOffs.as<uint32_t>();
     d->tv.stride = stride;
     d->tv.occFlag = N < (1ull << 31) ? 1u : 0u;
+    d->tv.nibbleOrder = d->info.sliceWidth == 4 ? 1u : 0u;
     d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = pitch;
     d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
@@ -852,7 +855,9 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
 {
     unsigned long long *dc = d->counters.as<unsigned long long>();
     CKR(ensure_visits(d, maxDist, st));
-    const uint32_t v0 = d->waveStart[s0], v1 = d->waveStart[s0 + ns], nv = v1 - v0;
+    // the visit table is ordered by byte slice; sliceWidth 4 runs it in one piece (score_batch)
+    const bool nibble = d->info.sliceWidth == 4;
+    const uint32_t v0 = nibble ? d->waveStart[0] : d->waveStart[s0], v1 = nibble ? d->waveStart[5] : d->waveStart[s0 + ns], nv = v1 - v0;
     CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
     k_wave_candidates<<<blocks_for((uint64_t)n * ns, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
     d->stats.launches += 1;
@@ -967,13 +972,16 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
 
     // without early exit all slices go in one wave; with it, one wave per slice so that guides
     // which exited stop generating work (ref :501-502)
-    const uint32_t wave = checkExit ? 1 : S;
+    // sliceWidth 4 under TRIPLE: a whole byte is exact only up to maxDist 4, and the visit table's waves are by byte,
+    // not by the reference's 2-base slices: one wave, the early exit takes effect in the ordered accumulation
+    const bool nibble = d->layout == ISSL_LAYOUT_TRIPLE && d->info.sliceWidth == 4;
+    const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= (nibble ? std::min(d->tripleMaxDist, 4) : d->tripleMaxDist);
+    const uint32_t wave = (checkExit && !(useTriple && nibble)) ? 1 : S;
     for (uint32_t s0 = 0; s0 < S; s0 += wave) {
         const uint32_t ns = std::min(wave, S - s0);
         const uint64_t pairs = (uint64_t)n * ns;
         const uint8_t *doneMask = checkExit ? d->done.as<uint8_t>() : nullptr;
 
-        const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= d->tripleMaxDist;
         const int posBits = useTriple ? kTripleKeyBits : d->pbits;
         uint64_t nHits = 0;
         if (useTriple) {

@@ -24,7 +24,9 @@ namespace issl {
 constexpr uint32_t kTripleCount = 10;
 constexpr uint32_t kTripleBuckets = 1u << 24;
 constexpr int kTripleThreads = 128;              // per CTA = per guide
-constexpr int kTripleKeyBits = 35;               // survivor key = guide << 35 | lowest exact slice << 32 | site id
+constexpr int kTripleKeyBits = 36;               // survivor key = guide << 36 | ordering slice << 32 | site id
+constexpr uint32_t kOrderSlices = 10;            // ordering slices: 5 (sliceWidth 8) or 10 (sliceWidth 4)
+constexpr uint32_t kNoSlice = 15;                // a record that is not a hit in its triple
 
 // slices of triple t: key bytes 0..2 (L, M, H), then p < q (residual bytes 0..1) -- issl_triple_tables.h
 __constant__ uint8_t c_tripleSlices[kTripleCount][5] = ISSL_TRIPLE_LAYOUT_INIT;
@@ -43,6 +45,10 @@ struct TripleView {
     // lookup in front of it, and 31 residuals are tested with ~30 bitwise instructions.
     const uint4 *blk;
     uint32_t pitch;         // 16-bit slots per bucket: 0 (no blocked copy), 32, 64 or 128
+    // sliceWidth 4 (ten 2-base slices): with maxDist <= 4 every site within maxDist agrees with the guide on a whole
+    // byte, so the same buckets are read; only the order differs -- the reference meets a hit first in the lowest
+    // 2-base slice that matches exactly, which may lie below the lowest exact byte
+    uint32_t nibbleOrder;
 };
 constexpr uint32_t kSubEntries = 31;
 
@@ -152,7 +158,7 @@ constexpr uint32_t kTripleHitCap = ISSL_TRIPLE_HIT_CAP;   // per CTA; a guide wi
 // ------------------------------------------------------------------------------------------------
 // Finishing one guide inside a CTA (used by the fused tail of the bucket scan and by k_score_segments):
 // every hit is scored where it lies (ref :392-461); the accumulation order wanted is (slice, id) -- the
-// reference's visiting order, ref :330-344 -- so hits are split by slice (5 groups, a counting pass), every hit's
+// reference's visiting order, ref :330-344 -- so hits are split by slice (5 or 10 groups, a counting pass), every hit's
 // rank inside its group is counted by one warp per group (~55 ids per group on a uniform genome), the
 // contributions are moved into that order, and one thread adds them up one rounded sum at a time with the
 // reference's early exit (ref :394, :460, :466-502).
@@ -172,7 +178,7 @@ struct ScoreParams {
 
 struct ScoreShared {
     double mit[kTripleThreads], cfd[kTripleThreads];   // a window of contributions in accumulation order
-    uint32_t cnt[5], fill[5], out[6];
+    uint32_t cnt[kOrderSlices], fill[kOrderSlices], out[kOrderSlices + 1];
 };
 constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one u32 id per hit
 
@@ -183,7 +189,7 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
                                             const ScoreParams &sp, double *totMitOut, double *totCfdOut, uint8_t *doneOut, Load load)
 {
     constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
-    if (threadIdx.x < 5) { ss.cnt[threadIdx.x] = 0; ss.fill[threadIdx.x] = 0; }
+    if (threadIdx.x < kOrderSlices) { ss.cnt[threadIdx.x] = 0; ss.fill[threadIdx.x] = 0; }
     __syncthreads();
     uint32_t myId[kPerThread], mySlice[kPerThread];
     double myMit[kPerThread], myCfd[kPerThread];   // shared memory per SM is L1 the scan cannot use: contributions stay in registers
@@ -191,12 +197,12 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         const uint32_t j = threadIdx.x + k * kTripleThreads;
-        mySlice[k] = 7;
+        mySlice[k] = kNoSlice;
         if (j < n) {
-            uint32_t idRaw = 0, slice = 7;
+            uint32_t idRaw = 0, slice = kNoSlice;
             uint64_t site = kSiteUnknown;
             load(j, idRaw, slice, site);
-            if (slice >= 5) continue;   // not a hit in this triple (the triple responsible for it reports it)
+            if (slice >= kOrderSlices) continue;   // not a hit in this triple (the triple responsible for it reports it)
             const uint32_t id = idRaw & idMask;
             myId[k] = id; mySlice[k] = slice;
             atomicAdd(&ss.cnt[slice], 1u);
@@ -211,14 +217,14 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t out = 0;
-        for (uint32_t s = 0; s < 5; s++) { ss.out[s] = out; out += ss.cnt[s]; }
-        ss.out[5] = out;
+        for (uint32_t s = 0; s < kOrderSlices; s++) { ss.out[s] = out; out += ss.cnt[s]; }
+        ss.out[kOrderSlices] = out;
     }
     __syncthreads();
     uint32_t *gid = reinterpret_cast<uint32_t *>(group);                       // ids, grouped by slice
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++)
-        if (mySlice[k] < 5) gid[ss.out[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u)] = myId[k];
+        if (mySlice[k] < kOrderSlices) gid[ss.out[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u)] = myId[k];
     __syncthreads();
     // rank of every hit inside its slice group = number of smaller ids (ids of one guide are distinct): every thread
     // counts for its own hits over the whole group (broadcast reads); groups are small (~55 ids)
@@ -226,7 +232,7 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         myRank[k] = 0xFFFFFFFFu;
-        if (mySlice[k] < 5) {
+        if (mySlice[k] < kOrderSlices) {
             const uint32_t c = ss.cnt[mySlice[k]], base = ss.out[mySlice[k]], mine = myId[k];
             uint32_t r = 0;
             for (uint32_t q = 0; q < c; q++) r += (uint32_t)(gid[base + q] < mine);
@@ -235,7 +241,7 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
     }
     // ordered accumulation with the reference's early exit (ref :394, :460, :466-502): the contributions pass through
     // a window of shared memory in rank order, kTripleThreads at a time, and one thread adds them up
-    const uint32_t kept = ss.out[5];
+    const uint32_t kept = ss.out[kOrderSlices];
     double mit = 0.0, cfd = 0.0;
     bool stop = false;
     if (threadIdx.x == 0) { mit = sp.totMit[guide]; cfd = sp.totCfd[guide]; }
@@ -383,6 +389,26 @@ __device__ __forceinline__ uint64_t hit_site(const TripleView &tv, uint2 h)
            ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
 }
 
+// the slice through which the reference meets a hit first (ref isslScoreOfftargets.cpp:330-390): the lowest exactly
+// matching slice -- a byte for sliceWidth 8, a 2-base nibble for sliceWidth 4
+__device__ __forceinline__ uint32_t order_slice(const TripleView &tv, uint64_t siteXorGuide, uint32_t minExactByte)
+{
+    if (!tv.nibbleOrder) return minExactByte;
+    uint32_t s = 0;
+    while (s < 2 * minExactByte && ((siteXorGuide >> (4 * s)) & 15ull) != 0) s++;   // the exact byte is two exact nibbles
+    return s;
+}
+
+// ... for a record whose id is known (general-pipeline keys, segments)
+__device__ __forceinline__ uint32_t record_order_slice(const TripleView &tv, const uint64_t *sig, uint2 h, uint64_t g, uint32_t idRaw,
+                                                       uint32_t minExactByte)
+{
+    if (!tv.nibbleOrder) return minExactByte;
+    uint64_t site = hit_site(tv, h);
+    if (site == kSiteUnknown) site = __ldg(sig + (idRaw & (tv.occFlag ? 0x7FFFFFFFu : ~0u)));
+    return order_slice(tv, site ^ g, minExactByte);
+}
+
 template <bool CHECKED = false>
 __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 h)
 {
@@ -396,7 +422,8 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
         if (!record_keep(h, minE)) return;
         const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)];
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
-        if (gs < a.hitCap) a.hitKeys[gs] = general_key(a.tv, guide, minE, id);
+        if (gs < a.hitCap)
+            a.hitKeys[gs] = general_key(a.tv, guide, record_order_slice(a.tv, a.sp.sig, h, a.guides[guide], id, minE), id);
     }
 }
 
@@ -416,7 +443,8 @@ __device__ __forceinline__ void triple_flush(const TripleArgs &a, TripleShared &
         record_keep(h, minE);
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + j;
-        if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, minE, id);
+        if (slot < a.hitCap)
+            a.hitKeys[slot] = general_key(a.tv, guide, record_order_slice(a.tv, a.sp.sig, h, a.guides[guide], id, minE), id);
     }
     __syncthreads();
     if (threadIdx.x == 0) { sh.nHits = 0; sh.flushed = 1; }
@@ -509,11 +537,15 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         score_guide(sm.score, sm.group, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
                     [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
                         const uint2 h = sh.hits[j];
-                        if (!record_keep(h, slice)) { slice = 7; return; }
+                        if (!record_keep(h, slice)) { slice = kNoSlice; return; }
                         idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
                         site = hit_site(a.tv, h);
+                        if (a.tv.nibbleOrder) {
+                            if (site == kSiteUnknown) site = __ldg(a.sp.sig + (idRaw & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u)));
+                            slice = order_slice(a.tv, site ^ g, slice);
+                        }
                     });
-        if (threadIdx.x == 0 && sm.score.out[5]) atomicAdd(a.fusedHits, (unsigned long long)sm.score.out[5]);
+        if (threadIdx.x == 0 && sm.score.out[kOrderSlices]) atomicAdd(a.fusedHits, (unsigned long long)sm.score.out[kOrderSlices]);
         return;
     }
     // hand the hits on: de-duplicate, compact, reserve a range of the segment / key buffer, resolve ids
@@ -544,10 +576,11 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         const uint2 h = sh.hits[threadIdx.x + k * kTripleThreads];
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + myPos[k];
+        const uint32_t slice = record_order_slice(a.tv, a.sp.sig, h, g, id, myMinE[k]);
         if (!segment) {
-            if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, myMinE[k], id);
+            if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, slice, id);
         } else if (slot < a.segCap) {
-            a.segKeys[slot] = ((uint64_t)myMinE[k] << 32) | id;
+            a.segKeys[slot] = ((uint64_t)slice << 32) | id;
             a.segSites[slot] = hit_site(a.tv, h);
         }
     }
@@ -731,7 +764,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
     score_guide(ss, group, n, guide, a.guides[guide], a.sp, a.sp.totMit, a.sp.totCfd, a.sp.done,
                 [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
                     const uint64_t key = a.segKeys[off + j];
-                    idRaw = (uint32_t)key; slice = (uint32_t)(key >> 32) & 7u;
+                    idRaw = (uint32_t)key; slice = (uint32_t)(key >> 32) & 15u;
                     site = a.segSites[off + j];
                 });
 }

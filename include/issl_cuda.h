@@ -71,7 +71,8 @@ typedef enum issl_layout {
     ISSL_LAYOUT_SIG64 = 2,    /* slice lists hold the 64-bit signature inline: 8 B / candidate      */
     ISSL_LAYOUT_GATHER = 3,   /* slice lists hold 32-bit ids, signatures gathered: 4 + 8 B / candidate
                                  (the layout BASELINE.json's north_star describes; kept for comparison) */
-    ISSL_LAYOUT_TRIPLE = 4    /* seqLength 20, sliceWidth 8 only.  RES32 plus, for each of the 10 slice triples,
+    ISSL_LAYOUT_TRIPLE = 4    /* seqLength 20, sliceWidth 8 (or 4, maxDist <= 4: ids-only lists instead of RES32).  RES32
+                                 plus, for each of the 10 slice triples,
                                  the sites bucketed by their three slice values (2^24 buckets, ascending id inside)
                                  with the remaining 16 signature bits inline: every slice list sub-divided by two
                                  more slices.  A guide then reads only the sub-buckets that can hold a site within

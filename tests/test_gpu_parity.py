@@ -32,7 +32,7 @@ def fmt_stdout(guides_packed, mit, cfd, seq_length=20):
 def layouts_for(case):
     w, L = case.slice_width, case.seq_length
     res32 = w % 2 == 0 and 2 * L - min(w, 8) <= 32
-    triple = w == 8 and L == 20
+    triple = w in (8, 4) and L == 20
     return (["triple"] if triple else []) + (["res32"] if res32 else []) + ["sig64", "gather"]
 
 
@@ -295,6 +295,48 @@ def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     dev.close()
 
 
+@pytest.mark.parametrize("fuse,blocks", [(2, "64"), (1, "32"), (0, "0"), (2, "0")])
+def test_triple_layout_slice_width_4(fuse, blocks):
+    """sliceWidth 4 (ten 2-base slices) under TRIPLE: up to maxDist 4 the same sub-buckets are read, but hits are
+    accumulated in the order of the lowest exactly matching 2-base slice, and the early exit takes effect in the
+    ordered accumulation (one wave); above maxDist 4 the ids-only slice lists are scanned.  Large batch, so that the
+    fused tail, the segment kernel and the general pipeline (guides with more than 512 hits) all run."""
+    text = td.make_offtargets(61, n_random=100_000, n_families=25, family_size=800, max_sub_rate=0.12)
+    img = oracle.create_index(text, 20, 4)
+    rng = np.random.default_rng(62)
+    roots = td.pack_guides(td.make_guides(63, text, n=400, frac_exact=1.0, frac_mut=0.0))
+    guides = []
+    for r in roots:
+        for _ in range(6):
+            g = int(r)
+            for pos in rng.choice(20, size=int(rng.integers(0, 4)), replace=False):
+                g ^= int(rng.integers(1, 4)) << (2 * int(pos))
+            guides.append(g)
+    guides = np.concatenate([np.array(guides, dtype=np.uint64), rng.integers(0, 1 << 40, 400, dtype=np.uint64)])
+    os.environ["ISSL_TRIPLE_FUSE"] = str(fuse)
+    os.environ["ISSL_TRIPLE_BLOCKS"] = blocks
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, "auto")
+    finally:
+        del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"]
+    assert dev.info["layout"] == cb.LAYOUTS["triple"]
+    for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 4), ("mit", 0, 2), ("cfd", 20, 4), ("and", 30, 5)):
+        want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
+        mit, cfd = dev.score(guides, md, thr, method)
+        if method != "cfd":
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (fuse, blocks, method, thr, md)
+        if method != "mit":
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (fuse, blocks, method, thr, md)
+        st = dev.stats
+        if thr == 0:
+            assert st["candidates"] == int(want["candidates"].sum())
+        assert (st["bucket_visits"] > 0) == (md <= 4)
+    _, _, hits = dev.score_hits(guides[:600], 4, 0, "and")
+    want = oracle.score(img, guides[:600], 4, 0, "and", threads=1, want_hits=True)["hits"]
+    assert np.array_equal(hits, np.stack([want[k].astype(np.int64) for k in ("guide", "id", "dist", "occ")], axis=1))
+    dev.close()
+
+
 def test_edge_cases():
     case = golden_case("w8_families")
     dev = device_for("w8_families", "auto")
@@ -350,7 +392,7 @@ def test_corrupt_lists_are_refused():
     assert e.value.code == 6
 
 
-@pytest.mark.parametrize("w,layout", [(8, "triple"), (8, "res32"), (8, "gather"), (10, "res32"), (4, "sig64")])
+@pytest.mark.parametrize("w,layout", [(8, "triple"), (8, "res32"), (8, "gather"), (10, "res32"), (4, "sig64"), (4, "triple")])
 def test_synthetic_index_is_what_the_reference_builder_would_write(w, layout, tmp_path):
     dev = cb.Device.synthetic(0, layout, seed=5, uniform_sites=30_000, families=8, family_size=400, max_sub_rate=0.1,
                               slice_width=w)
