@@ -8,10 +8,11 @@ run --slice-width 8 --max-dist 2 --steps 3 --warmup 1
 run --slice-width 8 --max-dist 3 --steps 3 --warmup 1
 run --slice-width 8 --max-dist 5 --steps 3 --warmup 1
 run --slice-width 8 --max-dist 6 --guides 20000 --steps 2 --warmup 1
-# config 5: slice-width sweep (w=10 and w=4 take the list-scan layouts: inline 32-bit residuals / 64-bit signatures)
+# config 5: slice-width sweep (w=10 takes the list scan over inline 32-bit residuals; w=4 the sub-bucket scan up to maxDist 4)
 run --slice-width 10 --max-dist 3 --steps 3 --warmup 1
 run --slice-width 10 --max-dist 4 --steps 3 --warmup 1
-run --slice-width 4 --max-dist 4 --guides 10000 --steps 2 --warmup 1
+run --slice-width 4 --max-dist 4 --steps 3 --warmup 1
+run --slice-width 4 --max-dist 4 --layout sig64 --guides 10000 --steps 2 --warmup 1
 # config 4: repeat-rich mouse-scale genome (2.7 Gbp -> 506.25 M uniform sites + 2000 planted families of 5000 copies),
 # half of the guides from the families, thresholds 0 (full scan) and 75 (early exit)
 run --sites 506250000 --families 2000 --family-size 5000 --family-guides 0.5 --threshold 0 --steps 3 --warmup 1
