@@ -1067,6 +1067,10 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         }   // list scan
         if (nHits == 0) continue;
 
+        if (useTriple && nibble) {   // sliceWidth 4: the keys carry the lowest exact byte; the reference orders by 2-base slice
+            k_fix_order_slices<<<blocks_for(nHits, 256), 256, 0, st>>>(d->keysA.as<uint64_t>(), nHits, dGuides, d->sig.as<uint64_t>());
+            d->stats.launches += 1;
+        }
         // canonical order: sort keys (guide, position)
         int gbits = 1;
         while ((1ull << gbits) < n) gbits++;

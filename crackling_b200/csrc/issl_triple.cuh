@@ -365,8 +365,9 @@ __device__ __forceinline__ bool record_keep(uint2 h, uint32_t &minE)
     return resp == t;
 }
 
-// key of the general pipeline: guide << 35 | slice << 32 | id, plus -- outside the bits that are sorted -- "occurs
-// once" when the stored id says so, which saves k_contrib the occurrence lookup
+// key of the general pipeline: guide << 36 | slice << 32 | id, plus -- outside the bits that are sorted -- "occurs
+// once" when the stored id says so, which saves k_contrib the occurrence lookup.  The slice is the lowest exact BYTE;
+// for sliceWidth 4 k_fix_order_slices turns it into the lowest exact 2-base slice before the keys are sorted.
 __device__ __forceinline__ uint64_t general_key(const TripleView &tv, uint32_t guide, uint32_t minE, uint32_t idRaw)
 {
     const uint64_t once = (tv.occFlag && !(idRaw & 0x80000000u)) ? kKeyOccursOnce : 0ull;
@@ -422,8 +423,7 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
         if (!record_keep(h, minE)) return;
         const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)];
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
-        if (gs < a.hitCap)
-            a.hitKeys[gs] = general_key(a.tv, guide, record_order_slice(a.tv, a.sp.sig, h, a.guides[guide], id, minE), id);
+        if (gs < a.hitCap) a.hitKeys[gs] = general_key(a.tv, guide, minE, id);
     }
 }
 
@@ -443,8 +443,7 @@ __device__ __forceinline__ void triple_flush(const TripleArgs &a, TripleShared &
         record_keep(h, minE);
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + j;
-        if (slot < a.hitCap)
-            a.hitKeys[slot] = general_key(a.tv, guide, record_order_slice(a.tv, a.sp.sig, h, a.guides[guide], id, minE), id);
+        if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, minE, id);
     }
     __syncthreads();
     if (threadIdx.x == 0) { sh.nHits = 0; sh.flushed = 1; }
@@ -576,11 +575,10 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         const uint2 h = sh.hits[threadIdx.x + k * kTripleThreads];
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + myPos[k];
-        const uint32_t slice = record_order_slice(a.tv, a.sp.sig, h, g, id, myMinE[k]);
         if (!segment) {
-            if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, slice, id);
+            if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, myMinE[k], id);
         } else if (slot < a.segCap) {
-            a.segKeys[slot] = ((uint64_t)slice << 32) | id;
+            a.segKeys[slot] = ((uint64_t)record_order_slice(a.tv, a.sp.sig, h, g, id, myMinE[k]) << 32) | id;
             a.segSites[slot] = hit_site(a.tv, h);
         }
     }
@@ -736,6 +734,19 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
             if (__syncthreads_or(sh.nHits > kTripleFlushAt)) triple_flush(a, sh, guide);
     }
     triple_epilogue<FUSED>(a, sm, guide, g, entries, visited);
+}
+
+// sliceWidth 4: the ordering slice of every general-pipeline key, from the site itself (ref :330-390: a hit is met
+// first in the lowest exactly matching 2-base slice)
+__global__ void k_fix_order_slices(uint64_t *keys, uint64_t n, const uint64_t *guides, const uint64_t *sig)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t key = keys[j];
+    const uint64_t x = sig[(uint32_t)key] ^ guides[(key & ~kKeyOccursOnce) >> kTripleKeyBits];
+    uint64_t s = 0;
+    while (s < 9 && ((x >> (4 * s)) & 15ull) != 0) s++;
+    keys[j] = (key & ~(15ull << 32)) | (s << 32);
 }
 
 // ------------------------------------------------------------------------------------------------
