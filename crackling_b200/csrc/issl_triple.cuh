@@ -158,10 +158,10 @@ constexpr uint32_t kTripleHitCap = ISSL_TRIPLE_HIT_CAP;   // per CTA; a guide wi
 // ------------------------------------------------------------------------------------------------
 // Finishing one guide inside a CTA (used by the fused tail of the bucket scan and by k_score_segments):
 // every hit is scored where it lies (ref :392-461); the accumulation order wanted is (slice, id) -- the
-// reference's visiting order, ref :330-344 -- so hits are split by slice (5 or 10 groups, a counting pass), every hit's
-// rank inside its group is counted by one warp per group (~55 ids per group on a uniform genome), the
-// contributions are moved into that order, and one thread adds them up one rounded sum at a time with the
-// reference's early exit (ref :394, :460, :466-502).
+// reference's visiting order, ref :330-344 -- so hits are split by slice (5 or 10 groups, a counting pass), every
+// thread counts the rank of its own hits inside their group (~55 ids per group on a uniform genome), the
+// contributions pass through a window of shared memory in that order, and one thread adds them up one rounded
+// sum at a time with the reference's early exit (ref :394, :460, :466-502).
 // ------------------------------------------------------------------------------------------------
 constexpr uint64_t kSiteUnknown = ~0ull;   // a hit record without the site's signature: look it up in sig[]
 
