@@ -247,6 +247,10 @@ static int build_triple(issl_device *d)
     uint64_t needBlk = (uint64_t)kTripleCount * kTripleBuckets * pitch * 2;
     if (needBase + needBlk > freeB) { pitch = 0; needBlk = 0; }
     const uint64_t need = needBase;
+    // bit 31 of the stored ids doubles as "occurs more than once" when ids leave it free (ISSL_TRIPLE_OCCFLAG=0: tests
+    // of the path indexes with 2^31 sites or more take)
+    bool occFlag = N < (1ull << 31);
+    if (const char *e = getenv("ISSL_TRIPLE_OCCFLAG")) occFlag = occFlag && atoi(e) != 0;
     CKR(d->tripleRes.ensure(kTripleCount * stride * 2));
     CKR(d->tripleIds.ensure(kTripleCount * stride * 4));
     CKR(d->tripleOffs.ensure(kTripleCount * (kTripleBuckets + 1ull) * 4));
@@ -266,7 +270,7 @@ static int build_triple(issl_device *d)
         // stable: ids stay ascending inside a bucket, as inside the reference's lists (isslCreateIndex.cpp:225-233)
         CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(), ids, N, 0, 24, st));
         k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, d->tripleRes.as<uint16_t>() + t * stride);
-        if (N < (1ull << 31)) k_triple_flag_ids<<<blocks_for(N, 256), 256, 0, st>>>(d->occ.as<uint32_t>(), N, ids);
+        if (occFlag) k_triple_flag_ids<<<blocks_for(N, 256), 256, 0, st>>>(d->occ.as<uint32_t>(), N, ids);
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
         if (pitch)
@@ -281,7 +285,7 @@ static int build_triple(issl_device *d)
     d->tv.ids = d->tripleIds.as<uint32_t>();
     d->tv.offs = d->tripleOffs.as<uint32_t>();
     d->tv.stride = stride;
-    d->tv.occFlag = N < (1ull << 31) ? 1u : 0u;
+    d->tv.occFlag = occFlag ? 1u : 0u;
     d->tv.nibbleOrder = d->info.sliceWidth == 4 ? 1u : 0u;
     d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = pitch;

@@ -239,7 +239,8 @@ def test_triple_layout_sub_bucket_scan(triple_max):
 @pytest.mark.parametrize("fuse,blocks,flush,hit_cap", [(2, "64", "0", None), (2, "32", "0", None), (1, "64", "0", None),
                                                        (0, "0", "0", None), (2, "0", "0", None), (2, "64", "1", None),
                                                        (1, "32", "1", None), (0, "64", "1", None),
-                                                       (2, "64", "0", "3000"), (1, "64", "1", "3000"), (0, "32", "0", "3000")])
+                                                       (2, "64", "0", "3000"), (1, "64", "1", "3000"), (0, "32", "0", "3000"),
+                                                       (2, "64", "0", "noflag"), (1, "32", "1", "noflag"), (0, "64", "0", "noflag")])
 def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     """With at least 148 x 16 guides in a batch every guide gets one CTA, and the scan's tails come into play: 2 = the
     CTA sorts, scores and accumulates the guide's hits itself (fused), 1 = per-guide segments finished by
@@ -265,13 +266,16 @@ def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     os.environ["ISSL_TRIPLE_FUSE"] = str(fuse)
     os.environ["ISSL_TRIPLE_BLOCKS"] = blocks
     os.environ["ISSL_TRIPLE_FLUSH"] = flush
-    if hit_cap:
+    if hit_cap == "noflag":     # the path of indexes with >= 2^31 sites: no occurrence flag in the stored ids
+        os.environ["ISSL_TRIPLE_OCCFLAG"] = "0"
+    elif hit_cap:
         os.environ["ISSL_HIT_CAP"] = hit_cap
     try:
         dev = cb.Device.from_index(cb.Index(img), 0, "triple")
     finally:
         del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"], os.environ["ISSL_TRIPLE_FLUSH"]
         os.environ.pop("ISSL_HIT_CAP", None)
+        os.environ.pop("ISSL_TRIPLE_OCCFLAG", None)
     assert dev.info["triple_block_bytes"] == 2 * int(blocks)
     seen_big = False
     for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 5), ("mit", 0, 2), ("cfd", 20, 4)):
