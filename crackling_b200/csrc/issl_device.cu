@@ -951,6 +951,91 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     return ISSL_OK;
 }
 
+// List scan (RES32 / SIG64 / GATHER): survivors of slices [s0, s0 + ns) for the guides that are still active.
+// ref isslScoreOfftargets.cpp:330-390 for every (guide, slice) pair of the wave.
+static int list_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint32_t s0, uint32_t ns,
+                     const uint8_t *doneMask, int maxDist, EventTimer &timer, uint64_t *nHitsOut)
+{
+    unsigned long long *dc = d->counters.as<unsigned long long>();
+    const uint64_t pairs = (uint64_t)n * ns;
+    *nHitsOut = 0;
+    // group the (guide, slice) pairs by the list they select: radix sort of (list id, guide index)
+    const uint32_t nLists = (uint32_t)d->nLists;
+    CKR(d->pairKeys.ensure(pairs * 4)); CKR(d->pairVals.ensure(pairs * 4));
+    CKR(d->pairKeysSorted.ensure(pairs * 4)); CKR(d->pairValsSorted.ensure(pairs * 4));
+    CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
+    k_pair_keys<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, nLists,
+                                                       d->pairKeys.as<uint32_t>(), d->pairVals.as<uint32_t>(), dc + 0);
+    int keyBits = 1;
+    while ((1ull << keyBits) <= nLists) keyBits++;
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, d->pairKeys.as<uint32_t>(), d->pairKeysSorted.as<uint32_t>(),
+                                       d->pairVals.as<uint32_t>(), d->pairValsSorted.as<uint32_t>(), pairs, 0, keyBits, st));
+    CKR(d->sortTemp.ensure(tb));
+    CK(cub::DeviceRadixSort::SortPairs(d->sortTemp.p, tb, d->pairKeys.as<uint32_t>(), d->pairKeysSorted.as<uint32_t>(),
+                                       d->pairVals.as<uint32_t>(), d->pairValsSorted.as<uint32_t>(), pairs, 0, keyBits, st));
+    CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    d->stats.launches += 1 + (uint64_t)((keyBits + 7) / 8) + 2;
+    const uint64_t candidates = d->hCounters[0];
+    d->stats.candidates += candidates;
+    if (candidates == 0) return ISSL_OK;
+
+    // chunk: aim at a few hundred thousand items at most, never below two quanta
+    uint64_t chunk64 = (candidates / (1ull << 19) + kChunkQuantum - 1) / kChunkQuantum * kChunkQuantum;
+    chunk64 = std::max<uint64_t>(chunk64, 2 * kChunkQuantum);
+    chunk64 = std::min<uint64_t>(chunk64, 1ull << 30);
+    const uint32_t chunk = (uint32_t)chunk64;
+
+    uint32_t maxGroup = d->maxGroup;
+    if (maxGroup > kMaxGroup && !(d->iv.layout == ISSL_LAYOUT_RES32 && maxDist <= 7)) maxGroup = kMaxGroup;
+    CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
+    k_group_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
+                                                         maxGroup, d->pairCounts.as<uint32_t>(), dc + 4);
+    CK(cudaMemsetAsync(d->pairCounts.as<uint32_t>() + pairs, 0, 4, st));
+    tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
+    CKR(d->scanTemp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(d->scanTemp.p, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
+    CK(cudaMemcpyAsync(d->hCounters + 2, d->pairOffsets.as<uint32_t>() + pairs, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(d->hCounters + 4, dc + 4, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t nItems = *reinterpret_cast<uint32_t *>(d->hCounters + 2);
+    d->stats.streamed += d->hCounters[4];
+    CKR(d->items.ensure((size_t)nItems * sizeof(ScanItem)));
+    k_group_fill<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
+                                                        maxGroup, d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
+    d->stats.launches += 4;
+
+    // K1 (re-run with a larger survivor buffer if it overflowed)
+    for (;;) {
+        CKR(ensure_hit_buffers(d, n));
+        CK(cudaMemsetAsync(dc + 1, 0, 8, st));
+        ScanArgs a;
+        a.iv = d->iv; a.items = d->items.as<ScanItem>(); a.guides = dGuides;
+        a.sortedGuide = d->pairValsSorted.as<uint32_t>(); a.hitKeys = d->keysA.as<uint64_t>();
+        a.hitCount = dc + 1; a.hitCap = d->hitCap; a.maxDist = maxDist; a.pbits = d->pbits;
+        cudaEvent_t e0, e1;
+        CKR(timer.get(&e0)); CKR(timer.get(&e1));
+        timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
+        CK(cudaEventRecord(e0, st));
+        if (d->iv.layout == ISSL_LAYOUT_RES32) k_scan<kRes32><<<nItems, kScanThreads, 0, st>>>(a);
+        else if (d->iv.layout == ISSL_LAYOUT_SIG64) k_scan<kSig64><<<nItems, kScanThreads, 0, st>>>(a);
+        else k_scan<kGather><<<nItems, kScanThreads, 0, st>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, st));
+        CK(cudaMemcpyAsync(d->hCounters + 1, dc + 1, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        d->stats.scan_launches += 1;
+        d->stats.launches += 1;
+        *nHitsOut = d->hCounters[1];
+        if (*nHitsOut <= d->hitCap) break;
+        d->hitCap = *nHitsOut + *nHitsOut / 4;
+        CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+    }
+    return ISSL_OK;
+}
+
 // one batch of <= maxBatch guides, already resident at dGuides
 static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides, uint32_t n, uint64_t guideBase, int maxDist,
                        double threshold, int method, double *dMit, double *dCfd, HitSink *sink, EventTimer &timer)
@@ -983,7 +1068,6 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     const uint32_t wave = (checkExit && !(useTriple && nibble)) ? 1 : S;
     for (uint32_t s0 = 0; s0 < S; s0 += wave) {
         const uint32_t ns = std::min(wave, S - s0);
-        const uint64_t pairs = (uint64_t)n * ns;
         const uint8_t *doneMask = checkExit ? d->done.as<uint8_t>() : nullptr;
 
         const int posBits = useTriple ? kTripleKeyBits : d->pbits;
@@ -994,81 +1078,8 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             ws.method = method; ws.maximumSum = maximumSum;
             CKR(triple_wave(d, st, dGuides, n, s0, ns, doneMask, maxDist, ws, timer, &nHits));
         } else {
-        // group the (guide, slice) pairs by the list they select: radix sort of (list id, guide index)
-        const uint32_t nLists = (uint32_t)d->nLists;
-        CKR(d->pairKeys.ensure(pairs * 4)); CKR(d->pairVals.ensure(pairs * 4));
-        CKR(d->pairKeysSorted.ensure(pairs * 4)); CKR(d->pairValsSorted.ensure(pairs * 4));
-        CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
-        k_pair_keys<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, nLists,
-                                                           d->pairKeys.as<uint32_t>(), d->pairVals.as<uint32_t>(), dc + 0);
-        int keyBits = 1;
-        while ((1ull << keyBits) <= nLists) keyBits++;
-        size_t tb = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, d->pairKeys.as<uint32_t>(), d->pairKeysSorted.as<uint32_t>(),
-                                           d->pairVals.as<uint32_t>(), d->pairValsSorted.as<uint32_t>(), pairs, 0, keyBits, st));
-        CKR(d->sortTemp.ensure(tb));
-        CK(cub::DeviceRadixSort::SortPairs(d->sortTemp.p, tb, d->pairKeys.as<uint32_t>(), d->pairKeysSorted.as<uint32_t>(),
-                                           d->pairVals.as<uint32_t>(), d->pairValsSorted.as<uint32_t>(), pairs, 0, keyBits, st));
-        CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        d->stats.launches += 1 + (uint64_t)((keyBits + 7) / 8) + 2;
-        const uint64_t candidates = d->hCounters[0];
-        d->stats.candidates += candidates;
-        if (candidates == 0) continue;
-
-        // chunk: aim at a few hundred thousand items at most, never below two quanta
-        uint64_t chunk64 = (candidates / (1ull << 19) + kChunkQuantum - 1) / kChunkQuantum * kChunkQuantum;
-        chunk64 = std::max<uint64_t>(chunk64, 2 * kChunkQuantum);
-        chunk64 = std::min<uint64_t>(chunk64, 1ull << 30);
-        const uint32_t chunk = (uint32_t)chunk64;
-
-        uint32_t maxGroup = d->maxGroup;
-        if (maxGroup > kMaxGroup && !(d->iv.layout == ISSL_LAYOUT_RES32 && maxDist <= 7)) maxGroup = kMaxGroup;
-        CKR(d->pairCounts.ensure((pairs + 1) * 4)); CKR(d->pairOffsets.ensure((pairs + 1) * 4));
-        k_group_count<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
-                                                             maxGroup, d->pairCounts.as<uint32_t>(), dc + 4);
-        CK(cudaMemsetAsync(d->pairCounts.as<uint32_t>() + pairs, 0, 4, st));
-        tb = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
-        CKR(d->scanTemp.ensure(tb));
-        CK(cub::DeviceScan::ExclusiveSum(d->scanTemp.p, tb, d->pairCounts.as<uint32_t>(), d->pairOffsets.as<uint32_t>(), pairs + 1, st));
-        CK(cudaMemcpyAsync(d->hCounters + 2, d->pairOffsets.as<uint32_t>() + pairs, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(d->hCounters + 4, dc + 4, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const uint32_t nItems = *reinterpret_cast<uint32_t *>(d->hCounters + 2);
-        d->stats.streamed += d->hCounters[4];
-        CKR(d->items.ensure((size_t)nItems * sizeof(ScanItem)));
-        k_group_fill<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, d->pairKeysSorted.as<uint32_t>(), (uint32_t)pairs, nLists, chunk,
-                                                            maxGroup, d->pairOffsets.as<uint32_t>(), d->items.as<ScanItem>());
-        d->stats.launches += 4;
-
-        // K1 (re-run with a larger survivor buffer if it overflowed)
-        for (;;) {
-            CKR(ensure_hit_buffers(d, n));
-            CK(cudaMemsetAsync(dc + 1, 0, 8, st));
-            ScanArgs a;
-            a.iv = d->iv; a.items = d->items.as<ScanItem>(); a.guides = dGuides;
-            a.sortedGuide = d->pairValsSorted.as<uint32_t>(); a.hitKeys = d->keysA.as<uint64_t>();
-            a.hitCount = dc + 1; a.hitCap = d->hitCap; a.maxDist = maxDist; a.pbits = d->pbits;
-            cudaEvent_t e0, e1;
-            CKR(timer.get(&e0)); CKR(timer.get(&e1));
-            timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
-            CK(cudaEventRecord(e0, st));
-            if (d->iv.layout == ISSL_LAYOUT_RES32) k_scan<kRes32><<<nItems, kScanThreads, 0, st>>>(a);
-            else if (d->iv.layout == ISSL_LAYOUT_SIG64) k_scan<kSig64><<<nItems, kScanThreads, 0, st>>>(a);
-            else k_scan<kGather><<<nItems, kScanThreads, 0, st>>>(a);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(e1, st));
-            CK(cudaMemcpyAsync(d->hCounters + 1, dc + 1, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            d->stats.scan_launches += 1;
-            d->stats.launches += 1;
-            nHits = d->hCounters[1];
-            if (nHits <= d->hitCap) break;
-            d->hitCap = nHits + nHits / 4;
-            CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
+            CKR(list_wave(d, st, dGuides, n, s0, ns, doneMask, maxDist, timer, &nHits));
         }
-        }   // list scan
         if (nHits == 0) continue;
 
         if (useTriple && nibble) {   // sliceWidth 4: the keys carry the lowest exact byte; the reference orders by 2-base slice
