@@ -479,13 +479,13 @@ def main() -> int:
 
     result = {"metric": "guides scored/sec (MIT+CFD, <=4 mm)", "value": value, "unit": "guides/s", "n_gpus": world,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-              "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 xor+popcount, f64 scores", "data": "synthetic",
+              "scaling": "weak", "vs_baseline": None,
+              "dtype": "u16 bit-sliced compare (LOP3), f64 scores" if triple_scan else "u32/u64 xor+popcount, f64 scores", "data": "synthetic",
               "config": config, "clocks": dict(clocks.summary(), window=clock_window),
               "e2e": {"value": e2e_value, "unit": "guides/s", "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 16)},
               "gpu_launches": int(launches), "scan_launches": int(scan_launches),
               "hits_per_guide": hits / max(args.steps * n, 1), "candidates_per_guide": candidates / max(args.steps * n, 1),
               "early_exit_fraction": early_exits / max(args.steps * n, 1),
-              "dtype_note": "u16 bit-sliced residual compare (LOP3), f64 scores" if triple_scan else "u32/u64 xor+popcount, f64 scores",
               "roofline": roofline}
 
     if world == 1 and not args.no_cpu_baseline:
