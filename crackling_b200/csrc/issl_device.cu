@@ -55,6 +55,7 @@ struct issl_device {
     DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
+    int waves = 1;                   // ISSL_WAVES: how slices are cut into launches when there is an early exit (score_batch)
     int tripleFlush = -1;            // ISSL_TRIPLE_FLUSH: 1 / 0 force the scan variant that flushes full record lists; -1 automatic
     double lastHitsPerGuide = 0;     // of the previous scoring call on this handle
     int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments from
@@ -306,6 +307,7 @@ static int new_device(int cuda_device, issl_device **out)
         const long v = atol(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) d->maxGroup = (uint32_t)v;
     }
+    if (const char *e = getenv("ISSL_WAVES")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->waves = v; }
     if (const char *e = getenv("ISSL_HIT_CAP")) { const long v = atol(e); if (v > 0) d->firstHitCap = (uint64_t)v; }
     if (const char *e = getenv("ISSL_TRIPLE_FLUSH")) d->tripleFlush = atoi(e) != 0;
     if (const char *e = getenv("ISSL_TRIPLE_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->tripleFuse = v; }
@@ -861,7 +863,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     CKR(ensure_visits(d, maxDist, st));
     // the visit table is ordered by byte slice; sliceWidth 4 runs it in one piece (score_batch)
     const bool nibble = d->info.sliceWidth == 4;
-    const uint32_t v0 = nibble ? d->waveStart[0] : d->waveStart[s0], v1 = nibble ? d->waveStart[5] : d->waveStart[s0 + ns], nv = v1 - v0;
+    const uint32_t v0 = nibble ? d->waveStart[0] : d->waveStart[s0], v1 = nibble ? d->waveStart[5] : d->waveStart[std::min(s0 + ns, 5u)], nv = v1 - v0;
     CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
     k_wave_candidates<<<blocks_for((uint64_t)n * ns, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
     d->stats.launches += 1;
@@ -1065,9 +1067,25 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     // not by the reference's 2-base slices: one wave, the early exit takes effect in the ordered accumulation
     const bool nibble = d->layout == ISSL_LAYOUT_TRIPLE && d->info.sliceWidth == 4;
     const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= (nibble ? std::min(d->tripleMaxDist, 4) : d->tripleMaxDist);
-    const uint32_t wave = (checkExit && !(useTriple && nibble)) ? 1 : S;
-    for (uint32_t s0 = 0; s0 < S; s0 += wave) {
-        const uint32_t ns = std::min(wave, S - s0);
+    // Waves: one slice at a time pays when many guides leave through the early exit (repeat families: their later slices
+    // are never scanned); when few do, every further launch only costs.  So after each single-slice wave the guides that
+    // left are counted, and once a wave sends fewer than a tenth of the batch through the exit all remaining slices go in
+    // one launch -- the ordered accumulation reproduces the exit points either way.  (ISSL_WAVES: 0 = one launch,
+    // 1 = adaptive, 2 = always one slice per wave.)
+    const bool oneWave = !checkExit || (useTriple && nibble) || d->waves == 0;
+    uint64_t doneBefore = 0;
+    bool merged = false;
+    for (uint32_t s0 = 0, ns = 0; s0 < S; s0 += ns) {
+        ns = (oneWave || merged) ? S - s0 : 1;
+        if (!oneWave && !merged && d->waves == 1 && s0 > 0) {
+            CK(cudaMemsetAsync(dc + 3, 0, 8, st));
+            k_count_done<<<blocks_for(n, 256), 256, 0, st>>>(d->done.as<uint8_t>(), n, dc + 3);
+            CK(cudaMemcpyAsync(d->hCounters + 3, dc + 3, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            d->stats.launches += 1;
+            if (d->hCounters[3] - doneBefore < n / 10) { merged = true; ns = S - s0; }
+            doneBefore = d->hCounters[3];
+        }
         const uint8_t *doneMask = checkExit ? d->done.as<uint8_t>() : nullptr;
 
         const int posBits = useTriple ? kTripleKeyBits : d->pbits;

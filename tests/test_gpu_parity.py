@@ -341,6 +341,38 @@ def test_triple_layout_slice_width_4(fuse, blocks):
     dev.close()
 
 
+@pytest.mark.parametrize("waves", ["0", "1", "2"])
+@pytest.mark.parametrize("layout", ["triple", "res32"])
+def test_early_exit_wave_policies(waves, layout):
+    """With an early exit the slices are scanned in waves (guides that left are dropped from later waves), in one
+    launch, or adaptively (single-slice waves until few guides leave, then the rest at once).  The printed score of an
+    early-exited guide depends on exactly where it stopped: every policy must reproduce the reference's exit points."""
+    text = td.make_offtargets(71, n_random=100_000, n_families=25, family_size=700, max_sub_rate=0.1)
+    img = oracle.create_index(text, 20, 8)
+    rng = np.random.default_rng(72)
+    roots = td.pack_guides(td.make_guides(73, text, n=500, frac_exact=1.0, frac_mut=0.0))
+    guides = np.concatenate([roots.repeat(5), rng.integers(0, 1 << 40, 500, dtype=np.uint64)])
+    for i in range(guides.size):                      # 0-2 substitutions per guide
+        for pos in rng.choice(20, size=int(rng.integers(0, 3)), replace=False):
+            guides[i] ^= np.uint64(int(rng.integers(1, 4)) << (2 * int(pos)))
+    os.environ["ISSL_WAVES"] = waves
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, layout)
+    finally:
+        del os.environ["ISSL_WAVES"]
+    exits = 0
+    for method, thr in (("and", 75), ("or", 60), ("avg", 90), ("mit", 30), ("cfd", 99.5), ("and", 5)):
+        want = oracle.score(img, guides, 4, thr, method, threads=0)
+        mit, cfd = dev.score(guides, 4, thr, method)
+        if method != "cfd":
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (waves, layout, method, thr)
+        if method != "mit":
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (waves, layout, method, thr)
+        exits += dev.stats["early_exits"]
+    assert exits > 1000
+    dev.close()
+
+
 def test_edge_cases():
     case = golden_case("w8_families")
     dev = device_for("w8_families", "auto")
