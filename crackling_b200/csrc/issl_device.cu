@@ -58,6 +58,7 @@ struct issl_device {
     int waves = 1;                   // ISSL_WAVES: how slices are cut into launches when there is an early exit (score_batch)
     int tripleFlush = -1;            // ISSL_TRIPLE_FLUSH: 1 / 0 force the scan variant that flushes full record lists; -1 automatic
     double lastHitsPerGuide = 0;     // of the previous scoring call on this handle
+    double lastExitFraction = -1.0;  // early exits / guides of the previous call that had an early exit to take; -1: none yet
     int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments from
                                      // per-guide segments, 0 = everything through the general sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
@@ -1072,7 +1073,10 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     // left are counted, and once a wave sends fewer than a tenth of the batch through the exit all remaining slices go in
     // one launch -- the ordered accumulation reproduces the exit points either way.  (ISSL_WAVES: 0 = one launch,
     // 1 = adaptive, 2 = always one slice per wave.)
-    const bool oneWave = !checkExit || (useTriple && nibble) || d->waves == 0;
+    //   The previous call on the handle is a good predictor: if fewer than a third of its guides left early, this one
+    // starts as one launch right away.
+    const bool oneWave = !checkExit || (useTriple && nibble) || d->waves == 0 ||
+                         (d->waves == 1 && d->lastExitFraction >= 0.0 && d->lastExitFraction < 0.33);
     uint64_t doneBefore = 0;
     bool merged = false;
     for (uint32_t s0 = 0, ns = 0; s0 < S; s0 += ns) {
@@ -1215,6 +1219,11 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     CK(cudaEventElapsedTime(&ms, t0, t1));
     d->stats.total_ms = ms;
     d->lastHitsPerGuide = n ? (double)d->stats.hits / (double)n : 0.0;
+    {
+        const double maximumSum = (10000.0 - threshold * 100) / threshold;
+        if (n && !(std::isnan(maximumSum) || (std::isinf(maximumSum) && maximumSum > 0)))
+            d->lastExitFraction = (double)d->stats.early_exits / (double)n;
+    }
     for (auto &pr : timer.scanPairs) {
         CK(cudaEventElapsedTime(&ms, d->evPool[pr.first], d->evPool[pr.second]));
         d->stats.scan_ms += ms;
