@@ -29,8 +29,12 @@ $(LIBDIR)/issl_sites.o: $(CSRC)/issl_sites.cu $(CSRC)/issl_device_common.cuh $(C
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o $@ $< 2> $(LIBDIR)/ptxas_sites.log || (cat $(LIBDIR)/ptxas_sites.log; false)
 
-$(LIBDIR)/libissl_cuda.so: $(LIBDIR)/issl_host.o $(LIBDIR)/issl_device.o $(LIBDIR)/issl_sites.o
-	$(NVCC) $(ARCH) -shared -o $@ $^ -Xcompiler -fopenmp -lgomp
+$(LIBDIR)/issl_multi.o: $(CSRC)/issl_multi.cpp $(CSRC)/issl_internal.h include/issl_cuda.h
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -c -o $@ $<
+
+$(LIBDIR)/libissl_cuda.so: $(LIBDIR)/issl_host.o $(LIBDIR)/issl_multi.o $(LIBDIR)/issl_device.o $(LIBDIR)/issl_sites.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -Xcompiler -fopenmp -lgomp -lpthread
 
 HOSTHDR   := include/issl_cuda.h $(CSRC)/issl_hostcommon.h $(CSRC)/issl_wire.h
 

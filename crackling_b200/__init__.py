@@ -6,6 +6,6 @@ hand-written sm_100a kernels in crackling_b200/csrc/) and the host program
 tests and by bench.py; it adds no compute of its own and has no CPU fallback.
 """
 from .binding import (  # noqa: F401
-    IsslError, Index, Device, Sites, lib, lib_path, build, pack_guides, unpack_guide, method_code,
+    IsslError, Index, Device, Sites, HostBuffer, replicate, score_multi, multi_chunk, lib, lib_path, build, pack_guides, unpack_guide, format_lines, method_code,
     local_mit_score, mit_table, triple_visits, triple_layout, device_count, cli_path, create_cli_path, extract_cli_path, LAYOUTS, METHODS,
 )

@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
             "issl_pack_guides": ([C.c_char_p, sz, sz, vp], i),
             "issl_unpack_guide": ([u64, sz, C.c_char_p], None),
             "issl_method_from_string": ([C.c_char_p], i),
+            "issl_format_lines": ([vp, vp, vp, sz, sz, i, vp, sz], sz),
             "issl_device_count": ([], i),
             "issl_device_create": ([vp, i, i, pp], i),
             "issl_device_create_synthetic": ([i, i, u64, u64, C.c_uint32, C.c_uint32, d, C.c_uint32, C.c_uint32, pp], i),
@@ -97,6 +98,7 @@ def lib() -> C.CDLL:
             "issl_sites_write_text": ([vp, C.c_char_p], i),
             "issl_sites_read_keys": ([vp, u64, u64, vp], i),
             "issl_device_create_from_sites": ([vp, C.c_uint32, i, pp], i),
+            "issl_device_clone": ([vp, i, pp], i),
             "issl_device_get_info": ([vp, C.POINTER(_DeviceInfo)], i),
             "issl_device_destroy": ([vp], None),
             "issl_device_write_issl": ([vp, C.c_char_p], i),
@@ -105,6 +107,10 @@ def lib() -> C.CDLL:
             "issl_score_device": ([vp, vp, sz, i, d, i, vp, vp, vp], i),
             "issl_score_hits": ([vp, vp, sz, i, d, i, vp, vp, vp, vp, vp, vp, sz, C.POINTER(sz)], i),
             "issl_last_stats": ([vp, C.POINTER(_Stats)], i),
+            "issl_score_multi": ([vp, sz, vp, sz, i, d, i, vp, vp, sz, C.POINTER(_Stats), vp], i),
+            "issl_multi_chunk": ([sz, sz], sz),
+            "issl_host_alloc": ([sz, pp], i),
+            "issl_host_free": ([vp], None),
             "issl_guide_filters": ([vp, C.c_char_p, sz, vp, vp, vp], i),
             "issl_local_mit_score": ([u64, sz], d),
             "issl_mit_table": ([sz, sz, vp, vp, sz, C.POINTER(u64)], sz),
@@ -145,6 +151,20 @@ def unpack_guide(sig: int, seq_length: int = 20) -> str:
     buf = C.create_string_buffer(seq_length + 1)
     lib().issl_unpack_guide(int(sig), seq_length, buf)
     return buf.raw[:seq_length].decode()
+
+
+def format_lines(guides: np.ndarray, mit, cfd, method, seq_length: int = 20) -> bytes:
+    """issl_format_lines: the reference's stdout lines for these guides and scores."""
+    g = np.ascontiguousarray(guides, dtype=np.uint64)
+    m = method_code(method)
+    mit = None if mit is None else np.ascontiguousarray(mit, dtype=np.float64)
+    cfd = None if cfd is None else np.ascontiguousarray(cfd, dtype=np.float64)
+    args = (g.ctypes.data, mit.ctypes.data if mit is not None else None, cfd.ctypes.data if cfd is not None else None,
+            g.size, seq_length, m)
+    need = lib().issl_format_lines(*args, None, 0)
+    buf = C.create_string_buffer(max(need, 1))
+    n = lib().issl_format_lines(*args, buf, need)
+    return buf.raw[:n]
 
 
 def local_mit_score(mask: int, seq_length: int = 20) -> float:
@@ -255,6 +275,12 @@ class Device:
         _check(lib().issl_device_create_from_sites(sites._h, slice_width, lay, C.byref(h)))
         return cls(h)
 
+    def clone(self, cuda_device: int) -> "Device":
+        """issl_device_clone: a replica of this index on another GPU, copied over NVLink."""
+        h = C.c_void_p()
+        _check(lib().issl_device_clone(self._h, int(cuda_device), C.byref(h)))
+        return Device(h)
+
     @property
     def info(self) -> dict:
         s = _DeviceInfo()
@@ -333,6 +359,74 @@ class Device:
         if self._h:
             lib().issl_device_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def replicate(first: Device, cuda_devices) -> list:
+    """Replicas of `first` on every device of cuda_devices (which starts with first's own device), fanned out as a
+    binary tree of peer copies: 0 -> 1, then 0 -> 2 and 1 -> 3, ... -- log2(n) rounds instead of n - 1 copies out of one GPU."""
+    import threading
+    devs = [first] + [None] * (len(cuda_devices) - 1)
+    have = 1
+    while have < len(devs):
+        jobs = [(src, have + src) for src in range(have) if have + src < len(devs)]
+        errors = []
+
+        def run(src, dst):
+            try:
+                devs[dst] = devs[src].clone(cuda_devices[dst])
+            except Exception as e:     # re-raised below, on the caller's thread
+                errors.append(e)
+        threads = [threading.Thread(target=run, args=j) for j in jobs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            for d in devs[1:]:
+                if d is not None:
+                    d.close()
+            raise errors[0]
+        have += len(jobs)
+    return devs
+
+
+def multi_chunk(n: int, n_devs: int) -> int:
+    return int(lib().issl_multi_chunk(n, n_devs))
+
+
+def score_multi(devs, guides: np.ndarray, max_dist: int, threshold: float, method, mit: np.ndarray, cfd: np.ndarray,
+                chunk: int = 0):
+    """issl_score_multi: one call over several GPUs (dynamic chunks, one host thread per device).
+    Returns (stats summed over devices, guides scored per device)."""
+    handles = (C.c_void_p * len(devs))(*[d._h for d in devs])
+    st = _Stats()
+    per = np.zeros(len(devs), dtype=np.uint64)
+    _check(lib().issl_score_multi(handles, len(devs), guides.ctypes.data, guides.size, int(max_dist), float(threshold),
+                                  method_code(method), mit.ctypes.data if mit is not None else None,
+                                  cfd.ctypes.data if cfd is not None else None, int(chunk), C.byref(st), per.ctypes.data))
+    return {n: getattr(st, n) for n, _ in st._fields_}, per
+
+
+class HostBuffer:
+    """issl_host_alloc: pinned, portable host memory viewed as a numpy array."""
+
+    def __init__(self, n: int, dtype):
+        self.dtype = np.dtype(dtype)
+        self._p = C.c_void_p()
+        _check(lib().issl_host_alloc(n * self.dtype.itemsize, C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(n * self.dtype.itemsize, 1),))[:n * self.dtype.itemsize].view(self.dtype)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().issl_host_free(self._p)
+            self._p = C.c_void_p()
 
     def __del__(self):
         try:

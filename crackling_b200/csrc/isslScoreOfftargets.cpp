@@ -37,6 +37,28 @@ namespace {
 
 using issl_host::now_s;
 
+// Guide and score arrays.  From 65 536 guides on they live in pinned, portable host memory (issl_host_alloc) so that
+// every GPU copies straight out of / into them; small runs keep plain memory (pinning costs more than it saves).
+template <class T> struct HostArray {
+    T *p = nullptr;
+    size_t n = 0;
+    bool pinned = false;
+    explicit HostArray(size_t count, bool pin) : n(count)
+    {
+        void *q = nullptr;
+        if (pin && count && issl_host_alloc(count * sizeof(T), &q) == ISSL_OK) { p = static_cast<T *>(q); pinned = true; }
+        else p = static_cast<T *>(calloc(count ? count : 1, sizeof(T)));
+        if (pinned) memset(p, 0, count * sizeof(T));
+    }
+    ~HostArray() { if (pinned) issl_host_free(p); else free(p); }
+    HostArray(const HostArray &) = delete;
+    HostArray &operator=(const HostArray &) = delete;
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+};
+
 // Starts bin/isslScoreServer (next to this executable) detached from the caller's terminal and pipes.
 bool spawn_server(const char *sockPath)
 {
@@ -67,8 +89,8 @@ bool spawn_server(const char *sockPath)
 
 // Scores through the resident server.  Returns 0 on success, 1 when the server answered with an error
 // (message already on stderr), -1 when no server could be reached (the caller then scores in-process).
-int score_remote(const char *sockPath, const char *indexPath, const std::vector<uint64_t> &guides, int maxDist, double threshold,
-                 int method, std::vector<double> &mit, std::vector<double> &cfd, bool timing)
+int score_remote(const char *sockPath, const char *indexPath, const HostArray<uint64_t> &guides, int maxDist, double threshold,
+                 int method, HostArray<double> &mit, HostArray<double> &cfd, bool timing)
 {
     using namespace issl_wire;
     int fd = connect_to(sockPath);
@@ -160,16 +182,19 @@ int main(int argc, char **argv)
     }
     fclose(fp);
 
-    std::vector<uint64_t> querySignatures(queryCount);
+    // pinned memory needs a CUDA context; a score server client never creates one
+    const bool pin = queryCount >= 65536 && !(getenv("ISSL_SERVER") && *getenv("ISSL_SERVER")) && issl_device_count() > 0;
+    HostArray<uint64_t> querySignatures(queryCount, pin);
     if (issl_pack_guides(queryDataSet.data(), fileSize, info.seqLength, querySignatures.data()) != ISSL_OK) {
         fprintf(stderr, "%s\n", issl_last_error());
         return 1;
     }
-    std::vector<double> mit(queryCount, 0.0), cfd(queryCount, 0.0);
+    HostArray<double> mit(queryCount, pin), cfd(queryCount, pin);
     const double t1 = now_s();
 
     // index replicated per GPU, guides partitioned into contiguous ranges, no cross-GPU reduction
-    double tLoad = 0, tScore = 0;
+    double tLoad = 0, tFan = 0, tScore = 0;
+    size_t nGpus = 0;
     if (calcMit || calcCfd) {
         int remote = -1;
         const char *server = getenv("ISSL_SERVER");
@@ -182,53 +207,47 @@ int main(int argc, char **argv)
             const std::vector<int> devs = issl_host::pick_devices(queryCount);
             issl_host::DeviceSet set;
             std::string err;
-            const double a0 = now_s();
-            if (set.ensure(index, devs, issl_host::layout_from_env(), &err) != ISSL_OK) {
+            double sec[2] = {0, 0};
+            if (set.ensure(index, devs, issl_host::layout_from_env(), &err, sec) != ISSL_OK) {
                 fprintf(stderr, "%s\n", err.c_str());
                 return 1;
             }
             const double a1 = now_s();
+            nGpus = devs.size();
             if (set.score(devs, querySignatures.data(), queryCount, maxDist, threshold, method, mit.data(), cfd.data(), nullptr, &err, timing) != ISSL_OK) {
                 fprintf(stderr, "%s\n", err.c_str());
                 return 1;
             }
-            tLoad = a1 - a0; tScore = now_s() - a1;
+            tLoad = sec[0]; tFan = sec[1]; tScore = now_s() - a1;
         }
     }
     const double t2 = now_s();
 
-    // ref :514-527: "%s\t" then "%f\t" / "-1\t" then "%f\n" / "-1\n", in input order.  Lines are formatted in
-    // parallel chunks (glibc's %f is the slow part at millions of guides) and written sequentially.
+    // ref :514-527: "%s\t" then "%f\t" / "-1\t" then "%f\n" / "-1\n", in input order.  issl_format_lines formats with all
+    // cores (the digits of printf's %f); a million lines at a time bounds the buffer.
     {
-        const size_t L = info.seqLength;
-        const size_t chunkLines = 1 << 11;
-        const size_t nChunks = (queryCount + chunkLines - 1) / chunkLines;
-        std::vector<std::string> chunks(nChunks);
-#pragma omp parallel for schedule(dynamic, 1)
-        for (long c = 0; c < (long)nChunks; c++) {
-            std::string &o = chunks[c];
-            const size_t b = (size_t)c * chunkLines, e = std::min(queryCount, b + chunkLines);
-            o.reserve((e - b) * (L + 48));
-            char num[512];
-            std::vector<char> seq(L);
-            for (size_t i = b; i < e; i++) {
-                issl_unpack_guide(querySignatures[i], L, seq.data());
-                o.append(seq.data(), L);
-                o.push_back('\t');
-                if (calcMit) o.append(num, (size_t)snprintf(num, sizeof num, "%f\t", mit[i])); else o.append("-1\t");
-                if (calcCfd) o.append(num, (size_t)snprintf(num, sizeof num, "%f\n", cfd[i])); else o.append("-1\n");
+        const size_t L = info.seqLength, step = 1u << 20;
+        std::vector<char> text;
+        for (size_t b = 0; b < queryCount; b += step) {
+            const size_t n = std::min(step, queryCount - b);
+            text.resize(n * (L + 2 + 2 * 24));
+            size_t bytes = issl_format_lines(querySignatures.data() + b, mit.data() + b, cfd.data() + b, n, L, method, text.data(), text.size());
+            if (bytes > text.size()) {   // scores with very many digits
+                text.resize(bytes);
+                bytes = issl_format_lines(querySignatures.data() + b, mit.data() + b, cfd.data() + b, n, L, method, text.data(), text.size());
             }
-        }
-        for (const std::string &o : chunks)
-            if (!o.empty() && fwrite(o.data(), 1, o.size(), stdout) != o.size()) {
+            if (fwrite(text.data(), 1, bytes, stdout) != bytes) {
                 fprintf(stderr, "Failed to write results.\n");
                 return 1;
             }
+        }
         fflush(stdout);
     }
+    const double t3 = now_s();
     issl_index_close(index);
     if (timing)
-        fprintf(stderr, "[issl] parse+guides %.3f s, index to HBM %.3f s, scoring %.3f s, print %.3f s, total %.3f s\n",
-                t1 - t0, tLoad, tScore, now_s() - t2, now_s() - t0);
+        fprintf(stderr, "[issl] parse+guides %.3f s, index to HBM %.3f s, replicas on %zu more gpu(s) %.3f s, scoring %.3f s, print %.3f s, "
+                        "index close %.3f s, total %.3f s\n",
+                t1 - t0, tLoad, nGpus ? nGpus - 1 : 0, tFan, tScore, t3 - t2, now_s() - t3, now_s() - t0);
     return 0;
 }

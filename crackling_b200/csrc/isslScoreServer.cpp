@@ -117,6 +117,12 @@ int main(int argc, char **argv)
         const int fd = accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
         if (fd < 0) continue;
         lastActive = now_s();
+        {   // a stalled client must not block the (single-threaded) loop for ever
+            timeval tv{};
+            tv.tv_sec = 30;
+            setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+            setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
+        }
         Request req;
         Response rsp{};
         std::string msg;
@@ -124,11 +130,14 @@ int main(int argc, char **argv)
         if (req.op == kPing) { rsp.status = ISSL_OK; rsp.nDevices = (uint32_t)issl_device_count(); reply(fd, rsp, "", nullptr, nullptr); close(fd); continue; }
         if (req.op == kShutdown) { rsp.status = ISSL_OK; reply(fd, rsp, "", nullptr, nullptr); close(fd); stop = true; continue; }
         if (req.op == kDrop) { cache.clear(); rsp.status = ISSL_OK; reply(fd, rsp, "", nullptr, nullptr); close(fd); continue; }
-        if (req.op != kScore || req.pathLen == 0 || req.pathLen > 65536 || req.nDevices > (uint32_t)kMaxDevices) {
+        if (req.op != kScore || req.pathLen == 0 || req.pathLen > 65536 || req.nDevices > (uint32_t)kMaxDevices ||
+            req.nGuides > (1ull << 28)) {   // 2^28 guides = 2 GB of packed guides: far beyond a page of the pipeline (5 M)
             rsp.status = ISSL_ERR_ARG; reply(fd, rsp, "malformed request", nullptr, nullptr); close(fd); continue;
         }
         std::string path(req.pathLen, '\0');
-        std::vector<uint64_t> guides(req.nGuides);
+        std::vector<uint64_t> guides;
+        try { guides.resize(req.nGuides); }
+        catch (const std::exception &) { rsp.status = ISSL_ERR_NOMEM; reply(fd, rsp, "out of host memory for the guides", nullptr, nullptr); close(fd); continue; }
         if (!read_full(fd, path.data(), req.pathLen) || (req.nGuides && !read_full(fd, guides.data(), req.nGuides * 8))) { close(fd); continue; }
 
         struct stat st;
@@ -153,12 +162,25 @@ int main(int argc, char **argv)
             cache.push_front(std::move(fresh));
             res = cache.front().get();
         }
-        std::vector<int> use(req.devices, req.devices + req.nDevices);
+        std::vector<int> use;
+        for (uint32_t k = 0; k < req.nDevices; k++) {   // ordinals that exist, each once
+            bool drop = req.devices[k] < 0 || req.devices[k] >= issl_device_count();
+            for (int u : use) drop |= u == req.devices[k];
+            if (!drop) use.push_back(req.devices[k]);
+        }
         if (use.empty()) use = issl_host::pick_devices(req.nGuides);
         std::string err;
         int rc = res->devices.ensure(res->index, use, req.layout, &err);
+        // no room next to the other resident indexes: drop the least recently used ones and try again
+        while (rc == ISSL_ERR_NOMEM && cache.size() > 1) {
+            fprintf(stderr, "[issl-server] out of device memory, evicting %s\n", cache.back()->path.c_str());
+            cache.pop_back();
+            rc = res->devices.ensure(res->index, use, req.layout, &err);
+        }
         const double t1 = now_s();
-        std::vector<double> mit(req.nGuides, 0.0), cfd(req.nGuides, 0.0);
+        std::vector<double> mit, cfd;
+        try { mit.assign(req.nGuides, 0.0); cfd.assign(req.nGuides, 0.0); }
+        catch (const std::exception &) { rc = ISSL_ERR_NOMEM; err = "out of host memory for the score arrays"; }
         issl_stats stats{};
         if (rc == ISSL_OK)
             rc = res->devices.score(use, guides.data(), guides.size(), req.maxDist, req.threshold, req.method, mit.data(), cfd.data(), &stats, &err);

@@ -150,18 +150,18 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     if (d->pbits > 40) return issl_set_error(ISSL_ERR_UNSUPPORTED, "index too large: %llu list positions", (unsigned long long)P);
 
     const uint64_t N = f.offtargetsCount;
-    CKR(d->sig.ensure(N * 8));
-    CKR(d->occ.ensure(N * 4));
-    CKR(d->ids.ensure(P * 4));
+    CKR(d->sig.exact(N * 8));
+    CKR(d->occ.exact(N * 4));
+    CKR(d->ids.exact(P * 4));
     CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
     // TRIPLE keeps slice lists too (maxDist beyond what the sub-bucket scan serves, .issl export): RES32 for sliceWidth 8,
     // ids only (GATHER) for sliceWidth 4
     const bool res32 = layout == ISSL_LAYOUT_RES32 || (layout == ISSL_LAYOUT_TRIPLE && f.sliceWidth == 8);
-    if (res32) { CKR(d->res32.ensure(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
-    if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.ensure(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
-    CKR(d->listStart.ensure(d->nLists * 8));
-    CKR(d->listLen.ensure(d->nLists * 8));
-    CKR(d->filePrefix.ensure((d->nLists + 1) * 8));
+    if (res32) { CKR(d->res32.exact(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
+    if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.exact(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
+    CKR(d->listStart.exact(d->nLists * 8));
+    CKR(d->listLen.exact(d->nLists * 8));
+    CKR(d->filePrefix.exact((d->nLists + 1) * 8));
     CK(cudaMemcpyAsync(d->listStart.p, d->hListStart.data(), d->nLists * 8, cudaMemcpyHostToDevice, d->stream));
     CK(cudaMemcpyAsync(d->listLen.p, d->hListLen.data(), d->nLists * 8, cudaMemcpyHostToDevice, d->stream));
     CK(cudaMemcpyAsync(d->filePrefix.p, d->hFilePrefix.data(), (d->nLists + 1) * 8, cudaMemcpyHostToDevice, d->stream));
@@ -189,8 +189,8 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
 static int upload_mit_table(issl_device *d)
 {
     d->mitCount = (uint32_t)d->hMitMasks.size();
-    CKR(d->mitMasks.ensure(std::max<size_t>(1, d->mitCount) * 8));
-    CKR(d->mitScores.ensure(std::max<size_t>(1, d->mitCount) * 8));
+    CKR(d->mitMasks.exact(std::max<size_t>(1, d->mitCount) * 8));
+    CKR(d->mitScores.exact(std::max<size_t>(1, d->mitCount) * 8));
     if (d->mitCount) {
         CK(cudaMemcpyAsync(d->mitMasks.p, d->hMitMasks.data(), d->mitCount * 8ull, cudaMemcpyHostToDevice, d->stream));
         CK(cudaMemcpyAsync(d->mitScores.p, d->hMitScores.data(), d->mitCount * 8ull, cudaMemcpyHostToDevice, d->stream));
@@ -206,7 +206,7 @@ static int upload_mit_table(issl_device *d)
             for (int p = 0; p < 20; p++) idx |= (uint32_t)((mk >> (2 * p)) & 1ull) << p;
             dense[idx] = d->hMitScores[k];
         }
-        CKR(d->mitDense.ensure(dense.size() * 8));
+        CKR(d->mitDense.exact(dense.size() * 8));
         CK(cudaMemcpyAsync(d->mitDense.p, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice, d->stream));
         CK(cudaStreamSynchronize(d->stream));   // dense is a local
         d->hbmBytes += dense.size() * 8;
@@ -229,6 +229,8 @@ static ScoreTables score_tables(const issl_device *d)
 static int build_triple(issl_device *d)
 {
     if (d->layout != ISSL_LAYOUT_TRIPLE) return ISSL_OK;
+    if (getenv("ISSL_TEST_TRIPLE_NOMEM"))   // test hook: behave as if the copies did not fit
+        return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc: out of memory (simulated by ISSL_TEST_TRIPLE_NOMEM)");
     cudaStream_t st = d->stream;
     const uint64_t N = d->info.offtargetsCount;
     const uint64_t stride = (N + 64 + 7) / 8 * 8;
@@ -253,12 +255,12 @@ static int build_triple(issl_device *d)
     // of the path indexes with 2^31 sites or more take)
     bool occFlag = N < (1ull << 31);
     if (const char *e = getenv("ISSL_TRIPLE_OCCFLAG")) occFlag = occFlag && atoi(e) != 0;
-    CKR(d->tripleRes.ensure(kTripleCount * stride * 2));
-    CKR(d->tripleIds.ensure(kTripleCount * stride * 4));
-    CKR(d->tripleOffs.ensure(kTripleCount * (kTripleBuckets + 1ull) * 4));
+    CKR(d->tripleRes.exact(kTripleCount * stride * 2));
+    CKR(d->tripleIds.exact(kTripleCount * stride * 4));
+    CKR(d->tripleOffs.exact(kTripleCount * (kTripleBuckets + 1ull) * 4));
     CK(cudaMemsetAsync(d->tripleRes.p, 0, kTripleCount * stride * 2, st));
     if (pitch) {
-        CKR(d->tripleBlk.ensure(needBlk));   // every sub-block is written by k_triple_blocks
+        CKR(d->tripleBlk.exact(needBlk));   // every sub-block is written by k_triple_blocks
     }
     DBuf keysIn, keysOut, idsIn, tmp;
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
@@ -292,6 +294,20 @@ static int build_triple(issl_device *d)
     d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = pitch;
     d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
+    return ISSL_OK;
+}
+
+// ISSL_LAYOUT_AUTO promised TRIPLE only "when it fits": when the ten copies cannot be allocated (a second human-scale
+// index next to a resident one, a smaller GPU), the index stays usable through its slice lists.
+static int build_triple_or_fall_back(issl_device *d)
+{
+    const int rc = build_triple(d);
+    if (rc != ISSL_ERR_NOMEM || !d->layoutAuto || d->layout != ISSL_LAYOUT_TRIPLE) return rc;
+    cudaGetLastError();
+    for (DBuf *b : {&d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk}) b->release();
+    d->tv = TripleView{};
+    d->layout = d->iv.layout;   // RES32 (sliceWidth 8) or the ids-only lists (sliceWidth 4)
+    if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] the sub-bucket copies do not fit this GPU's free memory: scanning the slice lists instead\n");
     return ISSL_OK;
 }
 
@@ -434,7 +450,7 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
         return fail(issl_set_error(ISSL_ERR_UNSUPPORTED,
                                    "Error reading index: %llu list entries violate the isslCreateIndex invariants "
                                    "(id range, list membership, ascending ids or occurrence counts)", bad));
-    if ((rc = build_triple(d)) != ISSL_OK) return fail(rc);
+    if ((rc = build_triple_or_fall_back(d)) != ISSL_OK) return fail(rc);
     *out = d;
     return ISSL_OK;
 }
@@ -558,7 +574,7 @@ static int collapse_and_build(issl_device *d, int layout, const uint64_t *dKeys,
         CK(cudaStreamSynchronize(st));   // vs[] is a stack buffer
     }
     for (DBuf *b : {&values, &valuesSorted, &idsTmp, &idsSorted, &hist, &valueStart, &tmp}) b->release();
-    return build_triple(d);
+    return build_triple_or_fall_back(d);
 }
 
 extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uint64_t uniform_sites,
@@ -612,8 +628,8 @@ int issl_internal_device_from_keys(int cuda_device, int layout, uint64_t *dKeys,
     issl_device *d = nullptr;
     CKR(new_device(cuda_device, &d));
     d->layoutAuto = (layout == ISSL_LAYOUT_AUTO);
-    DBuf alt;   // non-owning view
-    alt.p = dKeysAlt; alt.cap = nRaw * 8;
+    DBuf alt;
+    alt.view(dKeysAlt, nRaw * 8);   // the caller keeps ownership
     int rc = build_from_sites(d, lay, dKeys, nRaw, seqLength, sliceWidth, alt);
     if (rc == ISSL_OK) {
         cudaError_t e = cudaStreamSynchronize(d->stream);
@@ -693,6 +709,68 @@ extern "C" int issl_device_create_from_text(const char *text, size_t bytes, uint
     if (rc == ISSL_OK) cu(cudaStreamSynchronize(d->stream), "index build");
     cleanup();
     if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
+    *out = d;
+    return ISSL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a second copy of a resident index on another GPU, straight over NVLink: the index is replicated per GPU
+// (guides are independent, ref isslScoreOfftargets.cpp:316-317), and a peer copy of the finished layout
+// (~0.1 s for 87 GB) replaces another upload of the file from the host plus another build of the ten copies
+// ---------------------------------------------------------------------------------------------
+namespace {
+// the buffers that make up a resident index, in a fixed order
+std::vector<DBuf *> index_buffers(issl_device *d)
+{
+    return {&d->sig, &d->occ, &d->ids, &d->res32, &d->sig64, &d->listStart, &d->listLen, &d->filePrefix, &d->mitMasks,
+            &d->mitScores, &d->mitDense, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk};
+}
+template <class T> const T *rebase(const T *p, const DBuf &from, const DBuf &to)
+{
+    return p ? reinterpret_cast<const T *>(static_cast<const uint8_t *>(to.p) + (reinterpret_cast<const uint8_t *>(p) - static_cast<const uint8_t *>(from.p)))
+             : nullptr;
+}
+}  // namespace
+
+extern "C" int issl_device_clone(const issl_device *src_, int cuda_device, issl_device **out)
+{
+    if (!src_ || !out) return issl_set_error(ISSL_ERR_ARG, "issl_device_clone: null argument");
+    *out = nullptr;
+    issl_device *src = const_cast<issl_device *>(src_);   // buffers are only read
+    if (cuda_device == src->dev) return issl_set_error(ISSL_ERR_ARG, "issl_device_clone: device %d already holds this index", cuda_device);
+    issl_device *d = nullptr;
+    CKR(new_device(cuda_device, &d));
+    auto fail = [&](int rc) { issl_device_destroy(d); return rc; };
+    // direct peer copies need peer access from the copying side; without it the driver stages through the host
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, cuda_device, src->dev) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(src->dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        cudaGetLastError();
+    }
+    d->info = src->info; d->layout = src->layout; d->nLists = src->nLists; d->hbmBytes = src->hbmBytes; d->pbits = src->pbits;
+    d->mitCount = src->mitCount; d->hMitMasks = src->hMitMasks; d->hMitScores = src->hMitScores;
+    d->hListLen = src->hListLen; d->hListStart = src->hListStart; d->hFilePrefix = src->hFilePrefix;
+    d->layoutAuto = src->layoutAuto; d->tripleMaxDist = src->tripleMaxDist;
+    const std::vector<DBuf *> from = index_buffers(src), to = index_buffers(d);
+    for (size_t k = 0; k < from.size(); k++) {
+        if (!from[k]->p) continue;
+        int rc = to[k]->exact(from[k]->used);
+        if (rc != ISSL_OK) return fail(rc);
+        const cudaError_t e = cudaMemcpyPeerAsync(to[k]->p, cuda_device, from[k]->p, src->dev, from[k]->used, d->stream);
+        if (e != cudaSuccess) return fail(issl_set_error(ISSL_ERR_CUDA, "peer copy %d -> %d: %s", src->dev, cuda_device, cudaGetErrorString(e)));
+    }
+    d->iv = src->iv;
+    d->iv.sig = rebase(src->iv.sig, src->sig, d->sig); d->iv.occ = rebase(src->iv.occ, src->occ, d->occ);
+    d->iv.ids = rebase(src->iv.ids, src->ids, d->ids); d->iv.res32 = rebase(src->iv.res32, src->res32, d->res32);
+    d->iv.sig64 = rebase(src->iv.sig64, src->sig64, d->sig64);
+    d->iv.listStart = rebase(src->iv.listStart, src->listStart, d->listStart);
+    d->iv.listLen = rebase(src->iv.listLen, src->listLen, d->listLen);
+    d->tv = src->tv;
+    d->tv.res = rebase(src->tv.res, src->tripleRes, d->tripleRes); d->tv.ids = rebase(src->tv.ids, src->tripleIds, d->tripleIds);
+    d->tv.offs = rebase(src->tv.offs, src->tripleOffs, d->tripleOffs); d->tv.blk = rebase(src->tv.blk, src->tripleBlk, d->tripleBlk);
+    const cudaError_t e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) return fail(issl_set_error(ISSL_ERR_CUDA, "peer copy %d -> %d: %s", src->dev, cuda_device, cudaGetErrorString(e)));
     *out = d;
     return ISSL_OK;
 }
@@ -943,7 +1021,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             d->stats.hits += d->hCounters[6];
         }
         if (inScan) {   // the scan kernel wrote every guide's state of after this wave
-            std::swap(d->totMit, d->totMit2); std::swap(d->totCfd, d->totCfd2); std::swap(d->done, d->done2);
+            d->totMit.swap(d->totMit2); d->totCfd.swap(d->totCfd2); d->done.swap(d->done2);
             d->stats.hits += d->hCounters[7];
         }
     } else {
@@ -1046,6 +1124,8 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     const bool calcMit = method == ISSL_METHOD_MIT || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
     const bool calcCfd = method == ISSL_METHOD_CFD || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
     if (!calcMit && !calcCfd) return ISSL_OK;   // unknown method: nothing is scored, both columns print as -1
+    if (const char *e = getenv("ISSL_TEST_NOMEM_ABOVE"))   // test hook: batches above this size "run out of memory"
+        if (n > (uint32_t)atol(e)) return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc: out of memory (simulated by ISSL_TEST_NOMEM_ABOVE)");
 
     const double maximumSum = (10000.0 - threshold * 100) / threshold;   // ref :326
     const bool checkExit = !(std::isnan(maximumSum) || (std::isinf(maximumSum) && maximumSum > 0));
@@ -1193,8 +1273,20 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     if ((calcMit && !mitOut) || (calcCfd && !cfdOut))
         return issl_set_error(ISSL_ERR_ARG, "issl_score: output array missing for a column the method computes");
 
-    for (size_t b0 = 0; b0 < n; b0 += d->maxBatch) {
-        const uint32_t nb = (uint32_t)std::min<size_t>(d->maxBatch, n - b0);
+    // A batch's scratch grows with its hits (general pipeline: two key buffers and two contribution arrays, 32 B per
+    // hit): at maxDist 5-6, or on repeat-rich genomes, 2^20 guides can ask for more than is left beside the index.  The
+    // batch is bounded by what the previous call saw, and a batch that still runs out of memory is halved and repeated.
+    uint32_t batch = d->maxBatch;
+    if (d->lastHitsPerGuide > 512.0) {
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            const double held = (double)d->keysA.cap + (double)d->keysB.cap + (double)d->contribMit.cap + (double)d->contribCfd.cap;
+            const double fit = 0.6 * ((double)freeB + held) / (40.0 * d->lastHitsPerGuide);
+            if (fit < (double)batch) batch = (uint32_t)std::max(4096.0, fit);
+        }
+    }
+    for (size_t b0 = 0; b0 < n;) {
+        const uint32_t nb = (uint32_t)std::min<size_t>(batch, n - b0);
         const uint64_t *dG = guides + b0;
         if (!guidesOnDevice) {
             CKR(d->guides.ensure(nb * 8ull));
@@ -1206,12 +1298,28 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
             CKR(d->outMit.ensure(nb * 8ull)); CKR(d->outCfd.ensure(nb * 8ull));
             dM = d->outMit.as<double>(); dC = d->outCfd.as<double>();
         }
-        CKR(score_batch(d, st, dG, nb, b0, maxDist, threshold, method, dM, dC, sink, timer));
+        const issl_stats before = d->stats;
+        const size_t hitsBefore = sink ? sink->guide.size() : 0;
+        const int rc = score_batch(d, st, dG, nb, b0, maxDist, threshold, method, dM, dC, sink, timer);
+        if (rc == ISSL_ERR_NOMEM && nb > 1024) {
+            cudaGetLastError();
+            cudaStreamSynchronize(st);
+            for (DBuf *b : {&d->keysA, &d->keysB, &d->contribMit, &d->contribCfd, &d->sortTemp, &d->segKeys, &d->segSites, &d->hitId, &d->hitDist, &d->hitOcc})
+                b->release();
+            d->hitCap = d->hitCapAuto = 0; d->segCap = 0;
+            d->stats = before;
+            if (sink) { sink->guide.resize(hitsBefore); sink->id.resize(hitsBefore); sink->dist.resize(hitsBefore); sink->occ.resize(hitsBefore); }
+            batch = std::max<uint32_t>(1024, nb / 2);
+            if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] batch of %u guides ran out of device memory: retrying with %u\n", nb, batch);
+            continue;
+        }
+        CKR(rc);
         if (!outOnDevice) {
             if (calcMit) CK(cudaMemcpyAsync(mitOut + b0, dM, nb * 8ull, cudaMemcpyDeviceToHost, st));
             if (calcCfd) CK(cudaMemcpyAsync(cfdOut + b0, dC, nb * 8ull, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
         }
+        b0 += nb;
     }
     CK(cudaEventRecord(t1, st));
     CK(cudaStreamSynchronize(st));
@@ -1294,6 +1402,26 @@ extern "C" int issl_guide_filters(issl_device *d, const char *text, size_t bytes
     if (rc != ISSL_OK) return rc;
     if (e != cudaSuccess) return issl_set_error(ISSL_ERR_CUDA, "issl_guide_filters: %s", cudaGetErrorString(e));
     return ISSL_OK;
+}
+
+// pinned host memory every device can copy from / into directly (cudaHostAllocPortable): what a host program should
+// hold its guide and score arrays in when it drives several GPUs (pageable memory is staged by the driver)
+extern "C" int issl_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return issl_set_error(ISSL_ERR_ARG, "issl_host_alloc: null argument");
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return issl_set_error(e == cudaErrorMemoryAllocation ? ISSL_ERR_NOMEM : ISSL_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return ISSL_OK;
+}
+
+extern "C" void issl_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int issl_last_stats(const issl_device *d, issl_stats *out)

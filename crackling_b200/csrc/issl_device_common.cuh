@@ -25,26 +25,48 @@
 
 namespace issl {
 
-// growable device buffer
+// growable device buffer; owns its allocation (freed on destruction) unless made a view()
 struct DBuf {
     void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
+    size_t cap = 0;       // bytes allocated
+    size_t used = 0;      // bytes last asked for
+    bool owner = true;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { release(); }
+    // scratch: over-allocates by a quarter so that slowly growing batches do not reallocate every call
+    int ensure(size_t bytes) { return grow(bytes, bytes + bytes / 4 + 256); }
+    // index storage: exactly what is asked for (a quarter of slack on an 87 GB index is 22 GB of HBM)
+    int exact(size_t bytes) { return grow(bytes, bytes); }
+    // a non-owning window onto memory the caller keeps
+    void view(void *ptr, size_t bytes) { release(); p = ptr; cap = used = bytes; owner = false; }
+    void release()
     {
+        if (p && owner) cudaFree(p);
+        p = nullptr; cap = used = 0; owner = true;
+    }
+    void swap(DBuf &o) { std::swap(p, o.p); std::swap(cap, o.cap); std::swap(used, o.used); std::swap(owner, o.owner); }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+
+private:
+    int grow(size_t bytes, size_t want)
+    {
+        used = bytes;
         if (bytes <= cap) return ISSL_OK;
+        if (!owner) return issl_set_error(ISSL_ERR_NOMEM, "buffer view too small (%zu > %zu bytes)", bytes, cap);
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        const size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && want != bytes) { cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
         if (e != cudaSuccess) {
-            e = cudaMalloc(&p, bytes);
-            if (e != cudaSuccess) { p = nullptr; return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
-            cap = bytes;
-        } else cap = want;
+            cudaGetLastError();
+            p = nullptr; used = 0;
+            return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        }
+        cap = want;
         return ISSL_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }

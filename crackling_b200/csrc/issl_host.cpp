@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
@@ -182,6 +184,52 @@ extern "C" int issl_pack_guides(const char *text, size_t bytes, size_t seqLength
 extern "C" void issl_unpack_guide(uint64_t signature, size_t seqLength, char *out)
 {
     for (size_t j = 0; j < seqLength; j++) out[j] = "ACGT"[(signature >> (2 * j)) & 3];
+}
+
+// "%f" of a double: std::to_chars in fixed notation with six decimals is correctly rounded, as glibc's printf is, so the
+// digits are the same (tests/test_lib_cpu.py compares them); it is several times faster.  Non-finite values keep printf.
+static inline char *put_f(char *p, double v)
+{
+    if (!std::isfinite(v)) return p + sprintf(p, "%f", v);
+    return std::to_chars(p, p + 400, v, std::chars_format::fixed, 6).ptr;
+}
+
+// ref isslScoreOfftargets.cpp:514-527: "%s\t" then "%f\t" or "-1\t" then "%f\n" or "-1\n", in input order
+extern "C" size_t issl_format_lines(const uint64_t *guides, const double *mit, const double *cfd, size_t n, size_t seqLength,
+                                    int method, char *out, size_t cap)
+{
+    const bool calcMit = method == ISSL_METHOD_MIT || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
+    const bool calcCfd = method == ISSL_METHOD_CFD || method == ISSL_METHOD_AND || method == ISSL_METHOD_OR || method == ISSL_METHOD_AVG;
+    if (n == 0) return 0;
+    if (!guides || (calcMit && !mit) || (calcCfd && !cfd)) { issl_set_error(ISSL_ERR_ARG, "issl_format_lines: null argument"); return 0; }
+    // pass 1: every chunk of lines into its own buffer, in parallel; pass 2: lengths -> offsets -> out
+    const size_t chunkLines = 4096, nChunks = (n + chunkLines - 1) / chunkLines;
+    std::vector<std::string> chunks(nChunks);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long c = 0; c < (long)nChunks; c++) {
+        const size_t b = (size_t)c * chunkLines, e = std::min(n, b + chunkLines);
+        std::string &o = chunks[(size_t)c];
+        o.reserve((e - b) * (seqLength + 28));
+        char line[32 + 2 + 2 * 400];
+        for (size_t i = b; i < e; i++) {
+            char *p = line;
+            issl_unpack_guide(guides[i], seqLength, p);
+            p += seqLength;
+            *p++ = '\t';
+            if (calcMit) p = put_f(p, mit[i]); else { *p++ = '-'; *p++ = '1'; }
+            *p++ = '\t';
+            if (calcCfd) p = put_f(p, cfd[i]); else { *p++ = '-'; *p++ = '1'; }
+            *p++ = '\n';
+            o.append(line, (size_t)(p - line));
+        }
+    }
+    std::vector<size_t> off(nChunks + 1, 0);
+    for (size_t c = 0; c < nChunks; c++) off[c + 1] = off[c] + chunks[c].size();
+    if (out && off[nChunks] <= cap) {
+#pragma omp parallel for schedule(static)
+        for (long c = 0; c < (long)nChunks; c++) memcpy(out + off[(size_t)c], chunks[(size_t)c].data(), chunks[(size_t)c].size());
+    }
+    return off[nChunks];
 }
 
 extern "C" int issl_method_from_string(const char *name)

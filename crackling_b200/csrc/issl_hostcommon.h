@@ -5,6 +5,7 @@
 #ifndef ISSL_HOSTCOMMON_H
 #define ISSL_HOSTCOMMON_H
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -37,12 +38,19 @@ inline std::vector<int> devices_from_env()
     return devs;
 }
 
-// ISSL_DEVICES wins; else min(ISSL_GPUS, present); else at most one GPU per 65536 guides.
+// ISSL_DEVICES wins; else min(ISSL_GPUS, present); else at most one GPU per 65536 guides.  Ordinals outside the
+// machine and repeated ordinals are dropped (two host threads must never drive one handle).
 inline std::vector<int> pick_devices(size_t nGuides)
 {
-    std::vector<int> devs = devices_from_env();
+    const int present = issl_device_count();
+    std::vector<int> devs;
+    for (int d : devices_from_env()) {
+        bool seen = d < 0 || d >= (present > 0 ? present : 1);
+        for (int e : devs) seen |= e == d;
+        if (!seen) devs.push_back(d);
+    }
     if (!devs.empty()) return devs;
-    int want = issl_device_count();
+    int want = present;
     if (const char *e = getenv("ISSL_GPUS")) {
         const int v = atoi(e);
         if (v > 0 && v < want) want = v;
@@ -85,63 +93,97 @@ public:
         return false;
     }
 
-    // Makes the index resident on every device of `devs` that does not hold it yet (in parallel).
-    // Returns ISSL_OK or the first error (message in *err).
-    int ensure(const issl_index *index, const std::vector<int> &devs, int layout, std::string *err)
+    // Makes the index resident on every device of `devs` that does not hold it yet: the file goes to ONE GPU
+    // (issl_device_create: upload, validation, layout), every further GPU receives a peer copy of the finished layout
+    // over NVLink (issl_device_clone), fanned out as a tree -- every replica made in one round is a source in the next.
+    // ISSL_FANOUT=0: every GPU loads the file itself, in parallel (the round-1 behaviour, kept for comparison).
+    // Returns ISSL_OK or the first error (message in *err).  seconds[0] / seconds[1] (optional): first load / fan-out.
+    int ensure(const issl_index *index, const std::vector<int> &devs, int layout, std::string *err, double *seconds = nullptr)
     {
         std::vector<int> missing;
-        for (int d : devs) if (!has(d)) missing.push_back(d);
-        if (missing.empty()) return ISSL_OK;
-        std::vector<issl_device *> made(missing.size(), nullptr);
-        std::vector<int> rcs(missing.size(), ISSL_OK);
-        std::vector<std::string> errors(missing.size());
-        auto worker = [&](size_t k) {
-            rcs[k] = issl_device_create(index, missing[k], layout, &made[k]);
-            if (rcs[k] != ISSL_OK) errors[k] = issl_last_error();
-        };
-        run_parallel(missing.size(), worker);
-        int rc = ISSL_OK;
-        for (size_t k = 0; k < missing.size(); k++) {
-            if (rcs[k] == ISSL_OK) { devs_.push_back(missing[k]); handles_.push_back(made[k]); }
-            else if (rc == ISSL_OK) { rc = rcs[k]; if (err) *err = errors[k]; }
+        for (int d : devs) {
+            bool dup = has(d);
+            for (int m : missing) dup |= m == d;
+            if (!dup) missing.push_back(d);
         }
-        return rc;
+        if (seconds) seconds[0] = seconds[1] = 0;
+        if (missing.empty()) return ISSL_OK;
+        const bool fanout = !(getenv("ISSL_FANOUT") && atoi(getenv("ISSL_FANOUT")) == 0);
+        const double t0 = now_s();
+        if (handles_.empty() || !fanout) {
+            // from the file: one device when replicas follow, all of them otherwise
+            const size_t n = fanout ? 1 : missing.size();
+            std::vector<issl_device *> made(n, nullptr);
+            std::vector<int> rcs(n, ISSL_OK);
+            std::vector<std::string> errors(n);
+            auto worker = [&](size_t k) {
+                rcs[k] = issl_device_create(index, missing[k], layout, &made[k]);
+                if (rcs[k] != ISSL_OK) errors[k] = issl_last_error();
+            };
+            run_parallel(n, worker);
+            int rc = ISSL_OK;
+            for (size_t k = 0; k < n; k++) {
+                if (rcs[k] == ISSL_OK) { devs_.push_back(missing[k]); handles_.push_back(made[k]); }
+                else if (rc == ISSL_OK) { rc = rcs[k]; if (err) *err = errors[k]; }
+            }
+            if (rc != ISSL_OK) return rc;
+            missing.erase(missing.begin(), missing.begin() + (long)n);
+        }
+        const double t1 = now_s();
+        if (seconds) seconds[0] = t1 - t0;
+        while (!missing.empty()) {
+            const size_t n = std::min(missing.size(), handles_.size());
+            std::vector<issl_device *> made(n, nullptr);
+            std::vector<int> rcs(n, ISSL_OK);
+            std::vector<std::string> errors(n);
+            auto worker = [&](size_t k) {
+                rcs[k] = issl_device_clone(handles_[k], missing[k], &made[k]);
+                if (rcs[k] != ISSL_OK) {   // no peer path, or no room for a copy made that way: load the file instead
+                    rcs[k] = issl_device_create(index, missing[k], layout, &made[k]);
+                    if (rcs[k] != ISSL_OK) errors[k] = issl_last_error();
+                }
+            };
+            run_parallel(n, worker);
+            int rc = ISSL_OK;
+            for (size_t k = 0; k < n; k++) {
+                if (rcs[k] == ISSL_OK) { devs_.push_back(missing[k]); handles_.push_back(made[k]); }
+                else if (rc == ISSL_OK) { rc = rcs[k]; if (err) *err = errors[k]; }
+            }
+            if (rc != ISSL_OK) return rc;
+            missing.erase(missing.begin(), missing.begin() + (long)n);
+        }
+        if (seconds) seconds[1] = now_s() - t1;
+        return ISSL_OK;
     }
 
-    // Scores guides[0..n) on the devices of `use` (all of which must be resident): contiguous partitions,
-    // disjoint output ranges.  stats (optional) receives the sums over devices.
+    // Scores guides[0..n) on the devices of `use` (all of which must be resident) through issl_score_multi: chunks of
+    // guides handed out dynamically, one host thread per device, disjoint output ranges.  stats (optional) receives the
+    // sums over devices.
     int score(const std::vector<int> &use, const uint64_t *guides, size_t n, int maxDist, double threshold, int method,
               double *mit, double *cfd, issl_stats *stats, std::string *err, bool verbose = false)
     {
-        const size_t nd = use.size();
-        std::vector<int> rcs(nd, ISSL_OK);
-        std::vector<std::string> errors(nd);
-        std::vector<issl_stats> st(nd);
-        auto worker = [&](size_t k) {
-            issl_device *dev = handle_of(use[k]);
-            const size_t b = n * k / nd, e = n * (k + 1) / nd;
-            if (!dev) { rcs[k] = ISSL_ERR_ARG; errors[k] = "index is not resident on the requested device"; return; }
-            rcs[k] = issl_score(dev, guides + b, e - b, maxDist, threshold, method, mit ? mit + b : nullptr, cfd ? cfd + b : nullptr);
-            if (rcs[k] != ISSL_OK) { errors[k] = issl_last_error(); return; }
-            issl_last_stats(dev, &st[k]);
-            if (verbose)
-                fprintf(stderr, "[issl] gpu %d: guides %zu candidates %llu hits %llu early-exits %llu scan %.3f ms device-total %.3f ms\n",
-                        use[k], e - b, (unsigned long long)st[k].candidates, (unsigned long long)st[k].hits,
-                        (unsigned long long)st[k].early_exits, st[k].scan_ms, st[k].total_ms);
-        };
-        run_parallel(nd, worker);
-        if (stats) {
-            memset(stats, 0, sizeof *stats);
-            for (size_t k = 0; k < nd; k++) {
-                stats->guides += st[k].guides; stats->candidates += st[k].candidates; stats->hits += st[k].hits;
-                stats->early_exits += st[k].early_exits; stats->launches += st[k].launches; stats->scan_launches += st[k].scan_launches;
-                stats->streamed += st[k].streamed;
-                if (st[k].scan_ms > stats->scan_ms) stats->scan_ms = st[k].scan_ms;
-                if (st[k].total_ms > stats->total_ms) stats->total_ms = st[k].total_ms;
-            }
+        std::vector<issl_device *> hs;
+        for (int d : use) {
+            issl_device *h = handle_of(d);
+            if (!h) { if (err) *err = "index is not resident on the requested device"; return ISSL_ERR_ARG; }
+            bool dup = false;
+            for (issl_device *o : hs) dup |= o == h;
+            if (!dup) hs.push_back(h);
         }
-        for (size_t k = 0; k < nd; k++)
-            if (rcs[k] != ISSL_OK) { if (err) *err = errors[k]; return rcs[k]; }
+        issl_stats st;
+        std::vector<uint64_t> per(hs.size(), 0);
+        size_t chunk = 0;
+        if (const char *e = getenv("ISSL_CHUNK")) { const long long v = atoll(e); if (v > 0) chunk = (size_t)v; }
+        const int rc = issl_score_multi(hs.data(), hs.size(), guides, n, maxDist, threshold, method, mit, cfd, chunk, &st, per.data());
+        if (rc != ISSL_OK) { if (err) *err = issl_last_error(); return rc; }
+        if (verbose) {
+            fprintf(stderr, "[issl] %zu gpu(s), chunks of %zu guides: candidates %llu hits %llu early-exits %llu scan %.3f ms device-total %.3f ms (busiest gpu); guides per gpu:",
+                    hs.size(), chunk ? chunk : issl_multi_chunk(n, hs.size()), (unsigned long long)st.candidates, (unsigned long long)st.hits,
+                    (unsigned long long)st.early_exits, st.scan_ms, st.total_ms);
+            for (uint64_t g : per) fprintf(stderr, " %llu", (unsigned long long)g);
+            fprintf(stderr, "\n");
+        }
+        if (stats) *stats = st;
         return ISSL_OK;
     }
 

@@ -255,8 +255,7 @@ int grow_keys(issl_sites *s, uint64_t need)
     CKR(bigger.ensure(std::max<uint64_t>(need, s->n + s->n / 2) * 8));
     if (s->n) CK(cudaMemcpyAsync(bigger.p, s->keys.p, s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    s->keys.release();
-    s->keys = bigger;
+    s->keys.swap(bigger);   // the old allocation leaves with `bigger`
     return ISSL_OK;
 }
 
@@ -393,7 +392,7 @@ static int sort_sites(issl_sites *s)
     CK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, s->n, 0, 2 * kSiteLen, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     tmp.release();
-    if (db.Current() != s->keys.as<uint64_t>()) std::swap(s->keys, s->keysAlt);
+    if (db.Current() != s->keys.as<uint64_t>()) s->keys.swap(s->keysAlt);
     s->sorted = true;
     return ISSL_OK;
 }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ISSL_CUDA_ABI_VERSION 2
+#define ISSL_CUDA_ABI_VERSION 3
 
 typedef enum issl_status {
     ISSL_OK = 0,
@@ -134,6 +134,14 @@ void issl_unpack_guide(uint64_t signature, size_t seqLength, char *out);
 /* ref :121-143 */
 int issl_method_from_string(const char *name);
 
+/* The output lines of isslScoreOfftargets.cpp:514-527 for guides[0..n): the sequence re-decoded from the packed guide
+ * (:82-89, :515), a tab, "%f" of the MIT score or the literal -1 when the method does not compute it (:516-520), a tab,
+ * the same for CFD (:521-525), a newline.  Formatted by all host cores; the digits are those of printf("%f").
+ * Returns the number of bytes the lines take; they are written to out only when that fits cap (call with
+ * out = NULL to size the buffer: at most seqLength + 2 + 2 * 330 bytes per line). */
+size_t issl_format_lines(const uint64_t *guides, const double *mit, const double *cfd, size_t n, size_t seqLength,
+                         int method, char *out, size_t cap);
+
 /* ---- device side -------------------------------------------------------------------------- */
 
 /* Number of usable sm_100 devices (0 when there is none; never an error). */
@@ -196,6 +204,12 @@ int issl_sites_read_keys(issl_sites *sites, uint64_t first, uint64_t n, uint64_t
  * extractOfftargets followed by isslCreateIndex (seqLength 20) produces. */
 int issl_device_create_from_sites(issl_sites *sites, uint32_t sliceWidth, int layout, issl_device **out);
 
+/* A second copy of a resident index on another GPU, copied device to device over NVLink (no second pass over the
+ * file, no second build of the layout).  The reference shares one in-memory index between its OpenMP threads
+ * (isslScoreOfftargets.cpp:308-317); across GPUs the index is replicated instead, and this is how a replica is
+ * made.  The source handle is only read and may be scoring meanwhile. */
+int issl_device_clone(const issl_device *src, int cuda_device, issl_device **out);
+
 int issl_device_get_info(const issl_device *dev, issl_device_info *out);
 void issl_device_destroy(issl_device *dev);
 
@@ -233,6 +247,23 @@ int issl_score_hits(issl_device *dev, const uint64_t *guides, size_t n, int maxD
                     size_t cap, size_t *count);
 
 int issl_last_stats(const issl_device *dev, issl_stats *out);
+
+/* One call, several GPUs (one process): replaces the `#pragma omp for` over guides of isslScoreOfftargets.cpp:308-317
+ * across devices.  devs[0..n_devs) hold replicas of the same index (issl_device_create / issl_device_clone), one per
+ * GPU.  The guides are cut into chunks of `chunk` guides (0 = issl_multi_chunk(n, n_devs)) that the devices take from a
+ * shared counter, one host thread per device -- dynamic, because the early exit makes a guide's cost uneven; every chunk
+ * writes its own range of mit_out / cfd_out, so results are in input order and there is no cross-GPU reduction.
+ * Host buffers as for issl_score (pinned memory from issl_host_alloc avoids the driver's staging copies).
+ * stats_out (optional): counters summed over devices, times of the busiest device; guides_per_device (optional,
+ * n_devs entries): how many guides each device ended up scoring. */
+int issl_score_multi(issl_device *const *devs, size_t n_devs, const uint64_t *guides, size_t n, int maxDist,
+                     double threshold, int method, double *mit_out, double *cfd_out, size_t chunk,
+                     issl_stats *stats_out, uint64_t *guides_per_device);
+size_t issl_multi_chunk(size_t n, size_t n_devs);
+
+/* Pinned, portable host memory (cudaHostAlloc) for guide and score arrays shared by several devices. */
+int issl_host_alloc(size_t bytes, void **out);
+void issl_host_free(void *p);
 
 /* ---- guide-side pre-filters of the pipeline (the step before the scorer) ------------------- */
 

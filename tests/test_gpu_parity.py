@@ -102,21 +102,106 @@ def test_host_program_stdout_byte_identical(name, tmp_path):
 
 
 def test_host_program_on_several_gpus(tmp_path):
-    """Index replicated per GPU, guides split into contiguous ranges, output in input order."""
+    """Index on one GPU from the file, replicas by peer copy, guides handed out in chunks, output in input order."""
     n = cb.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     case = golden_case("w8_families")
     (tmp_path / "i.issl").write_bytes(case.issl)
     (tmp_path / "g.txt").write_bytes(case.guides)
-    for run in case.expected["runs"][::17]:
-        env = dict(os.environ, ISSL_GPUS=str(n), ISSL_TIMING="1")
-        p = subprocess.run([str(cb.cli_path()), str(tmp_path / "i.issl"), str(tmp_path / "g.txt"), str(run["maxDist"]),
-                            str(run["threshold"]), run["method"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
-        assert p.returncode == 0, p.stderr
-        assert p.stdout.decode() == run["stdout"]
-        if run["method"] != "bogus":
-            assert p.stderr.decode().count("[issl] gpu ") == n
+    for fanout in ("1", "0"):
+        for run in case.expected["runs"][::17]:
+            env = dict(os.environ, ISSL_GPUS=str(n), ISSL_TIMING="1", ISSL_CHUNK="7", ISSL_FANOUT=fanout)
+            p = subprocess.run([str(cb.cli_path()), str(tmp_path / "i.issl"), str(tmp_path / "g.txt"), str(run["maxDist"]),
+                                str(run["threshold"]), run["method"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+            assert p.returncode == 0, p.stderr
+            assert p.stdout.decode() == run["stdout"]
+            if run["method"] != "bogus":
+                assert f"[issl] {n} gpu(s), chunks of 7 guides" in p.stderr.decode()
+
+
+def test_score_multi_chunks_on_one_device():
+    """issl_score_multi's chunking (the product's multi-GPU entry point) with a single device: any chunk size gives
+    issl_score's answer, in input order, and the per-device count adds up."""
+    case = golden_case("w8_families")
+    guides = np.tile(cb.pack_guides(case.guides, case.seq_length), 5)
+    dev = device_for("w8_families", "auto")
+    for method, thr in (("and", 0.0), ("mit", 75.0), ("avg", 50.0)):
+        mit0, cfd0 = dev.score(guides, 4, thr, method)
+        for chunk in (1, 7, 64, guides.size, 0):
+            mit, cfd = np.full(guides.size, -5.0), np.full(guides.size, -5.0)
+            st, per = cb.score_multi([dev], guides, 4, thr, method, mit, cfd, chunk)
+            assert np.array_equal(mit.view(np.uint64), mit0.view(np.uint64))
+            if cfd0 is not None:
+                assert np.array_equal(cfd.view(np.uint64), cfd0.view(np.uint64))
+            else:
+                assert np.all(cfd == -5.0)          # a column the method skips is left untouched
+            assert st["guides"] == guides.size and int(per.sum()) == guides.size
+
+
+def test_replicas_and_score_multi_on_several_gpus():
+    """issl_device_clone + issl_score_multi: replicas made by peer copy score exactly like the original, and one call
+    spread over all GPUs gives the single-GPU answer whatever the chunk size; pinned host buffers."""
+    n = cb.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    text = td.make_offtargets(31, n_random=150_000, n_families=30, family_size=200)
+    img = oracle.create_index(text, 20, 8)
+    first = cb.Device.from_index(cb.Index(img), 0, "auto")
+    devs = cb.replicate(first, list(range(n)))
+    assert [d.info["cuda_device"] for d in devs] == list(range(n))
+    assert all(d.info["hbm_bytes"] == first.info["hbm_bytes"] and d.info["layout"] == first.info["layout"] for d in devs)
+    guides = td.pack_guides(td.make_guides(32, text, n=3000))
+    hg, hm, hc = cb.HostBuffer(guides.size, np.uint64), cb.HostBuffer(guides.size, np.float64), cb.HostBuffer(guides.size, np.float64)
+    hg.array[:] = guides
+    for method, thr, md in (("and", 0.0, 4), ("and", 75.0, 4), ("or", 60.0, 3), ("cfd", 0.0, 5)):
+        want = oracle.score(img, guides, md, thr, method, threads=0)
+        for d in devs[1:]:
+            mit, cfd = d.score(guides, md, thr, method)
+            for got, ref in ((mit, want["mit"]), (cfd, want["cfd"])):
+                assert got is None or np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+        for chunk in (97, 1000, 0):
+            hm.array[:] = -1.0; hc.array[:] = -1.0
+            st, per = cb.score_multi(devs, hg.array, md, thr, method, hm.array, hc.array, chunk)
+            if method != "cfd":
+                assert np.array_equal(hm.array.view(np.uint64), want["mit"].view(np.uint64))
+            if method != "mit":
+                assert np.array_equal(hc.array.view(np.uint64), want["cfd"].view(np.uint64))
+            assert int(per.sum()) == guides.size
+            if chunk == 97:
+                assert np.count_nonzero(per) == n, per     # every GPU took part
+    with pytest.raises(cb.IsslError):
+        cb.score_multi([devs[0], devs[0]], hg.array, 4, 0.0, "and", hm.array, hc.array)
+    with pytest.raises(cb.IsslError):
+        devs[0].clone(0)
+    for d in devs:
+        d.close()
+
+
+def test_out_of_memory_batches_are_halved_and_layout_falls_back(monkeypatch):
+    """ISSL_ERR_NOMEM inside a batch halves the batch and repeats it (hooks simulate the failure); an index whose
+    sub-bucket copies do not fit under ISSL_LAYOUT_AUTO is scored through its slice lists -- same results either way."""
+    case = golden_case("w8_families")
+    guides = np.tile(cb.pack_guides(case.guides, case.seq_length), 40)
+    dev = device_for("w8_families", "auto")
+    want = dev.score(guides, 4, 75.0, "and")
+    monkeypatch.setenv("ISSL_TEST_NOMEM_ABOVE", "1500")
+    got = dev.score(guides, 4, 75.0, "and")
+    assert dev.stats["guides"] == guides.size
+    monkeypatch.delenv("ISSL_TEST_NOMEM_ABOVE")
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    monkeypatch.setenv("ISSL_TEST_TRIPLE_NOMEM", "1")
+    lists = cb.Device.from_index(cb.Index(case.issl), 0, "auto")
+    monkeypatch.delenv("ISSL_TEST_TRIPLE_NOMEM")
+    assert lists.info["layout"] == cb.LAYOUTS["res32"]
+    for a, b in zip(lists.score(guides, 4, 75.0, "and"), want):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    with pytest.raises(cb.IsslError) as e:      # an explicit request is not silently downgraded
+        monkeypatch.setenv("ISSL_TEST_TRIPLE_NOMEM", "1")
+        cb.Device.from_index(cb.Index(case.issl), 0, "triple")
+    assert e.value.code == 7
+    lists.close()
 
 
 @pytest.mark.parametrize("seed,w,n_random,families,fsize", [(11, 8, 200_000, 40, 300), (12, 10, 120_000, 20, 200),

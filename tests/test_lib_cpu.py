@@ -30,7 +30,37 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libissl_cuda.so does not export {n}"
     assert set(L._issl_symbols) == set(names), "binding.py and issl_cuda.h disagree"
-    assert L.issl_abi_version() == 2
+    assert L.issl_abi_version() == 3
+
+
+def test_format_lines_prints_what_printf_prints():
+    """issl_format_lines replaces the reference's printf loop (isslScoreOfftargets.cpp:514-527): same digits as "%f"."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    guides = rng.integers(0, 1 << 40, n, dtype=np.uint64)
+    # scores as the scorer produces them (10000 / (100 + sum)) plus awkward values: ties at the sixth decimal,
+    # tiny, huge, negative zero, infinities, NaN
+    mit = 10000.0 / (100.0 + rng.exponential(50.0, n))
+    cfd = 10000.0 / (100.0 + rng.exponential(5.0, n))
+    mit[:12] = [100.0, 0.0, -0.0, 0.0000005, 0.0000015, 0.0000025, 1e-300, 1e300, 99.9999995, np.inf, -np.inf, np.nan]
+    cfd[:6] = [0.5, 1.0000005, 2.5e-7, 123456789.123456789, 1e22, 5e-324]
+    for method, (a, b) in {"and": (mit, cfd), "mit": (mit, None), "cfd": (None, cfd), "bogus": (None, None)}.items():
+        got = cb.format_lines(guides, mit, cfd, method)
+        want = b"".join(b"%s\t%s\t%s\n" % (cb.unpack_guide(int(g)).encode(), (b"%f" % a[i]) if a is not None else b"-1",
+                                           (b"%f" % b[i]) if b is not None else b"-1") for i, g in enumerate(guides[:3000]))
+        assert got.startswith(want), method
+        assert got.count(b"\n") == n
+    assert cb.format_lines(guides[:0], mit[:0], cfd[:0], "and") == b""
+
+
+def test_multi_gpu_chunks():
+    """issl_multi_chunk: about eight chunks per device, between 65 536 guides and one internal batch."""
+    assert cb.multi_chunk(1000, 1) == 1000
+    assert cb.multi_chunk(1000, 8) == 65536
+    assert cb.multi_chunk(10_000_000, 8) % 4096 == 0 and 150_000 < cb.multi_chunk(10_000_000, 8) < 170_000
+    assert cb.multi_chunk(1 << 30, 2) == 1 << 20
+    with pytest.raises(cb.IsslError):
+        cb.score_multi([], np.zeros(1, np.uint64), 4, 0.0, "and", np.zeros(1), np.zeros(1))
 
 
 def test_pack_unpack_and_methods():
