@@ -32,7 +32,7 @@ class _Info(C.Structure):
 class _DeviceInfo(C.Structure):
     _fields_ = [("cuda_device", C.c_int), ("layout", C.c_int), ("bytes_per_candidate", C.c_uint32),
                 ("hbm_bytes", C.c_uint64), ("list_entries", C.c_uint64), ("info", _Info),
-                ("triple_block_bytes", C.c_uint32)]
+                ("triple_block_bytes", C.c_uint32), ("triple_hit_bytes", C.c_uint32)]
 
 
 class _Stats(C.Structure):
@@ -287,7 +287,7 @@ class Device:
         _check(lib().issl_device_get_info(self._h, C.byref(s)))
         d = {"cuda_device": s.cuda_device, "layout": s.layout, "bytes_per_candidate": s.bytes_per_candidate,
              "hbm_bytes": int(s.hbm_bytes), "list_entries": int(s.list_entries),
-             "triple_block_bytes": int(s.triple_block_bytes)}
+             "triple_block_bytes": int(s.triple_block_bytes), "triple_hit_bytes": int(s.triple_hit_bytes)}
         d.update(_info_dict(s.info))
         return d
 

@@ -266,25 +266,33 @@ static int build_triple(issl_device *d)
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
     size_t tb = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(),
-                                       d->tripleIds.as<uint32_t>(), N, 0, 24, st));
+                                       d->tripleIds.as<uint32_t>(), N, 0, 25, st));
     CKR(tmp.ensure(tb));
     for (uint32_t t = 0; t < kTripleCount; t++) {
         uint32_t *ids = d->tripleIds.as<uint32_t>() + t * stride;
-        k_triple_keys<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), N, t, keysIn.as<uint32_t>(), idsIn.as<uint32_t>());
-        // stable: ids stay ascending inside a bucket, as inside the reference's lists (isslCreateIndex.cpp:225-233)
-        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(), ids, N, 0, 24, st));
+        k_triple_keys<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), d->occ.as<uint32_t>(), N, t, keysIn.as<uint32_t>(), idsIn.as<uint32_t>());
+        // stable: inside a bucket the sites that occur more than once come first, ids ascending within either class
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(), ids, N, 0, 25, st));
         k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, d->tripleRes.as<uint16_t>() + t * stride);
         if (occFlag) k_triple_flag_ids<<<blocks_for(N, 256), 256, 0, st>>>(d->occ.as<uint32_t>(), N, ids);
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
         if (pitch)
             k_triple_blocks<<<blocks_for((uint64_t)kTripleBuckets * (pitch / 32), 256), 256, 0, st>>>(
-                d->tripleRes.as<uint16_t>() + t * stride, d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull), pitch / 32,
+                d->tripleRes.as<uint16_t>() + t * stride, d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull), keysOut.as<uint32_t>(), pitch / 32,
                 d->tripleBlk.as<uint4>() + (uint64_t)t * kTripleBuckets * (pitch / 8));
         CK(cudaGetLastError());
     }
+    // are the sites in text order, i.e. are ids text ranks?  (ISSL_SITE_ORDER=0: behave as if they were not)
+    CKR(d->counters.ensure(8 * 8));
+    CK(cudaMemsetAsync(d->counters.p, 0, 8, st));
+    k_check_site_order<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), N, (uint32_t)d->info.seqLength, d->counters.as<unsigned long long>());
+    CK(cudaMemcpyAsync(d->hCounters, d->counters.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    bool siteOrdered = d->hCounters[0] == 0;
+    if (const char *e = getenv("ISSL_SITE_ORDER")) siteOrdered = siteOrdered && atoi(e) != 0;
     for (DBuf *b : {&keysIn, &keysOut, &idsIn, &tmp}) b->release();
+    d->tv.siteOrdered = siteOrdered ? 1u : 0u;
     d->tv.res = d->tripleRes.as<uint16_t>();
     d->tv.ids = d->tripleIds.as<uint32_t>();
     d->tv.offs = d->tripleOffs.as<uint32_t>();
@@ -785,6 +793,9 @@ extern "C" int issl_device_get_info(const issl_device *d, issl_device_info *out)
     out->list_entries = d->info.sliceCount * d->info.offtargetsCount;
     out->info = d->info;
     out->triple_block_bytes = d->layout == ISSL_LAYOUT_TRIPLE ? d->tv.pitch * 2 : 0;
+    // what the fused tail gathers per hit: an offset pair, an id and the 16-byte record of the non-fused modes -- or
+    // nothing, when the site's own text rank orders the hits
+    out->triple_hit_bytes = d->layout == ISSL_LAYOUT_TRIPLE ? ((d->tv.siteOrdered && d->tv.pitch) ? 0 : 28) : 0;
     return ISSL_OK;
 }
 
@@ -899,8 +910,14 @@ static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
             uint32_t exact = 0;   // slices of the triple on which the bucket agrees with the guide
             for (int k = 0; k < 3; k++)
                 if (((raw[i] >> (8 * k)) & 0xFFu) == 0) exact |= 1u << slices[t][k];
+            // which of its entries this visit reports: resp(E) == t, for the four ways the residual's two slices can match exactly
+            uint32_t keep = 0;
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t E = exact | ((c & 1u) << slices[t][3]) | ((c >> 1) << slices[t][4]);
+                if (issl_triple_resp(E) == t) keep |= 1u << c;
+            }
             v[i].x = raw[i];
-            v[i].y = exact | ((uint32_t)slices[t][3] << 8) | ((uint32_t)slices[t][4] << 12);
+            v[i].y = exact | ((uint32_t)slices[t][3] << 8) | ((uint32_t)slices[t][4] << 12) | (keep << 16);
         }
         CKR(d->visits.ensure(std::max<size_t>(1, v.size()) * sizeof(TripleVisit)));
         CK(cudaMemcpyAsync(d->visits.p, v.data(), v.size() * sizeof(TripleVisit), cudaMemcpyHostToDevice, st));
@@ -961,6 +978,10 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         if (inScan) { CKR(d->totMit2.ensure(n * 8ull)); CKR(d->totCfd2.ensure(n * 8ull)); CKR(d->done2.ensure(n)); }
         ScoreParams sp;
         sp.sig = d->iv.sig; sp.occ = d->iv.occ; sp.occFlag = d->tv.occFlag; sp.tb = score_tables(d);
+        // order keys: site text ranks (40 bits) when the index is in text order, site ids otherwise
+        uint32_t idShift = 0;
+        while (idShift < 28 && (d->info.offtargetsCount >> idShift) > 16) idShift++;
+        sp.keyShift = d->tv.siteOrdered ? 36u : idShift;
         sp.calcMit = ws.calcMit; sp.calcCfd = ws.calcCfd; sp.method = ws.method; sp.checkExit = ws.checkExit;
         sp.maximumSum = ws.maximumSum;
         sp.totMit = d->totMit.as<double>(); sp.totCfd = d->totCfd.as<double>(); sp.done = d->done.as<uint8_t>();
@@ -1015,6 +1036,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             sa.segKeys = d->segKeys.as<uint64_t>(); sa.segSites = d->segSites.as<uint64_t>();
             sa.segOff = d->segOff.as<uint64_t>(); sa.segCnt = d->segCnt.as<uint32_t>();
             sa.guides = dGuides; sa.sp = sp;
+            sa.sp.keyShift = idShift;   // segments are ordered by id
             k_score_segments<<<n, kTripleThreads, 0, st>>>(sa);
             CK(cudaGetLastError());
             d->stats.launches += 1;

@@ -49,6 +49,14 @@ struct TripleView {
     // byte, so the same buckets are read; only the order differs -- the reference meets a hit first in the lowest
     // 2-base slice that matches exactly, which may lie below the lowest exact byte
     uint32_t nibbleOrder;
+    // Site ids are ranks in the text order of the sites (extractOfftargets sorts its output and isslCreateIndex numbers
+    // distinct lines as it reads them, ref isslCreateIndex.cpp:184-207): when the index really is sorted (checked once
+    // at load, k_check_site_order), "ascending id" -- the order the reference accumulates the hits of one slice in,
+    // ref isslScoreOfftargets.cpp:330-344 -- IS ascending site text, which a hit's own 40 bits give: the fused tail then
+    // orders hits by sig_to_sortkey(site) and never looks an id up (two dependent 64-byte lines per hit saved).
+    // A site that occurs more than once still needs its count: the blocks keep such entries FIRST in their bucket and
+    // note how many there are (see k_triple_blocks), so only those hits pay for the lookup.
+    uint32_t siteOrdered;
 };
 constexpr uint32_t kSubEntries = 31;
 
@@ -65,12 +73,31 @@ __host__ __device__ __forceinline__ uint32_t triple_res(uint64_t sig, uint32_t p
 // ------------------------------------------------------------------------------------------------
 // construction (once per index): sort (key, id) per triple, then residuals + bucket offsets
 // ------------------------------------------------------------------------------------------------
-__global__ void k_triple_keys(const uint64_t *sig, uint64_t n, uint32_t t, uint32_t *keys, uint32_t *ids)
+// sort key = bucket << 1 | "occurs once": inside a bucket the sites that occur more than once come first, ascending
+// id within either class (the sort is stable)
+__global__ void k_triple_keys(const uint64_t *sig, const uint32_t *occ, uint64_t n, uint32_t t, uint32_t *keys, uint32_t *ids)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = triple_key(sig[i], c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
+    keys[i] = (triple_key(sig[i], c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]) << 1) | (occ[i] > 1 ? 0u : 1u);
     ids[i] = (uint32_t)i;
+}
+
+// A site's rank key in text order (base 0 most significant, A < C < G < T): sig_to_sortkey without its loop -- reverse all
+// bits, then put the two bits of every base back in order
+__device__ __forceinline__ uint64_t site_text_key(uint64_t sig, uint32_t L)
+{
+    uint64_t r = __brevll(sig);
+    r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+    return r >> (64 - 2 * L);
+}
+
+// violations of "sites are in ascending text order" (then ids are text ranks, see TripleView::siteOrdered)
+__global__ void k_check_site_order(const uint64_t *sig, uint64_t n, uint32_t L, unsigned long long *violations)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    if (site_text_key(sig[i], L) >= site_text_key(sig[i + 1], L)) atomicAdd(violations, 1ull);
 }
 
 __global__ void k_triple_residuals(const uint64_t *sig, const uint32_t *sortedIds, uint64_t n, uint32_t t, uint16_t *res)
@@ -97,13 +124,16 @@ __global__ void k_triple_offsets(const uint32_t *sortedKeys, uint64_t n, uint32_
     uint64_t lo = 0, hi = n;
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
-        if (sortedKeys[mid] < k) lo = mid + 1; else hi = mid;
+        if ((sortedKeys[mid] >> 1) < k) lo = mid + 1; else hi = mid;
     }
     offs[k] = (uint32_t)lo;
 }
 
-// blocked copy of one triple: one thread transposes one sub-block
-__global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint32_t subs, uint4 *blk /* this triple's blocks */)
+// blocked copy of one triple: one thread transposes one sub-block.  Column 0 of a sub-block (bit 0 of its 16 words) is
+// not a residual: words 0..4 = number of entries, word 5 = "the bucket has more entries than its block holds",
+// words 6..10 = how many of this sub-block's entries occur more than once -- they are its first ones.
+__global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, const uint32_t *sortedKeys, uint32_t subs,
+                                uint4 *blk /* this triple's blocks */)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (uint64_t)kTripleBuckets * subs) return;
@@ -115,14 +145,18 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, uint3
     // the block holds the bucket's first subs*31 entries; the flag says that more follow in the contiguous copy
     const uint32_t first = sub * kSubEntries;
     const uint32_t n = count > first ? min(count - first, kSubEntries) : 0u;
+    uint32_t multi = 0;
     for (uint32_t e = 0; e < n; e++) {
         const uint32_t r = res[start + first + e];
 #pragma unroll
         for (int p = 0; p < 16; p++) w[p] |= ((r >> p) & 1u) << (e + 1);
+        multi += 1u - (sortedKeys[start + first + e] & 1u);
     }
 #pragma unroll
     for (int p = 0; p < 5; p++) w[p] |= (n >> p) & 1u;
     if (count > subs * kSubEntries) w[5] |= 1u;
+#pragma unroll
+    for (int p = 0; p < 5; p++) w[6 + p] |= (multi >> p) & 1u;
     uint4 *o = blk + i * 4;
     o[0] = make_uint4(w[0], w[1], w[2], w[3]);
     o[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -169,6 +203,7 @@ struct ScoreParams {
     const uint64_t *sig;          // [N] site signatures
     const uint32_t *occ;          // [N] occurrences
     uint32_t occFlag;             // ids carry "occurs more than once" in bit 31
+    uint32_t keyShift;            // order keys >> keyShift lie in [0, 16): 36 for site text keys, from the site count for ids
     ScoreTables tb;
     int calcMit, calcCfd, method, checkExit;
     double maximumSum;
@@ -176,38 +211,45 @@ struct ScoreParams {
     uint8_t *done;
 };
 
+// Hits are put into the reference's accumulation order -- slice, then ascending site id inside the slice (ref :330-344) --
+// by a counting pass over (slice, sixteenth of the key range) groups followed by a rank inside the group: a guide's
+// ~275 hits fall into ~60 groups of a few hits each, so the rank is a handful of comparisons.
+constexpr uint32_t kKeyBuckets = 16;
+constexpr uint32_t kOrderGroups = kOrderSlices * kKeyBuckets;
+
 struct ScoreShared {
     double mit[kTripleThreads], cfd[kTripleThreads];   // a window of contributions in accumulation order
-    uint32_t cnt[kOrderSlices], fill[kOrderSlices], out[kOrderSlices + 1];
+    uint32_t grp[kOrderGroups];                        // per group: count -> first position -> end position
+    uint32_t kept;
 };
-constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one u32 id per hit
+constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one 64-bit order key per hit
 
-// load(j, idRaw, slice, site): hit j of the guide.  group[] may alias whatever load() reads: it is first written
-// after a barrier that follows the last load.  Results go to totMitOut/totCfdOut/doneOut[guide].
+// load(j, slice, site, occ, orderKey): hit j of the guide -- the slice through which the reference meets it first
+// (kNoSlice: not a hit here), its signature, its occurrences, and a key that ascends as the site id does (the id itself,
+// or the site's text rank).  sp.keyShift: orderKey >> keyShift < 16.  group[] may alias whatever load() reads: it is
+// first written after a barrier that follows the last load.  Results go to totMitOut/totCfdOut/doneOut[guide].
 template <class Load>
-__device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, uint32_t n, uint32_t guide, uint64_t g,
+__device__ __forceinline__ void score_guide(ScoreShared &ss, uint64_t *group, uint32_t n, uint32_t guide, uint64_t g,
                                             const ScoreParams &sp, double *totMitOut, double *totCfdOut, uint8_t *doneOut, Load load)
 {
     constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
-    if (threadIdx.x < kOrderSlices) { ss.cnt[threadIdx.x] = 0; ss.fill[threadIdx.x] = 0; }
+    for (uint32_t i = threadIdx.x; i < kOrderGroups; i += kTripleThreads) ss.grp[i] = 0;
     __syncthreads();
-    uint32_t myId[kPerThread], mySlice[kPerThread];
+    uint32_t myGroup[kPerThread];
+    uint64_t myKey[kPerThread];
     double myMit[kPerThread], myCfd[kPerThread];   // shared memory per SM is L1 the scan cannot use: contributions stay in registers
-    const uint32_t idMask = sp.occFlag ? 0x7FFFFFFFu : ~0u;
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         const uint32_t j = threadIdx.x + k * kTripleThreads;
-        mySlice[k] = kNoSlice;
+        myGroup[k] = kOrderGroups;
         if (j < n) {
-            uint32_t idRaw = 0, slice = kNoSlice;
-            uint64_t site = kSiteUnknown;
-            load(j, idRaw, slice, site);
+            uint32_t slice = kNoSlice, occ = 1;
+            uint64_t site = 0, key = 0;
+            load(j, slice, site, occ, key);
             if (slice >= kOrderSlices) continue;   // not a hit in this triple (the triple responsible for it reports it)
-            const uint32_t id = idRaw & idMask;
-            myId[k] = id; mySlice[k] = slice;
-            atomicAdd(&ss.cnt[slice], 1u);
-            if (site == kSiteUnknown) site = __ldg(sp.sig + id);
-            const uint32_t occ = (sp.occFlag && !(idRaw & 0x80000000u)) ? 1u : __ldg(sp.occ + id);
+            myKey[k] = key;
+            myGroup[k] = slice * kKeyBuckets + min((uint32_t)(key >> sp.keyShift), kKeyBuckets - 1);
+            atomicAdd(&ss.grp[myGroup[k]], 1u);
             double cm, cc;
             int dist;
             hit_contrib(sp.tb, g, site, occ, sp.calcMit, sp.calcCfd, cm, cc, dist);
@@ -215,33 +257,42 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t out = 0;
-        for (uint32_t s = 0; s < kOrderSlices; s++) { ss.out[s] = out; out += ss.cnt[s]; }
-        ss.out[kOrderSlices] = out;
+    if (threadIdx.x < 32) {   // counts -> first positions (exclusive prefix sum by one warp)
+        constexpr uint32_t kPer = kOrderGroups / 32;
+        uint32_t c[kPer], sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < kPer; i++) { c[i] = ss.grp[threadIdx.x * kPer + i]; sum += c[i]; }
+        uint32_t incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += up;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (uint32_t i = 0; i < kPer; i++) { ss.grp[threadIdx.x * kPer + i] = run; run += c[i]; }
+        if (threadIdx.x == 31) ss.kept = incl;
     }
     __syncthreads();
-    uint32_t *gid = reinterpret_cast<uint32_t *>(group);                       // ids, grouped by slice
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++)
-        if (mySlice[k] < kOrderSlices) gid[ss.out[mySlice[k]] + atomicAdd(&ss.fill[mySlice[k]], 1u)] = myId[k];
+        if (myGroup[k] < kOrderGroups) group[atomicAdd(&ss.grp[myGroup[k]], 1u)] = myKey[k];   // keys, grouped; grp[] ends up as end positions
     __syncthreads();
-    // rank of every hit inside its slice group = number of smaller ids (ids of one guide are distinct): every thread
-    // counts for its own hits over the whole group (broadcast reads); groups are small (~55 ids)
+    // rank of every hit inside its group = number of smaller keys (the sites of one guide's hits are distinct)
     uint32_t myRank[kPerThread];
 #pragma unroll
     for (uint32_t k = 0; k < kPerThread; k++) {
         myRank[k] = 0xFFFFFFFFu;
-        if (mySlice[k] < kOrderSlices) {
-            const uint32_t c = ss.cnt[mySlice[k]], base = ss.out[mySlice[k]], mine = myId[k];
+        if (myGroup[k] < kOrderGroups) {
+            const uint32_t base = myGroup[k] ? ss.grp[myGroup[k] - 1] : 0u, end = ss.grp[myGroup[k]];
+            const uint64_t mine = myKey[k];
             uint32_t r = 0;
-            for (uint32_t q = 0; q < c; q++) r += (uint32_t)(gid[base + q] < mine);
+            for (uint32_t q = base; q < end; q++) r += (uint32_t)(group[q] < mine);
             myRank[k] = base + r;
         }
     }
     // ordered accumulation with the reference's early exit (ref :394, :460, :466-502): the contributions pass through
     // a window of shared memory in rank order, kTripleThreads at a time, and one thread adds them up
-    const uint32_t kept = ss.out[kOrderSlices];
+    const uint32_t kept = ss.kept;
     double mit = 0.0, cfd = 0.0;
     bool stop = false;
     if (threadIdx.x == 0) { mit = sp.totMit[guide]; cfd = sp.totCfd[guide]; }
@@ -271,9 +322,17 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint32_t *group, ui
     }
 }
 
+// occurrences of a site whose id is known: 1 when the stored id says so, else from occ[]
+__device__ __forceinline__ uint32_t occ_of(const ScoreParams &sp, uint32_t idRaw)
+{
+    return (sp.occFlag && !(idRaw & 0x80000000u)) ? 1u : __ldg(sp.occ + (idRaw & (sp.occFlag ? 0x7FFFFFFFu : ~0u)));
+}
+
 struct TripleVisit {
     uint32_t x;   // pattern24 | triple << 24 | budget << 28   (issl_triple_visits)
-    uint32_t y;   // exact slices inside the triple (5-bit set) | slice p << 8 | slice q << 12
+    uint32_t y;   // exact slices inside the triple (5-bit set) | slice p << 8 | slice q << 12 | keep table << 16:
+                  // bit (pExact | qExact << 1) of the table = "an entry of this bucket whose residual matches exactly on
+                  // slice p / q (or not) is this triple's to report" (resp(E) == triple), worked out once on the host
 };
 
 struct TripleArgs {
@@ -349,6 +408,7 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
 //   y: triple (0..3) | exact slices of the visit's pattern (4..8) | residual matches on slice p (9), on q (10) |
 //      blocked scan (11) | blocked scan: the entry's residual (16..31) -- with the bucket key, the whole site
 constexpr uint32_t kRecBlocked = 1u << 11;
+constexpr uint32_t kRecMulti = 1u << 12;     // blocked scan: the site occurs more than once (its count has to be looked up)
 
 __device__ __forceinline__ uint32_t record_y(uint2 v, uint32_t pExact, uint32_t qExact, uint32_t flag)
 {
@@ -427,6 +487,16 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
     }
 }
 
+// a record that found the CTA's list full (rare: dense repeat families): straight to the general pipeline's buffer
+__device__ __forceinline__ void triple_spill(const TripleArgs &a, uint32_t guide, uint2 h)
+{
+    uint32_t minE;
+    if (!record_keep(h, minE)) return;
+    const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)];
+    const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
+    if (gs < a.hitCap) a.hitKeys[gs] = general_key(a.tv, guide, minE, id);
+}
+
 // Guides with thousands of hits (maxDist 5 and 6, dense repeat families): when the CTA's record list is nearly full,
 // all threads empty it into the general pipeline's key buffer (one reservation, ids resolved in parallel) and the
 // scan goes on; such a guide is finished by the general pipeline.  Called by all threads of the CTA.
@@ -499,7 +569,7 @@ __device__ __forceinline__ void triple_bucket(const TripleArgs &a, TripleShared 
 struct TripleSmem {
     union {
         TripleShared scan;
-        uint32_t group[kScoreGroupWords];
+        uint64_t group[kScoreGroupWords];
     };
     ScoreShared score;
 };
@@ -534,17 +604,25 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         if (nAll == 0) return;
         __syncthreads();   // the defaults above are in place before score_guide's writer thread runs
         score_guide(sm.score, sm.group, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
-                    [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
+                    [&](uint32_t j, uint32_t &slice, uint64_t &site, uint32_t &occ, uint64_t &key) {
                         const uint2 h = sh.hits[j];
                         if (!record_keep(h, slice)) { slice = kNoSlice; return; }
-                        idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
                         site = hit_site(a.tv, h);
-                        if (a.tv.nibbleOrder) {
-                            if (site == kSiteUnknown) site = __ldg(a.sp.sig + (idRaw & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u)));
-                            slice = order_slice(a.tv, site ^ g, slice);
+                        if (a.tv.siteOrdered && site != kSiteUnknown) {
+                            // the site's text rank orders it; its id is only needed when it occurs more than once
+                            key = site_text_key(site, 20);
+                            if (h.y & kRecMulti)
+                                occ = occ_of(a.sp, __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)));
+                        } else {
+                            const uint32_t idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+                            const uint32_t id = idRaw & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u);
+                            if (site == kSiteUnknown) site = __ldg(a.sp.sig + id);
+                            occ = occ_of(a.sp, idRaw);
+                            key = a.tv.siteOrdered ? site_text_key(site, 20) : (uint64_t)id;
                         }
+                        if (a.tv.nibbleOrder) slice = order_slice(a.tv, site ^ g, slice);
                     });
-        if (threadIdx.x == 0 && sm.score.out[kOrderSlices]) atomicAdd(a.fusedHits, (unsigned long long)sm.score.out[kOrderSlices]);
+        if (threadIdx.x == 0 && sm.score.kept) atomicAdd(a.fusedHits, (unsigned long long)sm.score.kept);
         return;
     }
     // hand the hits on: de-duplicate, compact, reserve a range of the segment / key buffer, resolve ids
@@ -697,34 +775,49 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
         bs_full_add(ca, cb, cc, t1, u1);
         const uint32_t s1 = t1 ^ cd, u2 = t1 & cd;          // count bit 1
         const uint32_t s2 = u1 ^ u2, s3 = u1 & u2;          // count bits 2, 3
-        uint32_t over;                                       // slots whose count exceeds the budget
-        switch (v.x >> 28) {
-        case 0: over = s0 | s1 | s2 | s3; break;
-        case 1: over = s1 | s2 | s3; break;
-        case 2: over = s2 | s3 | (s1 & s0); break;
-        case 3: over = s2 | s3; break;
-        case 4: over = s3 | (s2 & (s1 | s0)); break;
-        case 5: over = s3 | (s2 & s1); break;
-        case 6: over = s3 | (s2 & s1 & s0); break;
-        default: over = s3; break;
-        }
-        uint32_t pass = ~over & ((2u << cnt) - 2u);          // slots 1..cnt hold residuals
+        // slots whose count exceeds the budget: a bit-sliced comparator, most significant bit last (lanes of a warp hold
+        // visits with different budgets -- no branches)
+        const uint32_t bud = v.x >> 28;
+        const uint32_t b0 = 0u - (bud & 1u), b1 = 0u - ((bud >> 1) & 1u), b2 = 0u - ((bud >> 2) & 1u);
+        uint32_t over = s0 & ~b0;
+        over = (s1 & ~b1) | (~(s1 ^ b1) & over);
+        over = (s2 & ~b2) | (~(s2 ^ b2) & over);
+        over |= s3;
+        // ... and of those within budget, the ones this triple is responsible for (the stateless replacement of the
+        // reference's toggle bitset, ref :385-390): a function of the visit and of "the residual matches exactly on slice
+        // p / on slice q", tabulated per visit.  Nearly all visits keep only entries that match on neither.
+        const uint32_t pEx = ~(x0 | x1 | x2 | x3), qEx = ~(x4 | x5 | x6 | x7);
+        const uint32_t kt = v.y >> 16;
+        uint32_t keep = ~(pEx | qEx);
+        if (kt != 1u)
+            keep = ((kt & 1u) ? ~(pEx | qEx) : 0u) | ((kt & 2u) ? (pEx & ~qEx) : 0u) | ((kt & 4u) ? (~pEx & qEx) : 0u) | ((kt & 8u) ? (pEx & qEx) : 0u);
+        uint32_t pass = ~over & keep & ((2u << cnt) - 2u);   // slots 1..cnt hold residuals
         if (pass) {
-            const uint32_t pEx = ~(x0 | x1 | x2 | x3), qEx = ~(x4 | x5 | x6 | x7);
+            // one reservation for all hits of the sub-block; the sub-block's entries that occur more than once are its first ones
+            uint32_t slot = atomicAdd(&sh.nHits, (uint32_t)__popc(pass));
+            const uint32_t multi = (q1.z & 1u) | ((q1.w & 1u) << 1) | ((q2.x & 1u) << 2) | ((q2.y & 1u) << 3) | ((q2.z & 1u) << 4);
+            const uint32_t multiMask = (2u << multi) - 2u;
+            const uint32_t y0 = ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | kRecBlocked;
             do {
                 const uint32_t sl = __ffs(pass) - 1;
                 pass &= pass - 1;
-                const uint32_t y = record_y(v, (pEx >> sl) & 1u, (qEx >> sl) & 1u, kRecBlocked);
-                uint32_t minE;
-                if (!record_keep(make_uint2(0u, y), minE)) continue;   // reported through the triple responsible for it
-                // the entry's residual, gathered back from the 16 planes (issue slots are free, DRAM lines are not)
-                const uint32_t r =
-                    ((q0.x >> sl) & 1u) | (((q0.y >> sl) & 1u) << 1) | (((q0.z >> sl) & 1u) << 2) | (((q0.w >> sl) & 1u) << 3) |
-                    (((q1.x >> sl) & 1u) << 4) | (((q1.y >> sl) & 1u) << 5) | (((q1.z >> sl) & 1u) << 6) | (((q1.w >> sl) & 1u) << 7) |
-                    (((q2.x >> sl) & 1u) << 8) | (((q2.y >> sl) & 1u) << 9) | (((q2.z >> sl) & 1u) << 10) | (((q2.w >> sl) & 1u) << 11) |
-                    (((q3.x >> sl) & 1u) << 12) | (((q3.y >> sl) & 1u) << 13) | (((q3.z >> sl) & 1u) << 14) | (((q3.w >> sl) & 1u) << 15);
+                // the entry's residual, gathered back from the 16 planes (issue slots are cheaper than DRAM lines): every
+                // plane is shifted so that the slot's bit becomes its top bit, which a funnel shift then feeds into r
+                const uint32_t up = 31u - sl;
+                uint32_t r = 0;
+                r = __funnelshift_l(q3.w << up, r, 1); r = __funnelshift_l(q3.z << up, r, 1);
+                r = __funnelshift_l(q3.y << up, r, 1); r = __funnelshift_l(q3.x << up, r, 1);
+                r = __funnelshift_l(q2.w << up, r, 1); r = __funnelshift_l(q2.z << up, r, 1);
+                r = __funnelshift_l(q2.y << up, r, 1); r = __funnelshift_l(q2.x << up, r, 1);
+                r = __funnelshift_l(q1.w << up, r, 1); r = __funnelshift_l(q1.z << up, r, 1);
+                r = __funnelshift_l(q1.y << up, r, 1); r = __funnelshift_l(q1.x << up, r, 1);
+                r = __funnelshift_l(q0.w << up, r, 1); r = __funnelshift_l(q0.z << up, r, 1);
+                r = __funnelshift_l(q0.y << up, r, 1); r = __funnelshift_l(q0.x << up, r, 1);
+                const uint32_t y = y0 | (((pEx >> sl) & 1u) << 9) | (((qEx >> sl) & 1u) << 10) | (((multiMask >> sl) & 1u) << 12) | (r << 16);
                 // entry number sub*31 + sl - 1 of the bucket, recorded as entry + 1
-                triple_push<true>(a, sh, guide, make_uint2(key | ((sub * kSubEntries + sl) << 24), y | (r << 16)));
+                const uint2 h = make_uint2(key | ((sub * kSubEntries + sl) << 24), y);
+                if (slot < kTripleHitCap) sh.hits[slot] = h; else triple_spill(a, guide, h);
+                slot++;
             } while (pass);
         }
     };
@@ -770,13 +863,19 @@ __global__ void __launch_bounds__(kTripleThreads) k_score_segments(const Segment
     const uint32_t n = a.segCnt[guide];
     if (n == 0) return;
     __shared__ ScoreShared ss;
-    __shared__ uint32_t group[kScoreGroupWords];
+    __shared__ uint64_t group[kScoreGroupWords];
     const uint64_t off = a.segOff[guide];
-    score_guide(ss, group, n, guide, a.guides[guide], a.sp, a.sp.totMit, a.sp.totCfd, a.sp.done,
-                [&](uint32_t j, uint32_t &idRaw, uint32_t &slice, uint64_t &site) {
-                    const uint64_t key = a.segKeys[off + j];
-                    idRaw = (uint32_t)key; slice = (uint32_t)(key >> 32) & 15u;
+    const uint64_t g = a.guides[guide];
+    score_guide(ss, group, n, guide, g, a.sp, a.sp.totMit, a.sp.totCfd, a.sp.done,
+                [&](uint32_t j, uint32_t &slice, uint64_t &site, uint32_t &occ, uint64_t &key) {
+                    const uint64_t k = a.segKeys[off + j];
+                    const uint32_t idRaw = (uint32_t)k;
+                    slice = (uint32_t)(k >> 32) & 15u;
                     site = a.segSites[off + j];
+                    const uint32_t id = idRaw & (a.sp.occFlag ? 0x7FFFFFFFu : ~0u);
+                    if (site == kSiteUnknown) site = __ldg(a.sp.sig + id);
+                    occ = occ_of(a.sp, idRaw);
+                    key = id;
                 });
 }
 

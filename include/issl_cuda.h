@@ -90,6 +90,8 @@ typedef struct issl_device_info {
     issl_info info;
     uint32_t triple_block_bytes;   /* TRIPLE: bytes of one bucket's block in the blocked copy (one read per
                                       bucket visit); 0 = no blocked copy, buckets are read through their offsets */
+    uint32_t triple_hit_bytes;     /* TRIPLE: bytes gathered per hit by the fused tail (offset pair, id, record): 28, or 0
+                                      when the index is in text order and a hit's own signature orders it */
 } issl_device_info;
 
 /* Counters of the last issl_score* call on a device handle. */

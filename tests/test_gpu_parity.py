@@ -384,6 +384,47 @@ def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     dev.close()
 
 
+@pytest.mark.parametrize("case", ["sorted", "sorted_ids", "shuffled", "w4_sorted", "w4_shuffled"])
+def test_fused_tail_orders_hits_by_site_text_or_by_id(case):
+    """The reference accumulates a slice's hits in ascending id (isslScoreOfftargets.cpp:330-344).  On an index whose
+    sites are in text order (what extractOfftargets + isslCreateIndex produce) ids are text ranks, and the fused tail
+    orders hits by their own signature without looking ids up; sites that occur more than once sit first in their
+    bucket and are the only ones whose count is fetched.  An index built from UNSORTED text (ids in file order, equal
+    sites under several ids) must be recognised at load and take the id path; ISSL_SITE_ORDER=0 forces that path.
+    Early exits make every printed digit depend on the order, so bit-identical scores prove it."""
+    w = 4 if case.startswith("w4") else 8
+    text = td.make_offtargets(81, n_random=110_000, n_families=30, family_size=600, max_sub_rate=0.1)
+    if case.endswith("shuffled"):
+        lines = np.frombuffer(text, dtype=np.uint8).reshape(-1, 21).copy()
+        np.random.default_rng(82).shuffle(lines, axis=0)
+        text = lines.tobytes()
+    img = oracle.create_index(text, 20, w)
+    rng = np.random.default_rng(83)
+    roots = td.pack_guides(td.make_guides(84, text, n=450, frac_exact=1.0, frac_mut=0.0))
+    guides = np.concatenate([roots.repeat(5), rng.integers(0, 1 << 40, 300, dtype=np.uint64)])
+    for i in range(roots.size * 5):
+        for pos in rng.choice(20, size=int(rng.integers(0, 3)), replace=False):
+            guides[i] ^= np.uint64(int(rng.integers(1, 4)) << (2 * int(pos)))
+    assert guides.size >= 148 * 16
+    os.environ["ISSL_TRIPLE_BLOCKS"] = "32"
+    if case == "sorted_ids":
+        os.environ["ISSL_SITE_ORDER"] = "0"
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, "triple")
+    finally:
+        del os.environ["ISSL_TRIPLE_BLOCKS"]
+        os.environ.pop("ISSL_SITE_ORDER", None)
+    assert dev.info["triple_hit_bytes"] == (0 if case in ("sorted", "w4_sorted") else 28)
+    for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 4), ("mit", 30, 2), ("cfd", 20, 4)):
+        want = oracle.score(img, guides, md, thr, method, threads=0)
+        mit, cfd = dev.score(guides, md, thr, method)
+        if method != "cfd":
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (case, method, thr, md)
+        if method != "mit":
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (case, method, thr, md)
+    dev.close()
+
+
 @pytest.mark.parametrize("fuse,blocks", [(2, "64"), (1, "32"), (0, "0"), (2, "0")])
 def test_triple_layout_slice_width_4(fuse, blocks):
     """sliceWidth 4 (ten 2-base slices) under TRIPLE: up to maxDist 4 the same sub-buckets are read, but hits are
