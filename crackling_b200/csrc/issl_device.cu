@@ -52,6 +52,9 @@ struct issl_device {
     // ISSL_LAYOUT_TRIPLE
     DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites, totMit2, totCfd2, done2;
     uint64_t segCap = 0;
+    DBuf heavyKeys;                  // sort keys of the guides with more hits than a CTA's record list holds (heavy_finish)
+    uint64_t heavyCap = 0;
+    int tripleHeavy = 1;             // ISSL_TRIPLE_HEAVY=0: such guides go through the general pipeline (device-wide sort) instead
     DBuf mitDense;                   // the score table spread over all 2^20 position sets (seqLength <= 20)
     TripleView tv{};
     int tripleMaxDist = 6;           // ISSL_TRIPLE_MAXDIST: larger maxDist takes the RES32 list scan
@@ -59,6 +62,7 @@ struct issl_device {
     int tripleFlush = -1;            // ISSL_TRIPLE_FLUSH: 1 / 0 force the scan variant that flushes full record lists; -1 automatic
     double lastHitsPerGuide = 0;     // of the previous scoring call on this handle
     double lastExitFraction = -1.0;  // early exits / guides of the previous call that had an early exit to take; -1: none yet
+    int tripleLaneSubs = 1;          // ISSL_TRIPLE_LSUBS: sub-blocks per lane of the blocked scan (2: a lane owns the whole 128-byte block)
     int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments from
                                      // per-guide segments, 0 = everything through the general sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
@@ -284,7 +288,7 @@ static int build_triple(issl_device *d)
         CK(cudaGetLastError());
     }
     // are the sites in text order, i.e. are ids text ranks?  (ISSL_SITE_ORDER=0: behave as if they were not)
-    CKR(d->counters.ensure(8 * 8));
+    CKR(d->counters.ensure(16 * 8));
     CK(cudaMemsetAsync(d->counters.p, 0, 8, st));
     k_check_site_order<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), N, (uint32_t)d->info.seqLength, d->counters.as<unsigned long long>());
     CK(cudaMemcpyAsync(d->hCounters, d->counters.p, 8, cudaMemcpyDeviceToHost, st));
@@ -335,13 +339,15 @@ static int new_device(int cuda_device, issl_device **out)
     if (const char *e = getenv("ISSL_WAVES")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->waves = v; }
     if (const char *e = getenv("ISSL_HIT_CAP")) { const long v = atol(e); if (v > 0) d->firstHitCap = (uint64_t)v; }
     if (const char *e = getenv("ISSL_TRIPLE_FLUSH")) d->tripleFlush = atoi(e) != 0;
+    if (const char *e = getenv("ISSL_TRIPLE_HEAVY")) d->tripleHeavy = atoi(e) != 0;
+    if (const char *e = getenv("ISSL_TRIPLE_LSUBS")) { const int v = atoi(e); if (v == 1 || v == 2) d->tripleLaneSubs = v; }
     if (const char *e = getenv("ISSL_TRIPLE_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->tripleFuse = v; }
     if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
         const long v = atol(e);
         if (v >= -1 && v <= 7) d->tripleMaxDist = (int)v;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMallocHost(&d->hCounters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&d->hCounters, 16 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         delete d;
         return issl_set_error(ISSL_ERR_CUDA, "device %d setup: %s", cuda_device, cudaGetErrorString(e));
@@ -361,7 +367,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
+                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
                     &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
@@ -927,12 +933,18 @@ static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
     return ISSL_OK;
 }
 
+// sub-blocks per lane of the blocked scan (ISSL_TRIPLE_LSUBS = 1 / 2)
+static int lane_subs(const issl_device *d) { return d->tv.pitch >= 64 ? d->tripleLaneSubs : 1; }
+
 // ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
 template <bool FUSED, bool FLUSH>
 static void launch_triple_scan_t(const issl_device *d, const TripleArgs &a, dim3 grid, cudaStream_t st)
 {
+    const bool two = lane_subs(d) == 2;   // a lane owns two sub-blocks: eight loads in flight (issl_triple.cuh)
     if (d->tv.pitch == 32) k_scan_triple_blocked<1, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 64 && two) k_scan_triple_blocked<2, FUSED, FLUSH, 2><<<grid, kTripleThreads, 0, st>>>(a);
     else if (d->tv.pitch == 64) k_scan_triple_blocked<2, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 128 && two) k_scan_triple_blocked<4, FUSED, FLUSH, 2><<<grid, kTripleThreads, 0, st>>>(a);
     else if (d->tv.pitch == 128) k_scan_triple_blocked<4, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
     else k_scan_triple<FUSED><<<grid, kTripleThreads, 0, st>>>(a);
 }
@@ -960,13 +972,13 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     // the visit table is ordered by byte slice; sliceWidth 4 runs it in one piece (score_batch)
     const bool nibble = d->info.sliceWidth == 4;
     const uint32_t v0 = nibble ? d->waveStart[0] : d->waveStart[s0], v1 = nibble ? d->waveStart[5] : d->waveStart[std::min(s0 + ns, 5u)], nv = v1 - v0;
-    CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
+    CK(cudaMemsetAsync(dc, 0, 16 * 8, st));
     k_wave_candidates<<<blocks_for((uint64_t)n * ns, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
     d->stats.launches += 1;
     *nHitsOut = 0;
     if (nv) {
         // enough CTAs to fill the machine even for a handful of guides
-        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 32) : kTripleThreads / 8;   // visits in flight per CTA
+        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 32 / lane_subs(d)) : kTripleThreads / 8;   // visits in flight per CTA
         uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
         chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
         chunks = std::min<uint32_t>(chunks, 65535u);
@@ -977,7 +989,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         if (fuse) { CKR(d->segOff.ensure(n * 8ull)); CKR(d->segCnt.ensure(n * 4ull)); }
         if (inScan) { CKR(d->totMit2.ensure(n * 8ull)); CKR(d->totCfd2.ensure(n * 8ull)); CKR(d->done2.ensure(n)); }
         ScoreParams sp;
-        sp.sig = d->iv.sig; sp.occ = d->iv.occ; sp.occFlag = d->tv.occFlag; sp.tb = score_tables(d);
+        sp.sig = d->iv.sig; sp.occ = d->iv.occ; sp.nSites = d->info.offtargetsCount; sp.occFlag = d->tv.occFlag; sp.tb = score_tables(d);
         // order keys: site text ranks (40 bits) when the index is in text order, site ids otherwise
         uint32_t idShift = 0;
         while (idShift < 28 && (d->info.offtargetsCount >> idShift) > 16) idShift++;
@@ -985,14 +997,24 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         sp.calcMit = ws.calcMit; sp.calcCfd = ws.calcCfd; sp.method = ws.method; sp.checkExit = ws.checkExit;
         sp.maximumSum = ws.maximumSum;
         sp.totMit = d->totMit.as<double>(); sp.totCfd = d->totCfd.as<double>(); sp.done = d->done.as<uint8_t>();
+        // heavy guides are finished inside the scan kernel when it runs fused, in its flush variant, on an index in text order
+        const bool heavy = inScan && flush && d->tripleHeavy && d->tv.siteOrdered && d->tv.pitch;
+        if (heavy) {
+            // first guess: what the previous call saw (chunks + the sort's second copy: up to ~3.5 keys per hit), else 2^24 keys
+            const double guess = 4.0 * std::max(d->lastHitsPerGuide, 64.0) * n;
+            uint64_t want = (uint64_t)std::min(std::max(guess, (double)(1ull << 24)), (double)(1ull << 31));
+            if (d->firstHitCap) want = d->firstHitCap;   // ISSL_HIT_CAP: start small, so that tests reach the re-launch after an overflow
+            d->heavyCap = std::max<uint64_t>(d->heavyCap, want);
+        }
         for (;;) {
             CKR(ensure_hit_buffers(d, n));
+            if (heavy) CKR(d->heavyKeys.ensure(d->heavyCap * 8));
             if (fuse && d->segCap < d->hitCap) {
                 d->segCap = d->hitCap;
                 CKR(d->segKeys.ensure(d->segCap * 8)); CKR(d->segSites.ensure(d->segCap * 8));
             }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
-            CK(cudaMemsetAsync(dc + 4, 0, 32, st));
+            CK(cudaMemsetAsync(dc + 4, 0, 48, st));
             if (fuse) CK(cudaMemsetAsync(d->segCnt.p, 0, n * 4ull, st));
             TripleArgs a;
             a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<TripleVisit>() + v0;
@@ -1004,6 +1026,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             a.fuse = inScan ? 1 : 0; a.sp = sp;
             a.totMitOut = d->totMit2.as<double>(); a.totCfdOut = d->totCfd2.as<double>(); a.doneOut = d->done2.as<uint8_t>();
             a.fusedHits = dc + 7; a.maxRecords = dc + 2;
+            a.heavyKeys = heavy ? d->heavyKeys.as<uint64_t>() : nullptr; a.heavyCount = dc + 8; a.heavyCap = heavy ? d->heavyCap : 0;
+            a.heavyHits = dc + 9;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
@@ -1011,11 +1035,12 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             launch_triple_scan(d, a, dim3(n, chunks), inScan, flush, st);
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
-            CK(cudaMemcpyAsync(d->hCounters, dc, 8 * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(d->hCounters, dc, 16 * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             d->stats.scan_launches += 1;
             d->stats.launches += 1;
-            if (d->hCounters[1] <= d->hitCap && d->hCounters[6] <= d->segCap) break;
+            if (d->hCounters[1] <= d->hitCap && d->hCounters[6] <= d->segCap && (!heavy || d->hCounters[8] <= d->heavyCap)) break;
+            if (heavy && d->hCounters[8] > d->heavyCap) d->heavyCap = d->hCounters[8] + d->hCounters[8] / 4;
             if (d->hCounters[1] > d->hitCap) {
                 d->hitCap = d->hCounters[1] + d->hCounters[1] / 4;
                 CKR(d->keysA.ensure(d->hitCap * 8)); CKR(d->keysB.ensure(d->hitCap * 8));
@@ -1026,8 +1051,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             }
         }
         *nHitsOut = d->hCounters[1];
-        if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] wave %u+%u: max records per guide %llu, general-pipeline hits %llu, fused hits %llu\n",
-                                          s0, ns, d->hCounters[2], d->hCounters[1], d->hCounters[7]);
+        if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] wave %u+%u: max records per guide %llu, general-pipeline hits %llu, fused hits %llu, heavy keys %llu\n",
+                                          s0, ns, d->hCounters[2], d->hCounters[1], d->hCounters[7], d->hCounters[8]);
         d->stats.streamed += d->hCounters[4];
         d->stats.bucket_visits += d->hCounters[5];
         if (fuse && d->hCounters[6]) {
@@ -1045,6 +1070,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         if (inScan) {   // the scan kernel wrote every guide's state of after this wave
             d->totMit.swap(d->totMit2); d->totCfd.swap(d->totCfd2); d->done.swap(d->done2);
             d->stats.hits += d->hCounters[7];
+            d->stats.heavy_hits += d->hCounters[9];
         }
     } else {
         CK(cudaMemcpyAsync(d->hCounters, dc, 8, cudaMemcpyDeviceToHost, st));
@@ -1066,7 +1092,7 @@ static int list_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides, u
     const uint32_t nLists = (uint32_t)d->nLists;
     CKR(d->pairKeys.ensure(pairs * 4)); CKR(d->pairVals.ensure(pairs * 4));
     CKR(d->pairKeysSorted.ensure(pairs * 4)); CKR(d->pairValsSorted.ensure(pairs * 4));
-    CK(cudaMemsetAsync(dc, 0, 8 * 8, st));
+    CK(cudaMemsetAsync(dc, 0, 16 * 8, st));
     k_pair_keys<<<blocks_for(pairs, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, nLists,
                                                        d->pairKeys.as<uint32_t>(), d->pairVals.as<uint32_t>(), dc + 0);
     int keyBits = 1;
@@ -1154,7 +1180,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     const uint32_t S = d->iv.sliceCount;
 
     CKR(d->totMit.ensure(n * 8ull)); CKR(d->totCfd.ensure(n * 8ull)); CKR(d->done.ensure(n));
-    CKR(d->counters.ensure(8 * 8));
+    CKR(d->counters.ensure(16 * 8));
     CK(cudaMemsetAsync(d->totMit.p, 0, n * 8ull, st));
     CK(cudaMemsetAsync(d->totCfd.p, 0, n * 8ull, st));
     CK(cudaMemsetAsync(d->done.p, 0, n, st));
@@ -1259,6 +1285,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             d->stats.hits += 0;
         }
         d->stats.hits += nHits;
+        d->stats.sorted_hits += nHits;
     }
 
     if (checkExit) {
@@ -1302,7 +1329,7 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     if (d->lastHitsPerGuide > 512.0) {
         size_t freeB = 0, totalB = 0;
         if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-            const double held = (double)d->keysA.cap + (double)d->keysB.cap + (double)d->contribMit.cap + (double)d->contribCfd.cap;
+            const double held = (double)d->keysA.cap + (double)d->keysB.cap + (double)d->contribMit.cap + (double)d->contribCfd.cap + (double)d->heavyKeys.cap;
             const double fit = 0.6 * ((double)freeB + held) / (40.0 * d->lastHitsPerGuide);
             if (fit < (double)batch) batch = (uint32_t)std::max(4096.0, fit);
         }
@@ -1326,9 +1353,10 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
         if (rc == ISSL_ERR_NOMEM && nb > 1024) {
             cudaGetLastError();
             cudaStreamSynchronize(st);
-            for (DBuf *b : {&d->keysA, &d->keysB, &d->contribMit, &d->contribCfd, &d->sortTemp, &d->segKeys, &d->segSites, &d->hitId, &d->hitDist, &d->hitOcc})
+            for (DBuf *b : {&d->keysA, &d->keysB, &d->contribMit, &d->contribCfd, &d->sortTemp, &d->segKeys, &d->segSites, &d->hitId, &d->hitDist, &d->hitOcc,
+                            &d->heavyKeys})
                 b->release();
-            d->hitCap = d->hitCapAuto = 0; d->segCap = 0;
+            d->hitCap = d->hitCapAuto = 0; d->segCap = 0; d->heavyCap = 0;
             d->stats = before;
             if (sink) { sink->guide.resize(hitsBefore); sink->id.resize(hitsBefore); sink->dist.resize(hitsBefore); sink->occ.resize(hitsBefore); }
             batch = std::max<uint32_t>(1024, nb / 2);

@@ -202,6 +202,7 @@ constexpr uint64_t kSiteUnknown = ~0ull;   // a hit record without the site's si
 struct ScoreParams {
     const uint64_t *sig;          // [N] site signatures
     const uint32_t *occ;          // [N] occurrences
+    uint64_t nSites;              // N
     uint32_t occFlag;             // ids carry "occurs more than once" in bit 31
     uint32_t keyShift;            // order keys >> keyShift lie in [0, 16): 36 for site text keys, from the site count for ids
     ScoreTables tb;
@@ -364,6 +365,13 @@ struct TripleArgs {
     uint8_t *doneOut;                // must start from the same state)
     unsigned long long *fusedHits;
     unsigned long long *maxRecords;   // largest number of candidate records of one guide (diagnostics)
+    // guides with more hits than a CTA's record list holds (maxDist 5-6, repeat families), fused mode on an index in text
+    // order: the CTA keeps such a guide's hits as 64-bit sort keys in its own chunks of this buffer, sorts them there and
+    // finishes the guide itself (heavy_finish) -- nullptr: such guides go through the general pipeline instead
+    uint64_t *heavyKeys;
+    unsigned long long *heavyCount;   // keys handed out so far (the launch is repeated with a larger buffer if > heavyCap)
+    uint64_t heavyCap;
+    unsigned long long *heavyHits;    // hits finished this way (statistics)
 };
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
@@ -375,14 +383,31 @@ __host__ __device__ constexpr uint64_t triple_resp_pack(uint32_t e0)
 }
 constexpr uint64_t kRespLo = triple_resp_pack(0), kRespHi = triple_resp_pack(16);
 
+// buckets with more entries than their block holds (~1 % of the visits at human scale) are noted during the scan and
+// finished by the whole CTA afterwards: two dependent loads in the middle of a warp's round stall the other 31 lanes
+constexpr uint32_t kTripleOvfCap = 64;
+constexpr uint32_t kTripleLongCap = 16;      // of those, buckets whose remainder is long enough for the whole CTA to share
+constexpr uint32_t kTripleLongBucket = 512;  // entries
+constexpr uint32_t kHeavyChunks = 23;        // 512 * (2^23 - 1) keys: more than any buffer holds
+
 // CTA-wide state of one guide's scan
 struct TripleShared {
     uint32_t key[kTripleCount], res[kTripleCount];   // the guide's bucket key / residual (both halves) per triple
     uint4 mask[kTripleCount][4];  // bit-sliced scan: word p = all ones when bit p of the guide's residual is set
     uint32_t count[2];            // entries / visits of this CTA (native 32-bit shared-memory atomics)
-    uint2 hits[kTripleHitCap];    // candidate records (record_y)
+    union {
+        uint2 hits[kTripleHitCap];    // candidate records (record_y)
+        uint32_t radix[4][256];       // heavy_finish: per-warp digit counters of the radix sort (the records are keys by then)
+    };
+    // a heavy guide's sort keys live in chunks of TripleArgs::heavyKeys: chunk k holds 512 << k keys
+    uint64_t chunkBase[kHeavyChunks];
+    uint32_t heavyChunks, heavyLen, heavyBroken;
+    uint32_t nLong;
+    uint16_t longList[kTripleLongCap];
     uint32_t nHits, nKept;
     uint32_t flushed;             // the guide's records were flushed to the general pipeline's buffer at least once
+    uint32_t nOvf;                // visits whose bucket has more entries than its block holds: noted, finished after the loop
+    uint16_t ovf[kTripleOvfCap];
     unsigned long long base;
 };
 
@@ -397,7 +422,7 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
         for (int p = 0; p < 16; p++) m[p] = 0u - ((r >> p) & 1u);
     }
     if (threadIdx.x < 2) sh.count[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { sh.nHits = 0; sh.nKept = 0; sh.flushed = 0; }
+    if (threadIdx.x == 0) { sh.nHits = 0; sh.nKept = 0; sh.flushed = 0; sh.nOvf = 0; sh.nLong = 0; sh.heavyChunks = 0; sh.heavyLen = 0; sh.heavyBroken = 0; }
     __syncthreads();
 }
 
@@ -520,10 +545,238 @@ __device__ __forceinline__ void triple_flush(const TripleArgs &a, TripleShared &
     __syncthreads();
 }
 
-// 8 residuals of one 16-byte vector against the guide's; `valid` masks the slots that belong to the bucket
-template <class RecX>
-__device__ __forceinline__ void triple_vector(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t gg,
-                                              const uint4 &r, uint32_t valid, RecX recX, uint32_t recFlag)
+// Shared memory of the scan kernels: the scan state; the grouping arrays of the fused tail reuse it once every
+// thread has taken its hits out.
+struct TripleSmem {
+    union {
+        TripleShared scan;
+        uint64_t group[kScoreGroupWords];
+    };
+    ScoreShared score;
+};
+// ... without the fused tail: the scan state alone.  Less shared memory per SM is more L1, and the L1 holds the lines
+// of the loads in flight: the scan is measurably faster with it (DESIGN.md 4).
+struct TripleSmemScan {
+    TripleShared scan;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Heavy guides (more hits than the CTA's record list holds: maxDist 5-6, dense repeat families), finished
+// inside the scan kernel.  ref isslScoreOfftargets.cpp:330-344 fixes the accumulation order -- slice, then
+// ascending site id, which on an index in text order is ascending site text -- and :466-502 makes the printed
+// value depend on it, so the guide's hits have to be sorted before they are added up.  Whenever the record list
+// fills, all threads turn the records into 64-bit keys
+//     ordering slice << 60 | site text rank (40 bits) << 20 | occurrences (20 bits, saturating)
+// and append them to the guide's own chunks of a global buffer (chunk k holds 512 << k keys, handed out by one
+// atomic per chunk); when the scan is done the CTA sorts them with a least-significant-digit radix sort over the
+// 44 ordering bits (six stable passes, ping-pong between the chunks and one contiguous range; each warp owns a
+// quarter of the keys and its own digit counters, so a pass costs five barriers whatever the number of keys;
+// passes in which all keys share the digit are skipped) and then walks them in order: 128 keys at a time are
+// turned back into sites and scored by all threads (ref :392-461) and one thread adds the contributions up one
+// rounded sum at a time with the reference's early exit.  No id is ever looked up (except for the occurrence
+// count of the few sites that occur more than once), no device-wide sort, no further kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kHeavyOccMax = 0xFFFFFu;   // occurrence counts from here on are looked up again when the hit is scored
+
+__device__ __forceinline__ uint64_t heavy_key(uint32_t slice, uint64_t site, uint32_t occ)
+{
+    return ((uint64_t)slice << 60) | (site_text_key(site, 20) << 20) | (uint64_t)min(occ, kHeavyOccMax);
+}
+
+// inverse of site_text_key for 20-base sites
+__device__ __forceinline__ uint64_t text_key_site(uint64_t textKey)
+{
+    uint64_t r = textKey << 24;
+    r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+    return __brevll(r);
+}
+
+// where key number L of the guide lives
+__device__ __forceinline__ uint64_t heavy_slot(const TripleShared &sh, uint32_t L)
+{
+    const uint32_t unit = (L >> 9) + 1u, k = 31u - (uint32_t)__clz(unit);
+    return sh.chunkBase[k] + (L - (((1u << k) - 1u) << 9));
+}
+
+// room for the guide's keys [0, newLen): called by all threads
+__device__ __forceinline__ void heavy_reserve(const TripleArgs &a, TripleShared &sh, uint32_t newLen)
+{
+    if (threadIdx.x == 0) {
+        while ((((1u << sh.heavyChunks) - 1u) << 9) < newLen && sh.heavyChunks < kHeavyChunks) {
+            const uint32_t k = sh.heavyChunks;
+            const unsigned long long base = atomicAdd(a.heavyCount, 512ull << k);
+            if (base + (512ull << k) > a.heavyCap) sh.heavyBroken = 1;   // the launch is repeated with a larger buffer
+            sh.chunkBase[k] = base;
+            sh.heavyChunks = k + 1;
+        }
+    }
+    __syncthreads();
+}
+
+// site, occurrences and ordering slice of a kept record
+__device__ __forceinline__ void record_resolve(const TripleArgs &a, uint2 h, uint64_t g, uint32_t &slice, uint64_t &site, uint32_t &occ)
+{
+    record_keep(h, slice);
+    site = hit_site(a.tv, h);
+    occ = 1;
+    if (site == kSiteUnknown) {
+        const uint32_t idRaw = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
+        site = __ldg(a.sp.sig + (idRaw & (a.tv.occFlag ? 0x7FFFFFFFu : ~0u)));
+        occ = occ_of(a.sp, idRaw);
+    } else if (h.y & kRecMulti) {
+        occ = occ_of(a.sp, __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)));
+    }
+    if (a.tv.nibbleOrder) slice = order_slice(a.tv, site ^ g, slice);
+}
+
+// the record list becomes keys at the end of the guide's chunks.  Called by all threads.
+__device__ __forceinline__ void heavy_flush(const TripleArgs &a, TripleShared &sh, uint64_t g)
+{
+    const uint32_t n = min(sh.nHits, kTripleHitCap), len = sh.heavyLen;
+    heavy_reserve(a, sh, len + n);
+    if (!sh.heavyBroken)
+        for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
+            uint32_t slice, occ;
+            uint64_t site;
+            record_resolve(a, sh.hits[j], g, slice, site, occ);
+            a.heavyKeys[heavy_slot(sh, len + j)] = heavy_key(slice, site, occ);
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) { sh.heavyLen = len + n; sh.nHits = 0; sh.flushed = 1; }
+    __syncthreads();
+}
+
+// occurrences of a site known only by its text: its id is its rank in sig[] (the index is in text order)
+__device__ __forceinline__ uint32_t occ_by_text(const ScoreParams &sp, uint64_t textKey)
+{
+    uint64_t lo = 0, hi = sp.nSites;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (site_text_key(__ldg(sp.sig + mid), 20) < textKey) lo = mid + 1; else hi = mid;
+    }
+    return lo < sp.nSites ? __ldg(sp.occ + lo) : 1u;
+}
+
+// sort the guide's keys and finish the guide (see above).  Called by all threads; the record list is empty.
+__device__ __forceinline__ void heavy_finish(const TripleArgs &a, TripleSmem &sm, uint32_t guide, uint64_t g)
+{
+    TripleShared &sh = sm.scan;
+    ScoreShared &ss = sm.score;
+    const uint32_t n = sh.heavyLen;
+    if (threadIdx.x == 0) {
+        const unsigned long long base = atomicAdd(a.heavyCount, (unsigned long long)n);   // the other half of the ping-pong
+        if (base + n > a.heavyCap) sh.heavyBroken = 1;
+        sh.base = base;
+    }
+    __syncthreads();
+    if (sh.heavyBroken) return;   // state "as before this wave" is already in place; the launch will be repeated
+    uint64_t *const flat = a.heavyKeys + sh.base;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t quarter = ((n + 127u) >> 7) << 5;                     // keys per warp, a multiple of 32
+    const uint32_t lo = min(n, warp * quarter), hi = min(n, lo + quarter);
+    uint32_t cur = 0;                                                    // 0: the keys are in the chunks, 1: in `flat`
+    auto load = [&](uint32_t c, uint32_t L) { return c ? flat[L] : a.heavyKeys[heavy_slot(sh, L)]; };
+    for (int pass = 0; pass < 6; pass++) {
+        const uint32_t shift = 20u + 8u * pass;
+        for (uint32_t i = threadIdx.x; i < 1024; i += kTripleThreads) (&sh.radix[0][0])[i] = 0;
+        __syncthreads();
+        for (uint32_t L0 = lo; L0 < hi; L0 += 32) {                      // digit counts of this warp's quarter
+            const uint32_t L = L0 + lane;
+            const bool valid = L < hi;
+            const uint32_t d = valid ? (uint32_t)(load(cur, L) >> shift) & 0xFFu : 256u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == (uint32_t)__ffs(peers) - 1u) sh.radix[warp][d] += (uint32_t)__popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive scan over (digit, warp): thread t owns digits 2t and 2t + 1
+        uint32_t c[2][4], tot = 0;
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) { c[q][w] = sh.radix[w][2 * threadIdx.x + q]; tot += c[q][w]; }
+        const bool single = (c[0][0] + c[0][1] + c[0][2] + c[0][3] == n) || (c[1][0] + c[1][1] + c[1][2] + c[1][3] == n);
+        uint32_t incl = tot;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        if (lane == 31) ss.grp[warp] = incl;
+        if (__syncthreads_or(single)) continue;                          // all keys share this digit: nothing to move
+        uint32_t run = incl - tot;
+        for (uint32_t w = 0; w < warp; w++) run += ss.grp[w];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) { sh.radix[w][2 * threadIdx.x + q] = run; run += c[q][w]; }
+        __syncthreads();
+        for (uint32_t L0 = lo; L0 < hi; L0 += 32) {                      // stable scatter, 32 keys of the quarter at a time
+            const uint32_t L = L0 + lane;
+            const bool valid = L < hi;
+            const uint64_t key = valid ? load(cur, L) : 0ull;
+            const uint32_t d = valid ? (uint32_t)(key >> shift) & 0xFFu : 256u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            uint32_t dst = 0;
+            if (valid) dst = sh.radix[warp][d];
+            __syncwarp();
+            if (valid && rank == 0) sh.radix[warp][d] = dst + (uint32_t)__popc(peers);
+            __syncwarp();
+            if (valid) {
+                if (cur) a.heavyKeys[heavy_slot(sh, dst + rank)] = key; else flat[dst + rank] = key;
+            }
+        }
+        __syncthreads();
+        cur ^= 1u;
+    }
+    // ordered accumulation (ref :394, :460, :466-502)
+    double mit = 0.0, cfd = 0.0;
+    bool stop = false;
+    if (threadIdx.x == 0) { mit = a.sp.totMit[guide]; cfd = a.sp.totCfd[guide]; ss.kept = 0; }
+    for (uint32_t w0 = 0; w0 < n; w0 += kTripleThreads) {
+        const uint32_t j = w0 + threadIdx.x;
+        if (j < n) {
+            const uint64_t key = load(cur, j);
+            const uint64_t textKey = (key >> 20) & 0xFFFFFFFFFFull;
+            uint32_t occ = (uint32_t)key & kHeavyOccMax;
+            if (occ == kHeavyOccMax) occ = occ_by_text(a.sp, textKey);
+            double cm, cc;
+            int dist;
+            hit_contrib(a.sp.tb, g, text_key_site(textKey), occ, a.sp.calcMit, a.sp.calcCfd, cm, cc, dist);
+            ss.mit[threadIdx.x] = cm; ss.cfd[threadIdx.x] = cc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t m = min((uint32_t)kTripleThreads, n - w0);
+            if (!a.sp.checkExit) {
+#pragma unroll 8
+                for (uint32_t i = 0; i < m; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
+            } else {
+                for (uint32_t i = 0; i < m && !stop; i++) {
+                    mit = __dadd_rn(mit, ss.mit[i]);
+                    cfd = __dadd_rn(cfd, ss.cfd[i]);
+                    stop = exit_predicate(a.sp.method, mit, cfd, a.sp.maximumSum);
+                }
+                if (stop) ss.kept = 1;
+            }
+        }
+        __syncthreads();
+        if (ss.kept) break;
+    }
+    if (threadIdx.x == 0) {
+        a.totMitOut[guide] = mit; a.totCfdOut[guide] = cfd;
+        if (stop) a.doneOut[guide] = 1;
+        atomicAdd(a.fusedHits, (unsigned long long)n);
+        atomicAdd(a.heavyHits, (unsigned long long)n);
+    }
+}
+
+// 8 residuals of one 16-byte vector against the guide's; `valid` masks the slots that belong to the bucket.
+// NOSPILL (the scan variant that flushes full record lists): a hit that finds the list full is not sent to the general
+// pipeline; its slot is returned, and the caller tries again once the list has been flushed.
+template <bool NOSPILL = false, class RecX>
+__device__ __forceinline__ uint32_t triple_vector(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t gg,
+                                                  const uint4 &r, uint32_t valid, RecX recX, uint32_t recFlag)
 {
     const int budget = (int)(v.x >> 28);
     const uint32_t w0 = r.x ^ gg, w1 = r.y ^ gg, w2 = r.z ^ gg, w3 = r.w ^ gg;
@@ -540,11 +793,22 @@ __device__ __forceinline__ void triple_vector(const TripleArgs &a, TripleShared 
     pass &= valid;
     while (pass) {
         const uint32_t i = __ffs(pass) - 1;
-        pass &= pass - 1;
         const uint32_t ws = (i & 4u) ? ((i & 2u) ? w3 : w2) : ((i & 2u) ? w1 : w0);
         const uint32_t x16 = (ws >> ((i & 1u) * 16u)) & 0xFFFFu;
-        triple_push(a, sh, guide, make_uint2(recX(i), record_y(v, (uint32_t)((x16 & 0xFFu) == 0), (uint32_t)((x16 >> 8) == 0), recFlag)));
+        const uint2 h = make_uint2(recX(i), record_y(v, (uint32_t)((x16 & 0xFFu) == 0), (uint32_t)((x16 >> 8) == 0), recFlag));
+        if constexpr (NOSPILL) {
+            uint32_t slice;
+            if (record_keep(h, slice)) {
+                const uint32_t slot = atomicAdd(&sh.nHits, 1u);
+                if (slot >= kTripleHitCap) return pass;   // this slot and the ones after it: again after the flush
+                sh.hits[slot] = h;
+            }
+        } else {
+            triple_push(a, sh, guide, h);
+        }
+        pass &= pass - 1;
     }
+    return 0;
 }
 
 // bucket [start, end) of the contiguous copy, `lanes` consecutive lanes (this one is number `gl`) share it
@@ -564,24 +828,9 @@ __device__ __forceinline__ void triple_bucket(const TripleArgs &a, TripleShared 
     }
 }
 
-// Shared memory of the scan kernels: the scan state; the grouping arrays of the fused tail reuse it once every
-// thread has taken its hits out.
-struct TripleSmem {
-    union {
-        TripleShared scan;
-        uint64_t group[kScoreGroupWords];
-    };
-    ScoreShared score;
-};
-// ... without the fused tail: the scan state alone.  Less shared memory per SM is more L1, and the L1 holds the lines
-// of the loads in flight: the scan is measurably faster with it (DESIGN.md 4).
-struct TripleSmemScan {
-    TripleShared scan;
-};
-
 // end of the scan: finish the guide here (fused), or hand its hits on -- as a segment for k_score_segments or as
 // keys for the general pipeline
-template <bool FUSED, class Smem>
+template <bool FUSED, bool FLUSH = false, class Smem>
 __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, uint32_t guide, uint64_t g,
                                                 uint32_t entries, uint32_t visited)
 {
@@ -599,6 +848,13 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
     if (a.maxRecords && threadIdx.x == 0) atomicMax(a.maxRecords, (unsigned long long)nAll);
     if (a.fuse && threadIdx.x == 0) {   // state after this wave unless the fused tail below changes it
         a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 0;
+    }
+    if constexpr (FUSED && FLUSH) if (a.fuse && a.heavyKeys && sh.flushed) {
+        // a heavy guide: the rest of its records become keys too, then the CTA sorts and finishes it
+        __syncthreads();
+        if (nAll) heavy_flush(a, sh, g);
+        heavy_finish(a, sm, guide, g);
+        return;
     }
     if constexpr (FUSED) if (a.fuse && nAll <= kTripleHitCap && !sh.flushed) {
         if (nAll == 0) return;
@@ -725,9 +981,19 @@ __device__ __forceinline__ void bs_full_add(uint32_t a, uint32_t b, uint32_t c, 
     carry = (a & b) | (c & (a ^ b));
 }
 
-template <int SUBS, bool FUSED, bool FLUSH>
-__global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(const TripleArgs a)
+// LSUBS = sub-blocks per lane: 1 = SUBS lanes share a visit; 2 = a lane owns two neighbouring sub-blocks (at pitch 64:
+// the whole 128-byte block), i.e. eight 16-byte loads in flight per lane before the first adder tree runs.  Measured
+// SLOWER (5.2 against 3.8 ms per 100 000 guides: 64 registers, 8 CTAs per SM) -- the kernel is bound by instruction
+// issue and latency across warps, not by bytes in flight per lane; kept selectable (ISSL_TRIPLE_LSUBS) as evidence.
+//
+// FLUSH = the variant for guides with more hits than the record list holds (maxDist 5-6, repeat families): one barrier
+// per round of visits; a full list is emptied by all threads -- into the guide's own sort keys (heavy_flush; the guide is
+// then sorted and finished by this CTA, heavy_finish) or, without that buffer, into the general pipeline's -- and a hit
+// that found the list full is tried again afterwards: nothing is ever dropped and nothing leaves the CTA hit by hit.
+template <int SUBS, bool FUSED, bool FLUSH, int LSUBS = 1>
+__global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_triple_blocked(const TripleArgs a)
 {
+    static_assert(SUBS % LSUBS == 0, "a lane owns whole sub-blocks of one visit");
     const uint32_t guide = blockIdx.x;
     if (a.done && a.done[guide]) {
         if (a.fuse && threadIdx.x == 0) {
@@ -740,28 +1006,27 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
     const uint64_t g = a.guides[guide];
     triple_prologue(a, sh, g);
 
-    constexpr uint32_t V = kTripleThreads / SUBS;          // visits in flight per CTA
-    const uint32_t sub = threadIdx.x % SUBS, vslot = threadIdx.x / SUBS;
+    constexpr uint32_t LPV = SUBS / LSUBS;                  // lanes per visit
+    constexpr uint32_t V = kTripleThreads / LPV;            // visits in flight per CTA
+    const uint32_t sub0 = (threadIdx.x % LPV) * LSUBS, vslot = threadIdx.x / LPV;
     const uint32_t v0 = blockIdx.y * a.visitsPerCta, v1 = min(a.nVisits, v0 + a.visitsPerCta);
     uint32_t entries = 0, visited = 0;
     const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
+    const bool heavy = FUSED && FLUSH && a.heavyKeys != nullptr;
 
-    auto visit = [&](uint32_t e) {
-        const uint2 v = __ldg(visits + e);
-        const uint32_t t = (v.x >> 24) & 15u, key = sh.key[t] ^ (v.x & 0xFFFFFFu);
-        const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
-        // read once: streaming loads, so that the visit table and the offsets keep their place in L1
-        const uint4 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2), q3 = __ldcs(p + 3);
-        if (sub == 0) visited++;
-        if (q1.y & 1u) {   // more entries than the block holds (~1 % of the visits at human scale): the rest is contiguous
-            const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
-            const uint32_t start = __ldg(o) + SUBS * kSubEntries, end = __ldg(o + 1);
-            triple_bucket(a, sh, guide, v, start, end, sub, SUBS);
-            if (sub == 0) entries += end - start;
-        }
+    // a full record list is emptied by all threads (FLUSH only)
+    auto flush = [&]() {
+        if constexpr (FUSED) { if (heavy) { heavy_flush(a, sh, g); return; } }
+        triple_flush(a, sh, guide);
+    };
+
+    // one sub-block: 31 residuals against the guide's, hits recorded.  `allowed`: the slots still to be reported; returns
+    // the slots that found the record list full (FLUSH only: 0 otherwise, such hits go to the general pipeline one by one)
+    auto sub_block = [&](const uint2 v, const uint32_t t, const uint32_t key, const uint32_t sub, const uint4 q0, const uint4 q1,
+                         const uint4 q2, const uint4 q3, const uint32_t allowed, const bool count) -> uint32_t {
         const uint32_t cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
-        if (cnt == 0) return;
-        entries += cnt;
+        if (cnt == 0) return 0;
+        if (count) entries += cnt;
         const uint4 m0 = sh.mask[t][0], m1 = sh.mask[t][1], m2 = sh.mask[t][2], m3 = sh.mask[t][3];
         const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
         const uint32_t x2 = (q1.x ^ m1.x) | (q1.y ^ m1.y), x3 = (q1.z ^ m1.z) | (q1.w ^ m1.w);
@@ -791,7 +1056,7 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
         uint32_t keep = ~(pEx | qEx);
         if (kt != 1u)
             keep = ((kt & 1u) ? ~(pEx | qEx) : 0u) | ((kt & 2u) ? (pEx & ~qEx) : 0u) | ((kt & 4u) ? (~pEx & qEx) : 0u) | ((kt & 8u) ? (pEx & qEx) : 0u);
-        uint32_t pass = ~over & keep & ((2u << cnt) - 2u);   // slots 1..cnt hold residuals
+        uint32_t pass = ~over & keep & ((2u << cnt) - 2u) & allowed;   // slots 1..cnt hold residuals
         if (pass) {
             // one reservation for all hits of the sub-block; the sub-block's entries that occur more than once are its first ones
             uint32_t slot = atomicAdd(&sh.nHits, (uint32_t)__popc(pass));
@@ -799,6 +1064,7 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
             const uint32_t multiMask = (2u << multi) - 2u;
             const uint32_t y0 = ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | kRecBlocked;
             do {
+                if (FLUSH && slot >= kTripleHitCap) break;   // list full: these slots again after the flush
                 const uint32_t sl = __ffs(pass) - 1;
                 pass &= pass - 1;
                 // the entry's residual, gathered back from the 16 planes (issue slots are cheaper than DRAM lines): every
@@ -816,17 +1082,131 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
                 const uint32_t y = y0 | (((pEx >> sl) & 1u) << 9) | (((qEx >> sl) & 1u) << 10) | (((multiMask >> sl) & 1u) << 12) | (r << 16);
                 // entry number sub*31 + sl - 1 of the bucket, recorded as entry + 1
                 const uint2 h = make_uint2(key | ((sub * kSubEntries + sl) << 24), y);
-                if (slot < kTripleHitCap) sh.hits[slot] = h; else triple_spill(a, guide, h);
+                if (FLUSH || slot < kTripleHitCap) sh.hits[slot] = h; else triple_spill(a, guide, h);
                 slot++;
             } while (pass);
         }
+        return pass;
     };
+
+    // entries [start, end) of the contiguous copy (the rest of a bucket that does not fit its block), shared by `lanes`
+    // threads of which this one is number `gl`.  FLUSH: every thread of the CTA calls this the same number of times
+    // (it contains barriers); an empty range is fine.
+    auto scan_range = [&](const uint2 v, const uint32_t start, const uint32_t end, const uint32_t gl, const uint32_t lanes) {
+        const uint32_t t = (v.x >> 24) & 15u;
+        if constexpr (!FLUSH) {
+            if (start < end) triple_bucket(a, sh, guide, v, start, end, gl, lanes);
+        } else {
+            const uint32_t gg = sh.res[t];
+            const uint4 *__restrict__ base = reinterpret_cast<const uint4 *>(a.tv.res + (uint64_t)t * a.tv.stride);
+            uint32_t vi = (start >> 3) + gl, allowed = 0xFFu;
+            const uint32_t vecEnd = start < end ? ((end - 1) >> 3) + 1u : 0u;   // one past the last vector
+            for (;;) {
+                if (vi < vecEnd) {
+                    const uint4 r = __ldg(base + vi);
+                    const uint32_t first = vi << 3;
+                    const uint32_t lo = start > first ? start - first : 0u, hi = min(end - first, 8u);
+                    const uint32_t left = triple_vector<true>(a, sh, guide, v, gg, r, ((1u << hi) - 1u) & ~((1u << lo) - 1u) & allowed,
+                                                              [first](uint32_t i) { return first + i; }, 0u);
+                    if (left) allowed = left; else { vi += lanes; allowed = 0xFFu; }
+                }
+                if (__syncthreads_or(sh.nHits > kTripleFlushAt)) flush();
+                if (!__syncthreads_or(vi < vecEnd)) break;
+            }
+        }
+        if (gl == 0 && start < end) entries += end - start;
+    };
+
     for (uint32_t e0 = v0; e0 < v1; e0 += V) {   // the same number of rounds for every thread of the CTA
-        if (e0 + vslot < v1) visit(e0 + vslot);
-        if constexpr (FLUSH)
-            if (__syncthreads_or(sh.nHits > kTripleFlushAt)) triple_flush(a, sh, guide);
+        const uint32_t e = e0 + vslot;
+        uint2 v = make_uint2(0, 0);
+        uint32_t t = 0, key = 0;
+        uint4 q[LSUBS][4];
+        uint32_t left[LSUBS];
+        bool ovfPending = false;
+#pragma unroll
+        for (int s = 0; s < LSUBS; s++) left[s] = 0;
+        if (e < v1) {
+            v = __ldg(visits + e);
+            t = (v.x >> 24) & 15u; key = sh.key[t] ^ (v.x & 0xFFFFFFu);
+            const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub0) * 4;
+            // read once: streaming loads, so that the visit table and the offsets keep their place in L1
+#pragma unroll
+            for (int s = 0; s < LSUBS; s++) {
+                q[s][0] = __ldcs(p + 4 * s); q[s][1] = __ldcs(p + 4 * s + 1); q[s][2] = __ldcs(p + 4 * s + 2); q[s][3] = __ldcs(p + 4 * s + 3);
+            }
+            if (sub0 == 0) visited++;
+            if ((q[0][1].y & 1u) && sub0 == 0) {   // more entries than the block holds: noted for after the loop
+                const uint32_t slot = atomicAdd(&sh.nOvf, 1u);
+                if (slot < kTripleOvfCap) sh.ovf[slot] = (uint16_t)(e - v0);   // visit tables have fewer than 2^16 entries
+                else if constexpr (FLUSH) ovfPending = true;
+                else {   // list full (dense repeat families): this lane reads the rest alone
+                    const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
+                    scan_range(v, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), 0, 1);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < LSUBS; s++) left[s] = sub_block(v, t, key, sub0 + s, q[s][0], q[s][1], q[s][2], q[s][3], ~0u, true);
+        }
+        if constexpr (FLUSH) {
+            // a flush is due when the list is nearly full -- always the case when a hit found it full
+            while (__syncthreads_or(sh.nHits > kTripleFlushAt)) {
+                flush();
+#pragma unroll
+                for (int s = 0; s < LSUBS; s++)
+                    if (left[s]) left[s] = sub_block(v, t, key, sub0 + s, q[s][0], q[s][1], q[s][2], q[s][3], left[s], false);
+            }
+            // the list of noted buckets is full: finish them now (all threads), so that none is ever skipped
+            while (__syncthreads_or(sh.nOvf >= kTripleOvfCap)) {
+                __syncthreads();
+                if (threadIdx.x == 0) sh.nOvf = 0;
+                for (uint32_t j = 0; j < kTripleOvfCap; j++) {
+                    const uint2 vo = __ldg(visits + v0 + sh.ovf[j]);
+                    const uint32_t to = (vo.x >> 24) & 15u;
+                    const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
+                    scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
+                }
+                __syncthreads();
+                if (ovfPending) {   // buckets that found the list full
+                    const uint32_t slot = atomicAdd(&sh.nOvf, 1u);
+                    if (slot < kTripleOvfCap) { sh.ovf[slot] = (uint16_t)(e - v0); ovfPending = false; }
+                }
+            }
+        }
     }
-    triple_epilogue<FUSED>(a, sm, guide, g, entries, visited);
+    __syncthreads();
+    if (sh.nOvf) {   // CTA-uniform: the buckets noted during the scan
+        const uint32_t nOvf = min(sh.nOvf, kTripleOvfCap);
+        // short remainders: sixteen buckets at a time, eight lanes each; long ones (repeat families) are noted once more
+        for (uint32_t j0 = 0; j0 < nOvf; j0 += kTripleThreads / 8) {
+            const uint32_t j = j0 + (threadIdx.x >> 3), gl = threadIdx.x & 7u;
+            uint2 vo = make_uint2(0, 0);
+            uint32_t start = 0, end = 0;
+            if (j < nOvf) {
+                vo = __ldg(visits + v0 + sh.ovf[j]);
+                const uint32_t to = (vo.x >> 24) & 15u;
+                const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
+                start = __ldg(o) + SUBS * kSubEntries; end = __ldg(o + 1);
+                uint32_t isLong = 0;
+                if (gl == 0 && end - start > kTripleLongBucket) {
+                    const uint32_t slot = atomicAdd(&sh.nLong, 1u);
+                    if (slot < kTripleLongCap) { sh.longList[slot] = sh.ovf[j]; isLong = 1; }
+                }
+                isLong = __shfl_sync(0xffu << (threadIdx.x & 24u), isLong, 0, 8);
+                if (isLong) end = start;
+            }
+            scan_range(vo, start, end, gl, 8);
+        }
+        __syncthreads();
+        const uint32_t nLong = min(sh.nLong, kTripleLongCap);
+        for (uint32_t j = 0; j < nLong; j++) {   // one bucket at a time, all threads
+            const uint2 vo = __ldg(visits + v0 + sh.longList[j]);
+            const uint32_t to = (vo.x >> 24) & 15u;
+            const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
+            scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
+        }
+    }
+    triple_epilogue<FUSED, FLUSH>(a, sm, guide, g, entries, visited);
 }
 
 // sliceWidth 4: the ordering slice of every general-pipeline key, from the site itself (ref :330-390: a hit is met

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ISSL_CUDA_ABI_VERSION 3
+#define ISSL_CUDA_ABI_VERSION 4
 
 typedef enum issl_status {
     ISSL_OK = 0,
@@ -107,6 +107,9 @@ typedef struct issl_stats {
     uint64_t streamed;         /* list entries actually read from HBM (each chunk once per guide GROUP;
                                   TRIPLE: entries of the sub-buckets visited)                        */
     uint64_t bucket_visits;    /* TRIPLE: (guide, sub-bucket) visits = bucket-offset pairs read; 0 otherwise */
+    uint64_t heavy_hits;       /* TRIPLE: hits of guides with more hits than a CTA's record list holds, sorted and
+                                  accumulated inside the scan kernel (ABI 4)                          */
+    uint64_t sorted_hits;      /* hits that went through the general pipeline's device-wide sort (ABI 4) */
 } issl_stats;
 
 typedef struct issl_index issl_index;     /* a parsed .issl image in host memory          */

@@ -325,13 +325,16 @@ def test_triple_layout_sub_bucket_scan(triple_max):
                                                        (0, "0", "0", None), (2, "0", "0", None), (2, "64", "1", None),
                                                        (1, "32", "1", None), (0, "64", "1", None),
                                                        (2, "64", "0", "3000"), (1, "64", "1", "3000"), (0, "32", "0", "3000"),
-                                                       (2, "64", "0", "noflag"), (1, "32", "1", "noflag"), (0, "64", "0", "noflag")])
+                                                       (2, "64", "0", "noflag"), (1, "32", "1", "noflag"), (0, "64", "0", "noflag"),
+                                                       (2, "32", "1", None), (2, "64", "1", "3000"), (2, "64", "1", "noflag"),
+                                                       (2, "64", "1", "noheavy"), (2, "0", "1", None)])
 def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     """With at least 148 x 16 guides in a batch every guide gets one CTA, and the scan's tails come into play: 2 = the
     CTA sorts, scores and accumulates the guide's hits itself (fused), 1 = per-guide segments finished by
-    k_score_segments, 0 = general pipeline; guides with more than 512 hits (dense families here) always take the
-    general pipeline, mixed with the others in one batch -- with flush = 1 through the scan variant that empties a
-    full record list in the middle of the scan.  Blocked (bit-sliced sub-blocks of 31/62 entries, with buckets that
+    k_score_segments, 0 = general pipeline; guides with more than 512 hits (dense families here) take the general
+    pipeline, mixed with the others in one batch -- except with fuse = 2 and flush = 1 on a blocked copy, where the
+    scan variant that empties a full record list in the middle of the scan keeps such a guide's hits as sort keys, and
+    the CTA sorts and finishes it too ("noheavy" switches that off).  Blocked (bit-sliced sub-blocks of 31/62 entries, with buckets that
     do not fit) and contiguous copies; with hit_cap the survivor buffers start far too small, so that every call is
     launched again after an overflow (the fused tail must then start from the same per-guide state).  Everything
     must stay bit-identical to the oracle, early exits included."""
@@ -353,6 +356,8 @@ def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
     os.environ["ISSL_TRIPLE_FLUSH"] = flush
     if hit_cap == "noflag":     # the path of indexes with >= 2^31 sites: no occurrence flag in the stored ids
         os.environ["ISSL_TRIPLE_OCCFLAG"] = "0"
+    elif hit_cap == "noheavy":
+        os.environ["ISSL_TRIPLE_HEAVY"] = "0"
     elif hit_cap:
         os.environ["ISSL_HIT_CAP"] = hit_cap
     try:
@@ -361,7 +366,9 @@ def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
         del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"], os.environ["ISSL_TRIPLE_FLUSH"]
         os.environ.pop("ISSL_HIT_CAP", None)
         os.environ.pop("ISSL_TRIPLE_OCCFLAG", None)
+        os.environ.pop("ISSL_TRIPLE_HEAVY", None)
     assert dev.info["triple_block_bytes"] == 2 * int(blocks)
+    in_kernel = fuse == 2 and flush == "1" and blocks != "0" and hit_cap != "noheavy"
     seen_big = False
     for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 5), ("mit", 0, 2), ("cfd", 20, 4)):
         want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
@@ -380,8 +387,59 @@ def test_triple_large_batch_tails(fuse, blocks, flush, hit_cap):
             per_guide = np.bincount(hits["guide"].astype(np.int64), minlength=guides.size)
             assert st["hits"] == per_guide.sum()
             seen_big = per_guide.max() > 512 and (per_guide <= 512).sum() > 1000
+            if in_kernel:      # every guide above the list's capacity was sorted and finished by its own CTA
+                assert st["sorted_hits"] == 0 and st["heavy_hits"] >= per_guide[per_guide > 512].sum()
+            elif fuse == 2:
+                assert st["heavy_hits"] == 0 and st["sorted_hits"] >= per_guide[per_guide > 512].sum()
     assert seen_big, "the fixture should mix guides above and below the per-CTA hit capacity"
     dev.close()
+
+
+@pytest.mark.parametrize("w,blocks", [(8, "64"), (8, "32"), (4, "64")])
+def test_heavy_guides_are_sorted_and_finished_inside_the_scan_kernel(w, blocks):
+    """Guides with thousands of hits (maxDist 5 and 6, families of near-copies with many exact duplicates): the scan's
+    flush variant turns full record lists into 64-bit sort keys (ordering slice, site text rank, occurrences), the CTA
+    radix-sorts them in its own chunks of global memory and accumulates them in the reference's order (ref
+    isslScoreOfftargets.cpp:330-344, :466-502) -- no device-wide sort.  Long bucket remainders (a family's root bucket
+    holds thousands of entries) are shared by the whole CTA.  Bit-identical to the oracle, early exits included; the
+    survivor buffers also start far too small once, so that the launch is repeated."""
+    text = td.make_offtargets(91, n_random=90_000, n_families=6, family_size=5000, max_sub_rate=0.07)
+    img = oracle.create_index(text, 20, w)
+    rng = np.random.default_rng(92)
+    roots = td.pack_guides(td.make_guides(93, text, n=300, frac_exact=1.0, frac_mut=0.0))
+    guides = np.concatenate([roots.repeat(7), rng.integers(0, 1 << 40, 300, dtype=np.uint64)])
+    for i in range(roots.size * 7):
+        for pos in rng.choice(20, size=int(rng.integers(0, 3)), replace=False):
+            guides[i] ^= np.uint64(int(rng.integers(1, 4)) << (2 * int(pos)))
+    assert guides.size >= 148 * 16
+    for hit_cap in (None, "5000"):
+        os.environ["ISSL_TRIPLE_BLOCKS"] = blocks
+        if hit_cap:
+            os.environ["ISSL_HIT_CAP"] = hit_cap
+        try:
+            dev = cb.Device.from_index(cb.Index(img), 0, "triple")
+        finally:
+            del os.environ["ISSL_TRIPLE_BLOCKS"]
+            os.environ.pop("ISSL_HIT_CAP", None)
+        if w == 4:
+            runs = (("and", 0, 4), ("or", 45, 4), ("avg", 70, 4))     # above maxDist 4 sliceWidth 4 takes its slice lists
+        elif hit_cap:
+            runs = (("and", 0, 5), ("or", 45, 5), ("avg", 70, 4))
+        else:
+            runs = (("and", 0, 5), ("and", 0, 6), ("or", 45, 5), ("avg", 70, 6), ("mit", 30, 4), ("cfd", 0, 4), ("and", 75, 4))
+        for method, thr, md in runs:
+            want = oracle.score(img, guides, md, thr, method, threads=0)
+            mit, cfd = dev.score(guides, md, thr, method)       # the first call on a handle learns that hits are many ...
+            mit, cfd = dev.score(guides, md, thr, method)       # ... and the second runs the flush variant
+            st = dev.stats
+            if method != "cfd":
+                assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (w, blocks, hit_cap, method, thr, md)
+            if method != "mit":
+                assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (w, blocks, hit_cap, method, thr, md)
+            if thr == 0:    # with an early exit fewer hits are found, and the handle may not expect heavy guides
+                assert st["sorted_hits"] == 0, (w, blocks, hit_cap, method, thr, md)
+                assert st["heavy_hits"] > 100 * 1000, (w, blocks, hit_cap, method, thr, md, st)
+        dev.close()
 
 
 @pytest.mark.parametrize("case", ["sorted", "sorted_ids", "shuffled", "w4_sorted", "w4_shuffled"])

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libissl_cuda.so does not export {n}"
     assert set(L._issl_symbols) == set(names), "binding.py and issl_cuda.h disagree"
-    assert L.issl_abi_version() == 3
+    assert L.issl_abi_version() == 4
 
 
 def test_format_lines_prints_what_printf_prints():

@@ -214,6 +214,155 @@ __global__ void __launch_bounds__(128, 10) k_variant(const VArgs a)
     if ((threadIdx.x & 31u) == 0 && acc) atomicAdd(a.sum, acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Asynchronous copies into a shared-memory ring instead of loads into registers (round 2: "a cp.async.bulk 128-B ring
+// with an mbarrier").  Both kernels do the bit-sliced compare of k_variant<HIT = 0> (hits are only counted), so their
+// times compare with its first line.
+//   k_ring_bulk    cp.async.bulk (the TMA unit's 1-D copy, SASS UBLKCP): every lane copies its visit's 128-byte block into
+//                  its slot of a per-warp stage (32 x 128 B), completion through one mbarrier per (warp, stage)
+//   k_ring_cpasync cp.async.cg 16 B (SASS LDGSTS.BYPASS): eight per lane and visit, chunk-major inside the warp's stage
+//                  (conflict-free writes and reads), completion through cp.async.wait_group
+// DEPTH stages per warp are in flight.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t compare_count(const uint4 *mask, uint32_t budget, const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3)
+{
+    const uint32_t cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
+    if (cnt == 0) return 0;
+    const uint4 m0 = mask[0], m1 = mask[1], m2 = mask[2], m3 = mask[3];
+    const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
+    const uint32_t x2 = (q1.x ^ m1.x) | (q1.y ^ m1.y), x3 = (q1.z ^ m1.z) | (q1.w ^ m1.w);
+    const uint32_t x4 = (q2.x ^ m2.x) | (q2.y ^ m2.y), x5 = (q2.z ^ m2.z) | (q2.w ^ m2.w);
+    const uint32_t x6 = (q3.x ^ m3.x) | (q3.y ^ m3.y), x7 = (q3.z ^ m3.z) | (q3.w ^ m3.w);
+    uint32_t sa, ca, sb, cb, sc, cc, t1, u1;
+    bs_full_add(x0, x1, x2, sa, ca); bs_full_add(x3, x4, x5, sb, cb); bs_full_add(x6, x7, sa, sc, cc);
+    const uint32_t s0 = sb ^ sc, cd = sb & sc;
+    bs_full_add(ca, cb, cc, t1, u1);
+    const uint32_t s1 = t1 ^ cd, u2 = t1 & cd, s2 = u1 ^ u2, s3 = u1 & u2;
+    const uint32_t b0 = 0u - (budget & 1u), b1 = 0u - ((budget >> 1) & 1u), b2 = 0u - ((budget >> 2) & 1u);
+    uint32_t over = s0 & ~b0;
+    over = (s1 & ~b1) | (~(s1 ^ b1) & over);
+    over = (s2 & ~b2) | (~(s2 ^ b2) & over);
+    over |= s3;
+    return (uint32_t)__popc(~over & ((2u << cnt) - 2u));
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(128) k_ring_bulk(const VArgs a)
+{
+    extern __shared__ __align__(128) uint8_t ring[];   // [4 warps][DEPTH][32 lanes][128 B]
+    __shared__ __align__(8) uint64_t bar[4][DEPTH];
+    __shared__ uint32_t key[10];
+    __shared__ uint4 mask[10][4];
+    __shared__ uint32_t nHits;
+    const uint64_t g = a.guides[blockIdx.x];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (threadIdx.x < 10) {
+        const uint32_t t = threadIdx.x;
+        key[t] = triple_key(g, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
+        const uint32_t r = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]);
+        uint32_t *m = reinterpret_cast<uint32_t *>(mask[t]);
+        for (int p = 0; p < 16; p++) m[p] = 0u - ((r >> p) & 1u);
+    }
+    if (threadIdx.x == 0) nHits = 0;
+    if (lane == 0)
+        for (int s = 0; s < DEPTH; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(&bar[warp][s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint8_t *mine = ring + (size_t)warp * DEPTH * 4096;
+    auto issue = [&](uint32_t round, uint32_t stage) {   // this lane's visit of the warp's round
+        const uint32_t e = round * 128 + threadIdx.x;
+        const uint32_t mb = smem_u32(&bar[warp][stage]);
+        if (e < a.nVisits) {
+            const uint2 v = __ldg(a.visits + e);
+            const uint32_t t = (v.x >> 24) & 15u, k = key[t] ^ (v.x & 0xFFFFFFu);
+            const uint4 *p = a.blk + (((uint64_t)t << 24) | k) * 8;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 128;" ::"r"(mb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+                         ::"r"(smem_u32(mine + stage * 4096 + lane * 128)), "l"(p), "r"(mb) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+        }
+    };
+    const uint32_t rounds = (a.nVisits + 127) / 128;
+    for (uint32_t r = 0; r < (uint32_t)DEPTH && r < rounds; r++) issue(r, r);
+    uint32_t hits = 0;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t stage = r % DEPTH, parity = (r / DEPTH) & 1u;
+        const uint32_t mb = smem_u32(&bar[warp][stage]);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+        const uint32_t e = r * 128 + threadIdx.x;
+        if (e < a.nVisits) {
+            const uint2 v = __ldg(a.visits + e);
+            const uint32_t t = (v.x >> 24) & 15u;
+            const uint4 *q = reinterpret_cast<const uint4 *>(mine + stage * 4096 + lane * 128);
+            hits += compare_count(mask[t], v.x >> 28, q[0], q[1], q[2], q[3]);
+            hits += compare_count(mask[t], v.x >> 28, q[4], q[5], q[6], q[7]);
+        }
+        __syncwarp();
+        if (r + DEPTH < rounds) issue(r + DEPTH, stage);
+    }
+    if (hits) atomicAdd(&nHits, hits);
+    __syncthreads();
+    if (threadIdx.x == 0 && nHits) atomicAdd(a.sum, (unsigned long long)nHits);
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(128) k_ring_cpasync(const VArgs a)
+{
+    extern __shared__ __align__(128) uint8_t ring[];   // [4 warps][DEPTH][8 chunks][32 lanes][16 B]
+    __shared__ uint32_t key[10];
+    __shared__ uint4 mask[10][4];
+    __shared__ uint32_t nHits;
+    const uint64_t g = a.guides[blockIdx.x];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (threadIdx.x < 10) {
+        const uint32_t t = threadIdx.x;
+        key[t] = triple_key(g, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
+        const uint32_t r = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]);
+        uint32_t *m = reinterpret_cast<uint32_t *>(mask[t]);
+        for (int p = 0; p < 16; p++) m[p] = 0u - ((r >> p) & 1u);
+    }
+    if (threadIdx.x == 0) nHits = 0;
+    __syncthreads();
+    uint8_t *mine = ring + (size_t)warp * DEPTH * 4096;
+    auto issue = [&](uint32_t round, uint32_t stage) {
+        const uint32_t e = round * 128 + threadIdx.x;
+        if (e < a.nVisits) {
+            const uint2 v = __ldg(a.visits + e);
+            const uint32_t t = (v.x >> 24) & 15u, k = key[t] ^ (v.x & 0xFFFFFFu);
+            const uint4 *p = a.blk + (((uint64_t)t << 24) | k) * 8;
+            const uint32_t dst = smem_u32(mine + stage * 4096 + lane * 16);
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 512), "l"(p + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const uint32_t rounds = (a.nVisits + 127) / 128;
+    for (uint32_t r = 0; r < (uint32_t)DEPTH; r++) issue(r, r);   // empty groups beyond the last round keep the count uniform
+    uint32_t hits = 0;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t stage = r % DEPTH;
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        const uint32_t e = r * 128 + threadIdx.x;
+        if (e < a.nVisits) {
+            const uint2 v = __ldg(a.visits + e);
+            const uint32_t t = (v.x >> 24) & 15u;
+            const uint4 *q = reinterpret_cast<const uint4 *>(mine + stage * 4096 + lane * 16);
+            hits += compare_count(mask[t], v.x >> 28, q[0], q[32], q[64], q[96]);
+            hits += compare_count(mask[t], v.x >> 28, q[128], q[160], q[192], q[224]);
+        }
+        issue(r + DEPTH, stage);
+    }
+    if (hits) atomicAdd(&nHits, hits);
+    __syncthreads();
+    if (threadIdx.x == 0 && nHits) atomicAdd(a.sum, (unsigned long long)nHits);
+}
+
 int main(int argc, char **argv)
 {
     const uint32_t n = argc > 1 ? (uint32_t)atol(argv[1]) : 100000u;
@@ -270,5 +419,37 @@ int main(int argc, char **argv)
     RUN(1, LD_CS, 1, 2, 3, 0); RUN(1, LD_CS, 1, 2, 3, 1); RUN(1, LD_CS, 1, 2, 3, 2); RUN(1, LD_CS, 1, 1, 3, 2);
     RUN(2, LD_CS, 1, 0, 0, 0); RUN(2, LD_CS, 1, 1, 0, 0); RUN(2, LD_CS, 1, 1, 3, 0); RUN(2, LD_CS, 1, 1, 3, 2);
     RUN(2, LD_NC, 1, 1, 3, 2); RUN(2, LD_CA, 1, 1, 3, 2);
+    RUN(0, LD_CS, 2, 0, 0, 0); RUN(1, LD_CS, 2, 1, 0, 2);
+
+#define RUN_RING(KERNEL, NAME, DEPTH)                                                                                          \
+    do {                                                                                                                       \
+        float ms = 0, best = 1e9f;                                                                                             \
+        int resident = 0;                                                                                                      \
+        const int smem = 4 * DEPTH * 4096;                                                                                     \
+        cudaFuncSetAttribute(KERNEL<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                                \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, KERNEL<DEPTH>, 128, smem);                                    \
+        for (int rep = 0; rep < 4; rep++) {                                                                                    \
+            cudaMemset(dsum, 0, 8);                                                                                            \
+            cudaEventRecord(e0);                                                                                               \
+            KERNEL<DEPTH><<<n, 128, smem>>>(a);                                                                                \
+            cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);                                  \
+            if (rep && ms < best) best = ms;                                                                                   \
+        }                                                                                                                      \
+        unsigned long long hsum = 0; cudaMemcpy(&hsum, dsum, 8, cudaMemcpyDeviceToHost);                                       \
+        printf("{\"ring\": \"%s\", \"depth\": %d, \"smem_kb_per_cta\": %d, \"ctas_per_sm\": %d, \"ms_per_100k\": %.3f, \"GB/s_blocks\": %.1f, " \
+               "\"hits\": %llu, \"error\": \"%s\"}\n", NAME, DEPTH, smem / 1024, resident, best * 1e5 / n, bytes / best / 1e6, hsum, \
+               cudaGetErrorString(cudaGetLastError()));                                                                        \
+        fflush(stdout);                                                                                                        \
+    } while (0)
+    {
+        cudaMemset(dsum, 0, 8);
+        k_variant<0, LD_CS, 1, 0, 0><<<n, 128>>>(a);
+        unsigned long long hsum = 0; cudaMemcpy(&hsum, dsum, 8, cudaMemcpyDeviceToHost);
+        printf("{\"ring\": \"none (registers)\", \"hits\": %llu}\n", hsum);
+    }
+    RUN_RING(k_ring_bulk, "cp.async.bulk 128 B per lane", 1); RUN_RING(k_ring_bulk, "cp.async.bulk 128 B per lane", 2);
+    RUN_RING(k_ring_bulk, "cp.async.bulk 128 B per lane", 3);
+    RUN_RING(k_ring_cpasync, "cp.async.cg 16 B x 8 per lane", 1); RUN_RING(k_ring_cpasync, "cp.async.cg 16 B x 8 per lane", 2);
+    RUN_RING(k_ring_cpasync, "cp.async.cg 16 B x 8 per lane", 3);
     return 0;
 }
