@@ -39,7 +39,7 @@ class _Stats(C.Structure):
     _fields_ = [("guides", C.c_uint64), ("candidates", C.c_uint64), ("hits", C.c_uint64),
                 ("scan_launches", C.c_uint64), ("launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("total_ms", C.c_double), ("early_exits", C.c_uint64), ("streamed", C.c_uint64),
-                ("bucket_visits", C.c_uint64), ("heavy_hits", C.c_uint64), ("sorted_hits", C.c_uint64)]
+                ("bucket_visits", C.c_uint64), ("heavy_hits", C.c_uint64), ("sorted_hits", C.c_uint64), ("heavy_ms", C.c_double)]
 
 
 _lib = None

@@ -52,6 +52,9 @@ struct issl_device {
     // ISSL_LAYOUT_TRIPLE
     DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites, totMit2, totCfd2, done2;
     uint64_t segCap = 0;
+    DBuf redo;                       // guides the warp-per-guide kernel left to the CTA-per-guide kernel
+    int tripleSmall = 1;             // ISSL_TRIPLE_SMALL=0: never use the warp-per-guide kernel
+    DBuf heavyDesc, heavyFlat;       // k_heavy_finish: one descriptor per heavy guide; the second half of its sort's ping-pong
     DBuf heavyKeys;                  // sort keys of the guides with more hits than a CTA's record list holds (heavy_finish)
     uint64_t heavyCap = 0;
     int tripleHeavy = 1;             // ISSL_TRIPLE_HEAVY=0: such guides go through the general pipeline (device-wide sort) instead
@@ -61,8 +64,8 @@ struct issl_device {
     int waves = 1;                   // ISSL_WAVES: how slices are cut into launches when there is an early exit (score_batch)
     int tripleFlush = -1;            // ISSL_TRIPLE_FLUSH: 1 / 0 force the scan variant that flushes full record lists; -1 automatic
     double lastHitsPerGuide = 0;     // of the previous scoring call on this handle
+    double lastHeavyFraction = 0;    // share of its hits that belonged to guides with more hits than a CTA's record list holds
     double lastExitFraction = -1.0;  // early exits / guides of the previous call that had an early exit to take; -1: none yet
-    int tripleLaneSubs = 1;          // ISSL_TRIPLE_LSUBS: sub-blocks per lane of the blocked scan (2: a lane owns the whole 128-byte block)
     int tripleFuse = 2;              // ISSL_TRIPLE_FUSE: 2 = guides are finished inside the scan kernel, 1 = by k_score_segments from
                                      // per-guide segments, 0 = everything through the general sort/score/accumulate kernels
     bool layoutAuto = false;         // TRIPLE was chosen by ISSL_LAYOUT_AUTO: fall back to RES32 if it does not fit
@@ -117,12 +120,12 @@ static int choose_layout(const issl_info &f, int requested, int *out)
 {
     const uint32_t w = (uint32_t)f.sliceWidth, kb = std::min<uint32_t>(w, 8);
     const bool res32ok = (w % 2 == 0) && (2 * f.seqLength >= kb) && (2 * f.seqLength - kb <= 32);
-    const bool tripleok = f.seqLength == 20 && ((w == 8 && f.sliceCount == 5) || (w == 4 && f.sliceCount == 10));
+    const bool tripleok = f.seqLength == 20 && ((w == 8 && f.sliceCount == 5) || (w == 4 && f.sliceCount == 10) || (w == 10 && f.sliceCount == 4));
     if (requested == ISSL_LAYOUT_AUTO) requested = tripleok ? ISSL_LAYOUT_TRIPLE : res32ok ? ISSL_LAYOUT_RES32 : ISSL_LAYOUT_SIG64;
     if (requested == ISSL_LAYOUT_RES32 && !res32ok)
         return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout RES32 needs an even slice width and 2*seqLength - min(width,8) <= 32");
     if (requested == ISSL_LAYOUT_TRIPLE && !tripleok)
-        return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout TRIPLE needs seqLength 20 and sliceWidth 8 or 4");
+        return issl_set_error(ISSL_ERR_UNSUPPORTED, "layout TRIPLE needs seqLength 20 and sliceWidth 8, 4 or 10");
     if (requested != ISSL_LAYOUT_RES32 && requested != ISSL_LAYOUT_SIG64 && requested != ISSL_LAYOUT_GATHER &&
         requested != ISSL_LAYOUT_TRIPLE)
         return issl_set_error(ISSL_ERR_ARG, "unknown layout %d", requested);
@@ -160,7 +163,7 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
     // TRIPLE keeps slice lists too (maxDist beyond what the sub-bucket scan serves, .issl export): RES32 for sliceWidth 8,
     // ids only (GATHER) for sliceWidth 4
-    const bool res32 = layout == ISSL_LAYOUT_RES32 || (layout == ISSL_LAYOUT_TRIPLE && f.sliceWidth == 8);
+    const bool res32 = layout == ISSL_LAYOUT_RES32 || (layout == ISSL_LAYOUT_TRIPLE && (f.sliceWidth == 8 || f.sliceWidth == 10));
     if (res32) { CKR(d->res32.exact(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
     if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.exact(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
     CKR(d->listStart.exact(d->nLists * 8));
@@ -266,6 +269,7 @@ static int build_triple(issl_device *d)
     if (pitch) {
         CKR(d->tripleBlk.exact(needBlk));   // every sub-block is written by k_triple_blocks
     }
+    const uint32_t perm10 = d->info.sliceWidth == 10 ? 1u : 0u;   // sliceWidth 10: copies of the permuted signatures (issl_triple.cuh)
     DBuf keysIn, keysOut, idsIn, tmp;
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
     size_t tb = 0;
@@ -274,10 +278,10 @@ static int build_triple(issl_device *d)
     CKR(tmp.ensure(tb));
     for (uint32_t t = 0; t < kTripleCount; t++) {
         uint32_t *ids = d->tripleIds.as<uint32_t>() + t * stride;
-        k_triple_keys<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), d->occ.as<uint32_t>(), N, t, keysIn.as<uint32_t>(), idsIn.as<uint32_t>());
+        k_triple_keys<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), d->occ.as<uint32_t>(), N, t, perm10, keysIn.as<uint32_t>(), idsIn.as<uint32_t>());
         // stable: inside a bucket the sites that occur more than once come first, ids ascending within either class
         CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(), ids, N, 0, 25, st));
-        k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, d->tripleRes.as<uint16_t>() + t * stride);
+        k_triple_residuals<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), ids, N, t, perm10, d->tripleRes.as<uint16_t>() + t * stride);
         if (occFlag) k_triple_flag_ids<<<blocks_for(N, 256), 256, 0, st>>>(d->occ.as<uint32_t>(), N, ids);
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
@@ -303,6 +307,7 @@ static int build_triple(issl_device *d)
     d->tv.stride = stride;
     d->tv.occFlag = occFlag ? 1u : 0u;
     d->tv.nibbleOrder = d->info.sliceWidth == 4 ? 1u : 0u;
+    d->tv.perm10 = perm10;
     d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = pitch;
     d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
@@ -340,7 +345,7 @@ static int new_device(int cuda_device, issl_device **out)
     if (const char *e = getenv("ISSL_HIT_CAP")) { const long v = atol(e); if (v > 0) d->firstHitCap = (uint64_t)v; }
     if (const char *e = getenv("ISSL_TRIPLE_FLUSH")) d->tripleFlush = atoi(e) != 0;
     if (const char *e = getenv("ISSL_TRIPLE_HEAVY")) d->tripleHeavy = atoi(e) != 0;
-    if (const char *e = getenv("ISSL_TRIPLE_LSUBS")) { const int v = atoi(e); if (v == 1 || v == 2) d->tripleLaneSubs = v; }
+    if (const char *e = getenv("ISSL_TRIPLE_SMALL")) d->tripleSmall = atoi(e) != 0;
     if (const char *e = getenv("ISSL_TRIPLE_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2) d->tripleFuse = v; }
     if (const char *e = getenv("ISSL_TRIPLE_MAXDIST")) {
         const long v = atol(e);
@@ -367,7 +372,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
+                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->heavyDesc, &d->heavyFlat, &d->redo, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
                     &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
@@ -878,7 +883,7 @@ struct HitSink {     // host-side collection for issl_score_hits
 struct EventTimer {
     issl_device *d;
     size_t used = 0;
-    std::vector<std::pair<size_t, size_t>> scanPairs;
+    std::vector<std::pair<size_t, size_t>> scanPairs, heavyPairs;
     int get(cudaEvent_t *ev)
     {
         if (used == d->evPool.size()) {
@@ -907,8 +912,10 @@ static int ensure_hit_buffers(issl_device *d, uint32_t n)
 static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
 {
     if (d->visitsDist != maxDist) {   // the visit table depends on maxDist only
-        std::vector<uint32_t> raw(issl_triple_visits(maxDist, nullptr, 0, nullptr));
-        issl_triple_visits(maxDist, raw.data(), raw.size(), d->waveStart);
+        const bool w4 = d->info.sliceWidth == 4;   // ten 2-base slices: also the buckets without an exact byte (maxDist >= 5)
+        std::vector<uint32_t> raw(w4 ? issl_triple_visits_w4(maxDist, nullptr, 0, nullptr) : issl_triple_visits(maxDist, nullptr, 0, nullptr));
+        if (w4) issl_triple_visits_w4(maxDist, raw.data(), raw.size(), d->waveStart);
+        else issl_triple_visits(maxDist, raw.data(), raw.size(), d->waveStart);
         static const uint8_t slices[10][5] = ISSL_TRIPLE_LAYOUT_INIT;
         std::vector<TripleVisit> v(raw.size());
         for (size_t i = 0; i < raw.size(); i++) {
@@ -922,6 +929,7 @@ static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
                 const uint32_t E = exact | ((c & 1u) << slices[t][3]) | ((c >> 1) << slices[t][4]);
                 if (issl_triple_resp(E) == t) keep |= 1u << c;
             }
+            if (exact == 0) keep = 1u;   // sliceWidth 4, no exact byte: triple 0 reports the entries both of whose residual slices differ
             v[i].x = raw[i];
             v[i].y = exact | ((uint32_t)slices[t][3] << 8) | ((uint32_t)slices[t][4] << 12) | (keep << 16);
         }
@@ -933,18 +941,16 @@ static int ensure_visits(issl_device *d, int maxDist, cudaStream_t st)
     return ISSL_OK;
 }
 
-// sub-blocks per lane of the blocked scan (ISSL_TRIPLE_LSUBS = 1 / 2)
-static int lane_subs(const issl_device *d) { return d->tv.pitch >= 64 ? d->tripleLaneSubs : 1; }
-
 // ISSL_LAYOUT_TRIPLE: survivors of slices [s0, s0 + ns) for the guides that are still active
 template <bool FUSED, bool FLUSH>
 static void launch_triple_scan_t(const issl_device *d, const TripleArgs &a, dim3 grid, cudaStream_t st)
 {
-    const bool two = lane_subs(d) == 2;   // a lane owns two sub-blocks: eight loads in flight (issl_triple.cuh)
-    if (d->tv.pitch == 32) k_scan_triple_blocked<1, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
-    else if (d->tv.pitch == 64 && two) k_scan_triple_blocked<2, FUSED, FLUSH, 2><<<grid, kTripleThreads, 0, st>>>(a);
+    const bool gates = d->tv.perm10 != 0;   // sliceWidth 10 (issl_triple.cuh)
+    if (d->tv.pitch == 32 && gates) k_scan_triple_blocked<1, FUSED, FLUSH, true><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 32) k_scan_triple_blocked<1, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 64 && gates) k_scan_triple_blocked<2, FUSED, FLUSH, true><<<grid, kTripleThreads, 0, st>>>(a);
     else if (d->tv.pitch == 64) k_scan_triple_blocked<2, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
-    else if (d->tv.pitch == 128 && two) k_scan_triple_blocked<4, FUSED, FLUSH, 2><<<grid, kTripleThreads, 0, st>>>(a);
+    else if (d->tv.pitch == 128 && gates) k_scan_triple_blocked<4, FUSED, FLUSH, true><<<grid, kTripleThreads, 0, st>>>(a);
     else if (d->tv.pitch == 128) k_scan_triple_blocked<4, FUSED, FLUSH><<<grid, kTripleThreads, 0, st>>>(a);
     else k_scan_triple<FUSED><<<grid, kTripleThreads, 0, st>>>(a);
 }
@@ -970,7 +976,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     unsigned long long *dc = d->counters.as<unsigned long long>();
     CKR(ensure_visits(d, maxDist, st));
     // the visit table is ordered by byte slice; sliceWidth 4 runs it in one piece (score_batch)
-    const bool nibble = d->info.sliceWidth == 4;
+    // ... nor does sliceWidth 10, where the slice a hit is met in depends on the guide's gates
+    const bool nibble = d->info.sliceWidth != 8;
     const uint32_t v0 = nibble ? d->waveStart[0] : d->waveStart[s0], v1 = nibble ? d->waveStart[5] : d->waveStart[std::min(s0 + ns, 5u)], nv = v1 - v0;
     CK(cudaMemsetAsync(dc, 0, 16 * 8, st));
     k_wave_candidates<<<blocks_for((uint64_t)n * ns, 256), 256, 0, st>>>(d->iv, dGuides, doneMask, n, s0, ns, dc + 0);
@@ -978,14 +985,16 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     *nHitsOut = 0;
     if (nv) {
         // enough CTAs to fill the machine even for a handful of guides
-        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 32 / lane_subs(d)) : kTripleThreads / 8;   // visits in flight per CTA
+        const uint32_t kOctets = d->tv.pitch ? kTripleThreads / (d->tv.pitch / 32) : kTripleThreads / 8;   // visits in flight per CTA
         uint32_t chunks = std::max<uint32_t>(1, (148u * 16u + n - 1) / n);
         chunks = std::min<uint32_t>(chunks, (nv + kOctets - 1) / kOctets);
         chunks = std::min<uint32_t>(chunks, 65535u);
         // finishing a guide where its hits are needs all of them in one CTA
         const bool inScan = ws.fuse == 2 && chunks == 1, fuse = ws.fuse == 1 && chunks == 1;
         // many hits per guide expected (large maxDist; the previous call saw repeat families): flush variant
-        const bool flush = d->tripleFlush == 1 || (d->tripleFlush < 0 && (maxDist >= 5 || d->lastHitsPerGuide > 0.6 * kTripleHitCap));
+        // (on average, or -- a genome with a few repeat families -- for a noticeable share of the hits)
+        const bool flush = d->tripleFlush == 1 || (d->tripleFlush < 0 && (maxDist >= 5 || d->lastHitsPerGuide > 0.6 * kTripleHitCap ||
+                                                                          d->lastHeavyFraction > 0.02));
         if (fuse) { CKR(d->segOff.ensure(n * 8ull)); CKR(d->segCnt.ensure(n * 4ull)); }
         if (inScan) { CKR(d->totMit2.ensure(n * 8ull)); CKR(d->totCfd2.ensure(n * 8ull)); CKR(d->done2.ensure(n)); }
         ScoreParams sp;
@@ -1006,15 +1015,18 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             if (d->firstHitCap) want = d->firstHitCap;   // ISSL_HIT_CAP: start small, so that tests reach the re-launch after an overflow
             d->heavyCap = std::max<uint64_t>(d->heavyCap, want);
         }
+        // a visit table of a few dozen buckets (maxDist <= 3): a warp per guide instead of a CTA per guide
+        const bool small = inScan && !flush && d->tripleSmall && nv <= kSmallMaxVisits && d->tv.pitch && d->tv.siteOrdered && !d->tv.perm10;
+        if (small) CKR(d->redo.ensure(n * 4ull));
         for (;;) {
             CKR(ensure_hit_buffers(d, n));
-            if (heavy) CKR(d->heavyKeys.ensure(d->heavyCap * 8));
+            if (heavy) { CKR(d->heavyKeys.ensure(d->heavyCap * 8)); CKR(d->heavyDesc.ensure((size_t)n * sizeof(HeavyDesc))); }
             if (fuse && d->segCap < d->hitCap) {
                 d->segCap = d->hitCap;
                 CKR(d->segKeys.ensure(d->segCap * 8)); CKR(d->segSites.ensure(d->segCap * 8));
             }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
-            CK(cudaMemsetAsync(dc + 4, 0, 48, st));
+            CK(cudaMemsetAsync(dc + 4, 0, 72, st));
             if (fuse) CK(cudaMemsetAsync(d->segCnt.p, 0, n * 4ull, st));
             TripleArgs a;
             a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<TripleVisit>() + v0;
@@ -1027,18 +1039,34 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             a.totMitOut = d->totMit2.as<double>(); a.totCfdOut = d->totCfd2.as<double>(); a.doneOut = d->done2.as<uint8_t>();
             a.fusedHits = dc + 7; a.maxRecords = dc + 2;
             a.heavyKeys = heavy ? d->heavyKeys.as<uint64_t>() : nullptr; a.heavyCount = dc + 8; a.heavyCap = heavy ? d->heavyCap : 0;
-            a.heavyHits = dc + 9;
+            a.heavyHits = dc + 9; a.heavyDesc = heavy ? d->heavyDesc.as<HeavyDesc>() : nullptr; a.heavyGuides = dc + 11;
+            a.nGuides = n; a.redo = small ? d->redo.as<uint32_t>() : nullptr; a.redoCount = dc + 10; a.guideList = nullptr;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));
             timer.scanPairs.push_back({timer.used - 2, timer.used - 1});
             CK(cudaEventRecord(e0, st));
-            launch_triple_scan(d, a, dim3(n, chunks), inScan, flush, st);
+            if (small) {
+                const dim3 sgrid((n + kTripleThreads / 32 - 1) / (kTripleThreads / 32));
+                if (d->tv.pitch == 32) k_scan_triple_small<1><<<sgrid, kTripleThreads, 0, st>>>(a);
+                else if (d->tv.pitch == 64) k_scan_triple_small<2><<<sgrid, kTripleThreads, 0, st>>>(a);
+                else k_scan_triple_small<4><<<sgrid, kTripleThreads, 0, st>>>(a);
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(d->hCounters + 10, dc + 10, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                d->stats.scan_launches += 1;
+                d->stats.launches += 1;
+                if (d->hCounters[10]) {   // the guides it left: repeat families, buckets that overflow their block
+                    a.guideList = d->redo.as<uint32_t>();
+                    launch_triple_scan(d, a, dim3((unsigned)d->hCounters[10], chunks), inScan, flush, st);
+                }
+            } else {
+                launch_triple_scan(d, a, dim3(n, chunks), inScan, flush, st);
+            }
             CK(cudaGetLastError());
             CK(cudaEventRecord(e1, st));
             CK(cudaMemcpyAsync(d->hCounters, dc, 16 * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            d->stats.scan_launches += 1;
-            d->stats.launches += 1;
+            if (!small || d->hCounters[10]) { d->stats.scan_launches += 1; d->stats.launches += 1; }
             if (d->hCounters[1] <= d->hitCap && d->hCounters[6] <= d->segCap && (!heavy || d->hCounters[8] <= d->heavyCap)) break;
             if (heavy && d->hCounters[8] > d->heavyCap) d->heavyCap = d->hCounters[8] + d->hCounters[8] / 4;
             if (d->hCounters[1] > d->hitCap) {
@@ -1051,6 +1079,22 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             }
         }
         *nHitsOut = d->hCounters[1];
+        if (heavy && d->hCounters[11]) {
+            // the guides whose hits did not fit their CTA's record list: sorted and finished by a CTA each (k_heavy_finish)
+            CKR(d->heavyFlat.ensure(d->hCounters[9] * 8));
+            HeavyArgs ha;
+            ha.desc = d->heavyDesc.as<HeavyDesc>(); ha.keys = d->heavyKeys.as<uint64_t>(); ha.flat = d->heavyFlat.as<uint64_t>();
+            ha.flatCount = dc + 12; ha.guides = dGuides; ha.sp = sp;
+            ha.totMitOut = d->totMit2.as<double>(); ha.totCfdOut = d->totCfd2.as<double>(); ha.doneOut = d->done2.as<uint8_t>();
+            cudaEvent_t h0, h1;
+            CKR(timer.get(&h0)); CKR(timer.get(&h1));
+            timer.heavyPairs.push_back({timer.used - 2, timer.used - 1});
+            CK(cudaEventRecord(h0, st));
+            k_heavy_finish<<<(unsigned)d->hCounters[11], kTripleThreads, 0, st>>>(ha);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h1, st));
+            d->stats.launches += 1;
+        }
         if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] wave %u+%u: max records per guide %llu, general-pipeline hits %llu, fused hits %llu, heavy keys %llu\n",
                                           s0, ns, d->hCounters[2], d->hCounters[1], d->hCounters[7], d->hCounters[8]);
         d->stats.streamed += d->hCounters[4];
@@ -1192,10 +1236,14 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
 
     // without early exit all slices go in one wave; with it, one wave per slice so that guides
     // which exited stop generating work (ref :501-502)
-    // sliceWidth 4 under TRIPLE: a whole byte is exact only up to maxDist 4, and the visit table's waves are by byte,
-    // not by the reference's 2-base slices: one wave, the early exit takes effect in the ordered accumulation
+    // sliceWidth 4 under TRIPLE: the visit table's waves are by byte, not by the reference's 2-base slices (and from maxDist 5
+    // on a hit need not match on any whole byte: issl_triple_visits_w4): one wave, the early exit takes effect in the ordered
+    // accumulation
+    // sliceWidth 10 under TRIPLE: the slice a hit is met in depends on the guide's gates (fifth base of a slice = A), not on
+    // the visit: one wave as well
     const bool nibble = d->layout == ISSL_LAYOUT_TRIPLE && d->info.sliceWidth == 4;
-    const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= (nibble ? std::min(d->tripleMaxDist, 4) : d->tripleMaxDist);
+    const bool gates = d->layout == ISSL_LAYOUT_TRIPLE && d->info.sliceWidth == 10;
+    const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= d->tripleMaxDist;
     // Waves: one slice at a time pays when many guides leave through the early exit (repeat families: their later slices
     // are never scanned); when few do, every further launch only costs.  So after each single-slice wave the guides that
     // left are counted, and once a wave sends fewer than a tenth of the batch through the exit all remaining slices go in
@@ -1203,7 +1251,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     // 1 = adaptive, 2 = always one slice per wave.)
     //   The previous call on the handle is a good predictor: if fewer than a third of its guides left early, this one
     // starts as one launch right away.
-    const bool oneWave = !checkExit || (useTriple && nibble) || d->waves == 0 ||
+    const bool oneWave = !checkExit || (useTriple && (nibble || gates)) || d->waves == 0 ||
                          (d->waves == 1 && d->lastExitFraction >= 0.0 && d->lastExitFraction < 0.33);
     uint64_t doneBefore = 0;
     bool merged = false;
@@ -1326,7 +1374,8 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     // hit): at maxDist 5-6, or on repeat-rich genomes, 2^20 guides can ask for more than is left beside the index.  The
     // batch is bounded by what the previous call saw, and a batch that still runs out of memory is halved and repeated.
     uint32_t batch = d->maxBatch;
-    if (d->lastHitsPerGuide > 512.0) {
+    // (cudaMemGetInfo takes milliseconds on a GPU this size: only asked when the call is large enough for the bound to matter)
+    if (d->lastHitsPerGuide > 512.0 && (double)n * d->lastHitsPerGuide * 40.0 > 8e9) {
         size_t freeB = 0, totalB = 0;
         if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
             const double held = (double)d->keysA.cap + (double)d->keysB.cap + (double)d->contribMit.cap + (double)d->contribCfd.cap + (double)d->heavyKeys.cap;
@@ -1354,7 +1403,7 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
             cudaGetLastError();
             cudaStreamSynchronize(st);
             for (DBuf *b : {&d->keysA, &d->keysB, &d->contribMit, &d->contribCfd, &d->sortTemp, &d->segKeys, &d->segSites, &d->hitId, &d->hitDist, &d->hitOcc,
-                            &d->heavyKeys})
+                            &d->heavyKeys, &d->heavyFlat})
                 b->release();
             d->hitCap = d->hitCapAuto = 0; d->segCap = 0; d->heavyCap = 0;
             d->stats = before;
@@ -1377,6 +1426,7 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     CK(cudaEventElapsedTime(&ms, t0, t1));
     d->stats.total_ms = ms;
     d->lastHitsPerGuide = n ? (double)d->stats.hits / (double)n : 0.0;
+    d->lastHeavyFraction = d->stats.hits ? (double)(d->stats.heavy_hits + d->stats.sorted_hits) / (double)d->stats.hits : 0.0;
     {
         const double maximumSum = (10000.0 - threshold * 100) / threshold;
         if (n && !(std::isnan(maximumSum) || (std::isinf(maximumSum) && maximumSum > 0)))
@@ -1385,6 +1435,10 @@ static int score_common(issl_device *d, const uint64_t *guides, bool guidesOnDev
     for (auto &pr : timer.scanPairs) {
         CK(cudaEventElapsedTime(&ms, d->evPool[pr.first], d->evPool[pr.second]));
         d->stats.scan_ms += ms;
+    }
+    for (auto &pr : timer.heavyPairs) {
+        CK(cudaEventElapsedTime(&ms, d->evPool[pr.first], d->evPool[pr.second]));
+        d->stats.heavy_ms += ms;
     }
     return ISSL_OK;
 }

@@ -355,7 +355,19 @@ extern "C" void issl_triple_layout(uint8_t slices_out[50], uint8_t resp_out[32])
         for (uint32_t E = 0; E < 32; E++) resp_out[E] = (uint8_t)issl_triple_resp(E);
 }
 
+static size_t triple_visits(int maxDist, int noExactByte, uint32_t *out, size_t cap, uint32_t waveStart[6]);
+
 extern "C" size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6])
+{
+    return triple_visits(maxDist, 0, out, cap, waveStart);
+}
+
+extern "C" size_t issl_triple_visits_w4(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6])
+{
+    return triple_visits(maxDist, 1, out, cap, waveStart);
+}
+
+static size_t triple_visits(int maxDist, int noExactByte, uint32_t *out, size_t cap, uint32_t waveStart[6])
 {
     std::vector<std::pair<uint32_t, uint32_t>> v;   // (wave, entry)
     if (maxDist > 7) { issl_set_error(ISSL_ERR_ARG, "issl_triple_visits: maxDist %d > 7", maxDist); maxDist = -1; }
@@ -379,6 +391,19 @@ extern "C" size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uin
             for (uint32_t xj = 1; xj < 256; xj++)
                 for (uint32_t xk = 1; xk < 256; xk++)
                     if (ham4(xj) + ham4(xk) <= D - 2) add(e, t, (xj << (8 * pj)) | (xk << (8 * pk)), D - ham4(xj) - ham4(xk));
+        }
+        if (noExactByte && D >= 5) {
+            // sliceWidth 4: a site may agree with the guide on a 2-base slice without agreeing on any whole byte -- every
+            // byte then carries a mismatch (maxDist >= 5).  Those sites belong to triple 0: all three key bytes differ, and
+            // so do both residual slices (at least two more mismatches).  Last wave: where the reference meets such a hit
+            // is worked out from the site itself (order_slice).
+            for (uint32_t x0 = 1; x0 < 256; x0++)
+                for (uint32_t x1 = 1; x1 < 256; x1++) {
+                    if (ham4(x0) + ham4(x1) > D - 3) continue;
+                    for (uint32_t x2 = 1; x2 < 256; x2++)
+                        if (ham4(x0) + ham4(x1) + ham4(x2) <= D - 2)
+                            add(4, 0, x0 | (x1 << 8) | (x2 << 16), D - ham4(x0) - ham4(x1) - ham4(x2));
+                }
         }
     }
     std::sort(v.begin(), v.end());

@@ -57,7 +57,7 @@ extern "C" int issl_score_multi(issl_device *const *devs, size_t n_devs, const u
             issl_last_stats(devs[k], &s);
             st[k].guides += s.guides; st[k].candidates += s.candidates; st[k].hits += s.hits; st[k].scan_launches += s.scan_launches;
             st[k].launches += s.launches; st[k].scan_ms += s.scan_ms; st[k].total_ms += s.total_ms; st[k].early_exits += s.early_exits;
-            st[k].streamed += s.streamed; st[k].bucket_visits += s.bucket_visits; st[k].heavy_hits += s.heavy_hits; st[k].sorted_hits += s.sorted_hits;
+            st[k].streamed += s.streamed; st[k].bucket_visits += s.bucket_visits; st[k].heavy_hits += s.heavy_hits; st[k].sorted_hits += s.sorted_hits; st[k].heavy_ms += s.heavy_ms;
         }
     };
     if (n_devs == 1) worker(0);
@@ -78,6 +78,7 @@ extern "C" int issl_score_multi(issl_device *const *devs, size_t n_devs, const u
         // devices run side by side: the call took as long as the busiest one
         stats_out->scan_ms = std::max(stats_out->scan_ms, st[k].scan_ms);
         stats_out->total_ms = std::max(stats_out->total_ms, st[k].total_ms);
+        stats_out->heavy_ms = std::max(stats_out->heavy_ms, st[k].heavy_ms);
     }
     return ISSL_OK;
 }

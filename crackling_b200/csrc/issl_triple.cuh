@@ -49,6 +49,13 @@ struct TripleView {
     // byte, so the same buckets are read; only the order differs -- the reference meets a hit first in the lowest
     // 2-base slice that matches exactly, which may lie below the lowest exact byte
     uint32_t nibbleOrder;
+    // sliceWidth 10 (four 5-base slices): the builder truncates slice values to 8 bits (ref isslCreateIndex.cpp:228), so
+    // list (i, v) holds the sites that agree with v on the slice's FIRST FOUR bases, and a guide only ever looks such a list
+    // up when the fifth base of its slice is A (its 10-bit slice value is then below 256; the lists above are empty).  The
+    // copies are therefore built from PERMUTED signatures -- bytes 0..3 = the four-base units of slices 0..3, byte 4 = the
+    // four fifth bases (sig_perm10) -- and a guide keeps a hit only if site and guide agree exactly on a unit whose gate
+    // (fifth base of the guide = A) is open; the lowest such unit is the slice the reference meets the hit in.
+    uint32_t perm10;
     // Site ids are ranks in the text order of the sites (extractOfftargets sorts its output and isslCreateIndex numbers
     // distinct lines as it reads them, ref isslCreateIndex.cpp:184-207): when the index really is sorted (checked once
     // at load, k_check_site_order), "ascending id" -- the order the reference accumulates the hits of one slice in,
@@ -70,16 +77,44 @@ __host__ __device__ __forceinline__ uint32_t triple_res(uint64_t sig, uint32_t p
     return (uint32_t)((sig >> (8 * p)) & 0xFFull) | ((uint32_t)((sig >> (8 * q)) & 0xFFull) << 8);
 }
 
+// sliceWidth 10: signature -> five bytes (units of slices 0..3, then the four fifth bases) and back
+__host__ __device__ __forceinline__ uint64_t sig_perm10(uint64_t sig)
+{
+    uint64_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        r |= ((sig >> (10 * i)) & 0xFFull) << (8 * i);
+        r |= ((sig >> (10 * i + 8)) & 3ull) << (32 + 2 * i);
+    }
+    return r;
+}
+__host__ __device__ __forceinline__ uint64_t sig_unperm10(uint64_t p)
+{
+    uint64_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        r |= ((p >> (8 * i)) & 0xFFull) << (10 * i);
+        r |= ((p >> (32 + 2 * i)) & 3ull) << (10 * i + 8);
+    }
+    return r;
+}
+// the units of a guide whose gate is open: fifth base of slice i = A
+__host__ __device__ __forceinline__ uint32_t gates10(uint64_t g)
+{
+    uint32_t m = 0;
+    for (int i = 0; i < 4; i++) m |= (uint32_t)(((g >> (10 * i + 8)) & 3ull) == 0) << i;
+    return m;
+}
+
 // ------------------------------------------------------------------------------------------------
 // construction (once per index): sort (key, id) per triple, then residuals + bucket offsets
 // ------------------------------------------------------------------------------------------------
 // sort key = bucket << 1 | "occurs once": inside a bucket the sites that occur more than once come first, ascending
 // id within either class (the sort is stable)
-__global__ void k_triple_keys(const uint64_t *sig, const uint32_t *occ, uint64_t n, uint32_t t, uint32_t *keys, uint32_t *ids)
+__global__ void k_triple_keys(const uint64_t *sig, const uint32_t *occ, uint64_t n, uint32_t t, uint32_t perm10, uint32_t *keys, uint32_t *ids)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = (triple_key(sig[i], c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]) << 1) | (occ[i] > 1 ? 0u : 1u);
+    const uint64_t s = perm10 ? sig_perm10(sig[i]) : sig[i];
+    keys[i] = (triple_key(s, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]) << 1) | (occ[i] > 1 ? 0u : 1u);
     ids[i] = (uint32_t)i;
 }
 
@@ -100,11 +135,12 @@ __global__ void k_check_site_order(const uint64_t *sig, uint64_t n, uint32_t L, 
     if (site_text_key(sig[i], L) >= site_text_key(sig[i + 1], L)) atomicAdd(violations, 1ull);
 }
 
-__global__ void k_triple_residuals(const uint64_t *sig, const uint32_t *sortedIds, uint64_t n, uint32_t t, uint16_t *res)
+__global__ void k_triple_residuals(const uint64_t *sig, const uint32_t *sortedIds, uint64_t n, uint32_t t, uint32_t perm10, uint16_t *res)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    res[i] = (uint16_t)triple_res(sig[sortedIds[i]], c_tripleSlices[t][3], c_tripleSlices[t][4]);
+    const uint64_t s = perm10 ? sig_perm10(sig[sortedIds[i]]) : sig[sortedIds[i]];
+    res[i] = (uint16_t)triple_res(s, c_tripleSlices[t][3], c_tripleSlices[t][4]);
 }
 
 // bit 31 of every stored id = the site occurs more than once (saves the occurrence lookup for all other hits)
@@ -336,6 +372,8 @@ struct TripleVisit {
                   // slice p / q (or not) is this triple's to report" (resp(E) == triple), worked out once on the host
 };
 
+struct HeavyDesc;
+
 struct TripleArgs {
     TripleView tv;
     const uint64_t *guides;
@@ -371,7 +409,15 @@ struct TripleArgs {
     uint64_t *heavyKeys;
     unsigned long long *heavyCount;   // keys handed out so far (the launch is repeated with a larger buffer if > heavyCap)
     uint64_t heavyCap;
-    unsigned long long *heavyHits;    // hits finished this way (statistics)
+    unsigned long long *heavyHits;    // hits finished this way (sum of the guides' key counts: the size of k_heavy_finish's second buffer)
+    HeavyDesc *heavyDesc;             // [guides] one per heavy guide, in order of completion
+    unsigned long long *heavyGuides;
+    // warp-per-guide kernel (k_scan_triple_small): guides it cannot finish (more hits than a warp's list holds, a long
+    // bucket remainder: repeat families) are listed in redo[]; the CTA-per-guide kernel then runs for exactly those (guideList)
+    uint32_t nGuides;
+    uint32_t *redo;
+    unsigned long long *redoCount;
+    const uint32_t *guideList;
 };
 
 // resp(E) packed 4 bits per E (E = 0 never occurs: every visit has an exact slice)
@@ -405,14 +451,19 @@ struct TripleShared {
     uint32_t nLong;
     uint16_t longList[kTripleLongCap];
     uint32_t nHits, nKept;
+    uint32_t guide;               // the guide's index (kept here, not in a register of every thread)
+    uint32_t gated;               // slices a hit may count as exactly matching: all five, or (sliceWidth 10) the guide's open gates
     uint32_t flushed;             // the guide's records were flushed to the general pipeline's buffer at least once
     uint32_t nOvf;                // visits whose bucket has more entries than its block holds: noted, finished after the loop
     uint16_t ovf[kTripleOvfCap];
     unsigned long long base;
 };
 
-__device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShared &sh, uint64_t g)
+__device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShared &sh, uint64_t gTrue, uint32_t guide)
 {
+    if (threadIdx.x == 33) sh.guide = guide;
+    const uint64_t g = a.tv.perm10 ? sig_perm10(gTrue) : gTrue;
+    if (threadIdx.x == 32) sh.gated = a.tv.perm10 ? gates10(gTrue) : 31u;
     if (threadIdx.x < kTripleCount) {
         const uint32_t t = threadIdx.x;
         sh.key[t] = triple_key(g, c_tripleSlices[t][0], c_tripleSlices[t][1], c_tripleSlices[t][2]);
@@ -441,13 +492,16 @@ __device__ __forceinline__ uint32_t record_y(uint2 v, uint32_t pExact, uint32_t 
 }
 
 // E = slices on which site and guide agree exactly; the record is a hit only in the triple responsible for E
-__device__ __forceinline__ bool record_keep(uint2 h, uint32_t &minE)
+// (gated: the slices that count -- sliceWidth 10: units whose gate is open; the hit is then met in the lowest of THOSE)
+__device__ __forceinline__ bool record_keep(uint2 h, uint32_t &minE, uint32_t gated = 31u)
 {
     const uint32_t t = h.y & 15u;
     const uint32_t E = ((h.y >> 4) & 31u) | (((h.y >> 9) & 1u) << c_tripleSlices[t][3]) | (((h.y >> 10) & 1u) << c_tripleSlices[t][4]);
     const uint32_t resp = (uint32_t)(((E & 16u) ? kRespHi : kRespLo) >> (4 * (E & 15u))) & 15u;
-    minE = __ffs(E) - 1;
-    return resp == t;
+    minE = __ffs(E & gated) - 1;
+    // E == 0: sliceWidth 4 only -- no byte matches exactly (order_slice finds the 2-base slice); such entries are triple 0's
+    if (E == 0) { minE = 5; return t == 0; }
+    return resp == t && (E & gated) != 0;
 }
 
 // key of the general pipeline: guide << 36 | slice << 32 | id, plus -- outside the bits that are sorted -- "occurs
@@ -470,9 +524,10 @@ __device__ __forceinline__ uint64_t hit_site(const TripleView &tv, uint2 h)
 {
     if (!(h.y & kRecBlocked)) return kSiteUnknown;
     const uint32_t t = h.y & 15u, key = h.x & 0xFFFFFFu, r = h.y >> 16;
-    return ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
-           ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
-           ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
+    const uint64_t s = ((uint64_t)(key & 0xFFu) << (8 * c_tripleSlices[t][0])) | ((uint64_t)((key >> 8) & 0xFFu) << (8 * c_tripleSlices[t][1])) |
+                       ((uint64_t)(key >> 16) << (8 * c_tripleSlices[t][2])) | ((uint64_t)(r & 0xFFu) << (8 * c_tripleSlices[t][3])) |
+                       ((uint64_t)(r >> 8) << (8 * c_tripleSlices[t][4]));
+    return tv.perm10 ? sig_unperm10(s) : s;
 }
 
 // the slice through which the reference meets a hit first (ref isslScoreOfftargets.cpp:330-390): the lowest exactly
@@ -499,13 +554,13 @@ template <bool CHECKED = false>
 __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 h)
 {
     uint32_t slice;
-    if (!CHECKED && !record_keep(h, slice)) return;   // found again, and reported, through the triple responsible for it
+    if (!CHECKED && !record_keep(h, slice, sh.gated)) return;   // found again, and reported, through the triple responsible for it
     const uint32_t slot = atomicAdd(&sh.nHits, 1u);
     if (slot < kTripleHitCap) {
         sh.hits[slot] = h;
     } else {   // rare (dense repeat families): straight to the general pipeline's buffer
         uint32_t minE;
-        if (!record_keep(h, minE)) return;
+        if (!record_keep(h, minE, sh.gated)) return;
         const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)];
         const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
         if (gs < a.hitCap) a.hitKeys[gs] = general_key(a.tv, guide, minE, id);
@@ -513,10 +568,10 @@ __device__ __forceinline__ void triple_push(const TripleArgs &a, TripleShared &s
 }
 
 // a record that found the CTA's list full (rare: dense repeat families): straight to the general pipeline's buffer
-__device__ __forceinline__ void triple_spill(const TripleArgs &a, uint32_t guide, uint2 h)
+__device__ __forceinline__ void triple_spill(const TripleArgs &a, uint32_t guide, uint2 h, uint32_t gated)
 {
     uint32_t minE;
-    if (!record_keep(h, minE)) return;
+    if (!record_keep(h, minE, gated)) return;
     const uint32_t id = a.tv.ids[(uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h)];
     const unsigned long long gs = atomicAdd(a.hitCount, 1ull);
     if (gs < a.hitCap) a.hitKeys[gs] = general_key(a.tv, guide, minE, id);
@@ -535,7 +590,7 @@ __device__ __forceinline__ void triple_flush(const TripleArgs &a, TripleShared &
     for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
         const uint2 h = sh.hits[j];
         uint32_t minE;
-        record_keep(h, minE);
+        record_keep(h, minE, sh.gated);
         const uint32_t id = __ldg(a.tv.ids + (uint64_t)(h.y & 15u) * a.tv.stride + hit_position(a.tv, h));
         const unsigned long long slot = sh.base + j;
         if (slot < a.hitCap) a.hitKeys[slot] = general_key(a.tv, guide, minE, id);
@@ -574,8 +629,33 @@ struct TripleSmemScan {
 // passes in which all keys share the digit are skipped) and then walks them in order: 128 keys at a time are
 // turned back into sites and scored by all threads (ref :392-461) and one thread adds the contributions up one
 // rounded sum at a time with the reference's early exit.  No id is ever looked up (except for the occurrence
-// count of the few sites that occur more than once), no device-wide sort, no further kernel.
+// count of the few sites that occur more than once) and there is no device-wide sort: the scan kernel leaves one
+// descriptor per heavy guide, and k_heavy_finish gives each of them a CTA.
 // ------------------------------------------------------------------------------------------------
+// what the scan kernel leaves behind for a heavy guide, and what k_heavy_finish works from
+struct HeavyDesc {
+    uint32_t guide, len, pad0, pad1;
+    uint64_t chunkBase[kHeavyChunks + 1];
+};
+struct HeavyArgs {
+    const HeavyDesc *desc;
+    uint64_t *keys;                   // the scan's key buffer (chunks)
+    uint64_t *flat;                   // one more range per guide, the other half of the sort's ping-pong: sum(len) keys in all
+    unsigned long long *flatCount;
+    const uint64_t *guides;
+    ScoreParams sp;                   // sp.totMit / totCfd: state before this wave
+    double *totMitOut, *totCfdOut;    // state after it
+    uint8_t *doneOut;
+};
+struct HeavySmem {
+    uint32_t radix[4][256];
+    uint64_t chunkBase[kHeavyChunks + 1];
+    double mit[kTripleThreads], cfd[kTripleThreads];
+    unsigned long long base;
+    uint32_t warpTot[4];
+    uint32_t stop;
+};
+
 constexpr uint32_t kHeavyOccMax = 0xFFFFFu;   // occurrence counts from here on are looked up again when the hit is scored
 
 __device__ __forceinline__ uint64_t heavy_key(uint32_t slice, uint64_t site, uint32_t occ)
@@ -592,10 +672,10 @@ __device__ __forceinline__ uint64_t text_key_site(uint64_t textKey)
 }
 
 // where key number L of the guide lives
-__device__ __forceinline__ uint64_t heavy_slot(const TripleShared &sh, uint32_t L)
+__device__ __forceinline__ uint64_t heavy_slot(const uint64_t *chunkBase, uint32_t L)
 {
     const uint32_t unit = (L >> 9) + 1u, k = 31u - (uint32_t)__clz(unit);
-    return sh.chunkBase[k] + (L - (((1u << k) - 1u) << 9));
+    return chunkBase[k] + (L - (((1u << k) - 1u) << 9));
 }
 
 // room for the guide's keys [0, newLen): called by all threads
@@ -614,9 +694,10 @@ __device__ __forceinline__ void heavy_reserve(const TripleArgs &a, TripleShared 
 }
 
 // site, occurrences and ordering slice of a kept record
-__device__ __forceinline__ void record_resolve(const TripleArgs &a, uint2 h, uint64_t g, uint32_t &slice, uint64_t &site, uint32_t &occ)
+__device__ __forceinline__ void record_resolve(const TripleArgs &a, uint2 h, uint64_t g, uint32_t gated, uint32_t &slice, uint64_t &site,
+                                               uint32_t &occ)
 {
-    record_keep(h, slice);
+    record_keep(h, slice, gated);
     site = hit_site(a.tv, h);
     occ = 1;
     if (site == kSiteUnknown) {
@@ -638,8 +719,8 @@ __device__ __forceinline__ void heavy_flush(const TripleArgs &a, TripleShared &s
         for (uint32_t j = threadIdx.x; j < n; j += kTripleThreads) {
             uint32_t slice, occ;
             uint64_t site;
-            record_resolve(a, sh.hits[j], g, slice, site, occ);
-            a.heavyKeys[heavy_slot(sh, len + j)] = heavy_key(slice, site, occ);
+            record_resolve(a, sh.hits[j], g, sh.gated, slice, site, occ);
+            a.heavyKeys[heavy_slot(sh.chunkBase, len + j)] = heavy_key(slice, site, occ);
         }
     __syncthreads();
     if (threadIdx.x == 0) { sh.heavyLen = len + n; sh.nHits = 0; sh.flushed = 1; }
@@ -657,82 +738,165 @@ __device__ __forceinline__ uint32_t occ_by_text(const ScoreParams &sp, uint64_t 
     return lo < sp.nSites ? __ldg(sp.occ + lo) : 1u;
 }
 
-// sort the guide's keys and finish the guide (see above).  Called by all threads; the record list is empty.
-__device__ __forceinline__ void heavy_finish(const TripleArgs &a, TripleSmem &sm, uint32_t guide, uint64_t g)
+// K2h: sort a heavy guide's keys and finish the guide (see above): one CTA per heavy guide, launched after the scan.  (Doing
+// this at the end of the scan CTA itself was measured: 40.3 ms per 100 000 guides at maxDist 5 instead of 30.6 ms for the
+// scan alone -- a chain of dependent L2 round trips during which the CTA requests no blocks; on its own, with a dozen
+// guides per SM in flight, the same work hides behind itself.)
+//   Two sorts.  Keys spread over many (slice, leading text bits) groups -- hits on a genome without dense repeat families --
+// take a counting sort over 16 x 64 groups followed by a rank inside the group (a handful of comparisons per key): three
+// sweeps over the keys.  When a group is large (a family of near-copies shares its leading bases) the rank would be
+// quadratic, and the keys take the radix sort: six stable passes, data-independent.  Either way every sweep requests four
+// keys per thread before it uses the first: the keys sit in L2, and a sweep is bound by that round trip, not by arithmetic.
+constexpr uint32_t kHeavyRankMax = 48;   // largest group the counting sort finishes by comparisons
+
+__global__ void __launch_bounds__(kTripleThreads, 12) k_heavy_finish(const HeavyArgs a)
 {
-    TripleShared &sh = sm.scan;
-    ScoreShared &ss = sm.score;
-    const uint32_t n = sh.heavyLen;
-    if (threadIdx.x == 0) {
-        const unsigned long long base = atomicAdd(a.heavyCount, (unsigned long long)n);   // the other half of the ping-pong
-        if (base + n > a.heavyCap) sh.heavyBroken = 1;
-        sh.base = base;
+    __shared__ HeavySmem sh;
+    const HeavyDesc &hd = a.desc[blockIdx.x];
+    const uint32_t guide = hd.guide, n = hd.len;
+    const uint64_t g = a.guides[guide];
+    if (threadIdx.x <= kHeavyChunks) sh.chunkBase[threadIdx.x] = hd.chunkBase[threadIdx.x];
+    if (threadIdx.x == 0) { sh.base = atomicAdd(a.flatCount, (unsigned long long)n); sh.stop = 0; }
+    __syncthreads();
+    uint64_t *const flat = a.flat + sh.base;
+    uint64_t *const chunks = a.keys;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t *const cnt = &sh.radix[0][0];
+    auto load = [&](uint32_t c, uint32_t L) { return c ? flat[L] : chunks[heavy_slot(sh.chunkBase, L)]; };
+    auto group_of = [](uint64_t key) { return (uint32_t)(key >> 60) << 6 | ((uint32_t)(key >> 54) & 63u); };
+    uint32_t cur = 0;                                                    // 0: the keys are in the chunks, 1: in `flat`
+
+    // ---- counting sort over (slice, six leading text bits), if no group is large
+    for (uint32_t i = threadIdx.x; i < 1024; i += kTripleThreads) cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t j0 = threadIdx.x; j0 < n; j0 += 4 * kTripleThreads) {
+        uint64_t k[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = j0 + u * kTripleThreads < n ? load(0, j0 + u * kTripleThreads) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j0 + u * kTripleThreads < n) atomicAdd(&cnt[group_of(k[u])], 1u);
     }
     __syncthreads();
-    if (sh.heavyBroken) return;   // state "as before this wave" is already in place; the launch will be repeated
-    uint64_t *const flat = a.heavyKeys + sh.base;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t quarter = ((n + 127u) >> 7) << 5;                     // keys per warp, a multiple of 32
-    const uint32_t lo = min(n, warp * quarter), hi = min(n, lo + quarter);
-    uint32_t cur = 0;                                                    // 0: the keys are in the chunks, 1: in `flat`
-    auto load = [&](uint32_t c, uint32_t L) { return c ? flat[L] : a.heavyKeys[heavy_slot(sh, L)]; };
-    for (int pass = 0; pass < 6; pass++) {
-        const uint32_t shift = 20u + 8u * pass;
-        for (uint32_t i = threadIdx.x; i < 1024; i += kTripleThreads) (&sh.radix[0][0])[i] = 0;
-        __syncthreads();
-        for (uint32_t L0 = lo; L0 < hi; L0 += 32) {                      // digit counts of this warp's quarter
-            const uint32_t L = L0 + lane;
-            const bool valid = L < hi;
-            const uint32_t d = valid ? (uint32_t)(load(cur, L) >> shift) & 0xFFu : 256u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == (uint32_t)__ffs(peers) - 1u) sh.radix[warp][d] += (uint32_t)__popc(peers);
-            __syncwarp();
-        }
-        __syncthreads();
-        // exclusive scan over (digit, warp): thread t owns digits 2t and 2t + 1
-        uint32_t c[2][4], tot = 0;
+    bool ranked;
+    {
+        uint32_t c[8], tot = 0, mx = 0;
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int w = 0; w < 4; w++) { c[q][w] = sh.radix[w][2 * threadIdx.x + q]; tot += c[q][w]; }
-        const bool single = (c[0][0] + c[0][1] + c[0][2] + c[0][3] == n) || (c[1][0] + c[1][1] + c[1][2] + c[1][3] == n);
+        for (int q = 0; q < 8; q++) { c[q] = cnt[8 * threadIdx.x + q]; tot += c[q]; mx = max(mx, c[q]); }
         uint32_t incl = tot;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)lane >= o) incl += up;
         }
-        if (lane == 31) ss.grp[warp] = incl;
-        if (__syncthreads_or(single)) continue;                          // all keys share this digit: nothing to move
-        uint32_t run = incl - tot;
-        for (uint32_t w = 0; w < warp; w++) run += ss.grp[w];
+        if (lane == 31) sh.warpTot[warp] = incl;
+        ranked = !__syncthreads_or(mx > kHeavyRankMax);
+        if (ranked) {
+            uint32_t run = incl - tot;
+            for (uint32_t w = 0; w < warp; w++) run += sh.warpTot[w];
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int w = 0; w < 4; w++) { sh.radix[w][2 * threadIdx.x + q] = run; run += c[q][w]; }
-        __syncthreads();
-        for (uint32_t L0 = lo; L0 < hi; L0 += 32) {                      // stable scatter, 32 keys of the quarter at a time
-            const uint32_t L = L0 + lane;
-            const bool valid = L < hi;
-            const uint64_t key = valid ? load(cur, L) : 0ull;
-            const uint32_t d = valid ? (uint32_t)(key >> shift) & 0xFFu : 256u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            uint32_t dst = 0;
-            if (valid) dst = sh.radix[warp][d];
-            __syncwarp();
-            if (valid && rank == 0) sh.radix[warp][d] = dst + (uint32_t)__popc(peers);
-            __syncwarp();
-            if (valid) {
-                if (cur) a.heavyKeys[heavy_slot(sh, dst + rank)] = key; else flat[dst + rank] = key;
-            }
+            for (int q = 0; q < 8; q++) { cnt[8 * threadIdx.x + q] = run; run += c[q]; }   // first position of every group
         }
         __syncthreads();
-        cur ^= 1u;
+    }
+    if (ranked) {
+        for (uint32_t j0 = threadIdx.x; j0 < n; j0 += 4 * kTripleThreads) {   // chunks -> flat, grouped; cnt[] ends up as end positions
+            uint64_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = j0 + u * kTripleThreads < n ? load(0, j0 + u * kTripleThreads) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (j0 + u * kTripleThreads < n) flat[atomicAdd(&cnt[group_of(k[u])], 1u)] = k[u];
+        }
+        __syncthreads();
+        for (uint32_t j0 = threadIdx.x; j0 < n; j0 += 2 * kTripleThreads) {   // flat -> chunks, every key at its rank
+            uint64_t k[2];
+            uint32_t base[2], end[2], r[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t j = j0 + u * kTripleThreads;
+                k[u] = j < n ? flat[j] : 0ull;
+                const uint32_t grp = group_of(k[u]);
+                base[u] = (j < n && grp) ? cnt[grp - 1] : 0u;
+                end[u] = j < n ? cnt[grp] : 0u;
+                r[u] = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                for (uint32_t q = base[u]; q < end[u]; q++) r[u] += (uint32_t)(flat[q] < k[u]);
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (j0 + u * kTripleThreads < n) chunks[heavy_slot(sh.chunkBase, base[u] + r[u])] = k[u];
+        }
+        __syncthreads();
+    } else {
+        // ---- radix sort: each warp owns a quarter of the keys and its own digit counters
+        const uint32_t quarter = ((n + 127u) >> 7) << 5;                     // keys per warp, a multiple of 32
+        const uint32_t lo = min(n, warp * quarter), hi = min(n, lo + quarter);
+        for (int pass = 0; pass < 6; pass++) {
+            const uint32_t shift = 20u + 8u * pass;
+            for (uint32_t i = threadIdx.x; i < 1024; i += kTripleThreads) cnt[i] = 0;
+            __syncthreads();
+            for (uint32_t L0 = lo; L0 < hi; L0 += 128) {                     // digit counts of this warp's quarter
+                uint64_t k[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) k[u] = L0 + 32 * u + lane < hi ? load(cur, L0 + 32 * u + lane) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool valid = L0 + 32 * u + lane < hi;
+                    const uint32_t d = valid ? (uint32_t)(k[u] >> shift) & 0xFFu : 256u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                    if (valid && lane == (uint32_t)__ffs(peers) - 1u) sh.radix[warp][d] += (uint32_t)__popc(peers);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // exclusive scan over (digit, warp): thread t owns digits 2t and 2t + 1
+            uint32_t c[2][4], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int w = 0; w < 4; w++) { c[q][w] = sh.radix[w][2 * threadIdx.x + q]; tot += c[q][w]; }
+            const bool single = (c[0][0] + c[0][1] + c[0][2] + c[0][3] == n) || (c[1][0] + c[1][1] + c[1][2] + c[1][3] == n);
+            uint32_t incl = tot;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += up;
+            }
+            if (lane == 31) sh.warpTot[warp] = incl;
+            if (__syncthreads_or(single)) continue;                          // all keys share this digit: nothing to move
+            uint32_t run = incl - tot;
+            for (uint32_t w = 0; w < warp; w++) run += sh.warpTot[w];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int w = 0; w < 4; w++) { sh.radix[w][2 * threadIdx.x + q] = run; run += c[q][w]; }
+            __syncthreads();
+            for (uint32_t L0 = lo; L0 < hi; L0 += 128) {                     // stable scatter, 32 keys of the quarter at a time
+                uint64_t k[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) k[u] = L0 + 32 * u + lane < hi ? load(cur, L0 + 32 * u + lane) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool valid = L0 + 32 * u + lane < hi;
+                    const uint32_t d = valid ? (uint32_t)(k[u] >> shift) & 0xFFu : 256u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                    const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+                    uint32_t dst = 0;
+                    if (valid) dst = sh.radix[warp][d];
+                    __syncwarp();
+                    if (valid && rank == 0) sh.radix[warp][d] = dst + (uint32_t)__popc(peers);
+                    __syncwarp();
+                    if (valid) {
+                        if (cur) chunks[heavy_slot(sh.chunkBase, dst + rank)] = k[u]; else flat[dst + rank] = k[u];
+                    }
+                }
+            }
+            __syncthreads();
+            cur ^= 1u;
+        }
     }
     // ordered accumulation (ref :394, :460, :466-502)
     double mit = 0.0, cfd = 0.0;
     bool stop = false;
-    if (threadIdx.x == 0) { mit = a.sp.totMit[guide]; cfd = a.sp.totCfd[guide]; ss.kept = 0; }
+    if (threadIdx.x == 0) { mit = a.sp.totMit[guide]; cfd = a.sp.totCfd[guide]; }
     for (uint32_t w0 = 0; w0 < n; w0 += kTripleThreads) {
         const uint32_t j = w0 + threadIdx.x;
         if (j < n) {
@@ -743,31 +907,29 @@ __device__ __forceinline__ void heavy_finish(const TripleArgs &a, TripleSmem &sm
             double cm, cc;
             int dist;
             hit_contrib(a.sp.tb, g, text_key_site(textKey), occ, a.sp.calcMit, a.sp.calcCfd, cm, cc, dist);
-            ss.mit[threadIdx.x] = cm; ss.cfd[threadIdx.x] = cc;
+            sh.mit[threadIdx.x] = cm; sh.cfd[threadIdx.x] = cc;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t m = min((uint32_t)kTripleThreads, n - w0);
             if (!a.sp.checkExit) {
 #pragma unroll 8
-                for (uint32_t i = 0; i < m; i++) { mit = __dadd_rn(mit, ss.mit[i]); cfd = __dadd_rn(cfd, ss.cfd[i]); }
+                for (uint32_t i = 0; i < m; i++) { mit = __dadd_rn(mit, sh.mit[i]); cfd = __dadd_rn(cfd, sh.cfd[i]); }
             } else {
                 for (uint32_t i = 0; i < m && !stop; i++) {
-                    mit = __dadd_rn(mit, ss.mit[i]);
-                    cfd = __dadd_rn(cfd, ss.cfd[i]);
+                    mit = __dadd_rn(mit, sh.mit[i]);
+                    cfd = __dadd_rn(cfd, sh.cfd[i]);
                     stop = exit_predicate(a.sp.method, mit, cfd, a.sp.maximumSum);
                 }
-                if (stop) ss.kept = 1;
+                if (stop) sh.stop = 1;
             }
         }
         __syncthreads();
-        if (ss.kept) break;
+        if (sh.stop) break;
     }
     if (threadIdx.x == 0) {
         a.totMitOut[guide] = mit; a.totCfdOut[guide] = cfd;
         if (stop) a.doneOut[guide] = 1;
-        atomicAdd(a.fusedHits, (unsigned long long)n);
-        atomicAdd(a.heavyHits, (unsigned long long)n);
     }
 }
 
@@ -776,8 +938,10 @@ __device__ __forceinline__ void heavy_finish(const TripleArgs &a, TripleSmem &sm
 // pipeline; its slot is returned, and the caller tries again once the list has been flushed.
 template <bool NOSPILL = false, class RecX>
 __device__ __forceinline__ uint32_t triple_vector(const TripleArgs &a, TripleShared &sh, uint32_t guide, uint2 v, uint32_t gg,
-                                                  const uint4 &r, uint32_t valid, RecX recX, uint32_t recFlag)
+                                                  const uint4 &r, uint32_t valid, RecX recX, uint32_t recFlag,
+                                                  uint32_t *nHits = nullptr, uint2 *hits = nullptr, uint32_t cap = 0, uint32_t gated = 31u)
 {
+    // NOSPILL: the record list is (nHits, hits, cap); otherwise the CTA's, through triple_push
     const int budget = (int)(v.x >> 28);
     const uint32_t w0 = r.x ^ gg, w1 = r.y ^ gg, w2 = r.z ^ gg, w3 = r.w ^ gg;
     const uint32_t f0 = w0 | (w0 >> 1), f1 = w1 | (w1 >> 1), f2 = w2 | (w2 >> 1), f3 = w3 | (w3 >> 1);
@@ -798,10 +962,10 @@ __device__ __forceinline__ uint32_t triple_vector(const TripleArgs &a, TripleSha
         const uint2 h = make_uint2(recX(i), record_y(v, (uint32_t)((x16 & 0xFFu) == 0), (uint32_t)((x16 >> 8) == 0), recFlag));
         if constexpr (NOSPILL) {
             uint32_t slice;
-            if (record_keep(h, slice)) {
-                const uint32_t slot = atomicAdd(&sh.nHits, 1u);
-                if (slot >= kTripleHitCap) return pass;   // this slot and the ones after it: again after the flush
-                sh.hits[slot] = h;
+            if (record_keep(h, slice, gated)) {
+                const uint32_t slot = atomicAdd(nHits, 1u);
+                if (slot >= cap) return pass;   // this slot and the ones after it: again after the flush
+                hits[slot] = h;
             }
         } else {
             triple_push(a, sh, guide, h);
@@ -853,7 +1017,17 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         // a heavy guide: the rest of its records become keys too, then the CTA sorts and finishes it
         __syncthreads();
         if (nAll) heavy_flush(a, sh, g);
-        heavy_finish(a, sm, guide, g);
+        if (!sh.heavyBroken) {   // (else the launch is repeated with a larger buffer)
+            if (threadIdx.x == 0) {
+                sh.base = atomicAdd(a.heavyGuides, 1ull);
+                atomicAdd(a.heavyHits, (unsigned long long)sh.heavyLen);
+                atomicAdd(a.fusedHits, (unsigned long long)sh.heavyLen);
+            }
+            __syncthreads();
+            HeavyDesc &hd = a.heavyDesc[sh.base];
+            if (threadIdx.x == 0) { hd.guide = guide; hd.len = sh.heavyLen; }
+            if (threadIdx.x <= kHeavyChunks) hd.chunkBase[threadIdx.x] = threadIdx.x < sh.heavyChunks ? sh.chunkBase[threadIdx.x] : 0ull;
+        }
         return;
     }
     if constexpr (FUSED) if (a.fuse && nAll <= kTripleHitCap && !sh.flushed) {
@@ -862,7 +1036,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
         score_guide(sm.score, sm.group, nAll, guide, g, a.sp, a.totMitOut, a.totCfdOut, a.doneOut,
                     [&](uint32_t j, uint32_t &slice, uint64_t &site, uint32_t &occ, uint64_t &key) {
                         const uint2 h = sh.hits[j];
-                        if (!record_keep(h, slice)) { slice = kNoSlice; return; }
+                        if (!record_keep(h, slice, sh.gated)) { slice = kNoSlice; return; }
                         site = hit_site(a.tv, h);
                         if (a.tv.siteOrdered && site != kSiteUnknown) {
                             // the site's text rank orders it; its id is only needed when it occurs more than once
@@ -889,7 +1063,7 @@ __device__ __forceinline__ void triple_epilogue(const TripleArgs &a, Smem &sm, u
     for (uint32_t k = 0; k < kPerThread; k++) {
         const uint32_t j = threadIdx.x + k * kTripleThreads;
         myPos[k] = 0xFFFFFFFFu;
-        if (j < nLocal && record_keep(sh.hits[j], myMinE[k])) myPos[k] = atomicAdd(&sh.nKept, 1u);
+        if (j < nLocal && record_keep(sh.hits[j], myMinE[k], sh.gated)) myPos[k] = atomicAdd(&sh.nKept, 1u);
     }
     __syncthreads();
     const uint32_t nKept = sh.nKept;
@@ -933,7 +1107,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
     __shared__ typename std::conditional<FUSED, TripleSmem, TripleSmemScan>::type sm;
     TripleShared &sh = sm.scan;
     const uint64_t g = a.guides[guide];
-    triple_prologue(a, sh, g);
+    triple_prologue(a, sh, g, guide);
 
     const uint32_t octet = threadIdx.x >> 3, lane8 = threadIdx.x & 7u;
     constexpr uint32_t kOctets = kTripleThreads / 8;
@@ -981,20 +1155,105 @@ __device__ __forceinline__ void bs_full_add(uint32_t a, uint32_t b, uint32_t c, 
     carry = (a & b) | (c & (a ^ b));
 }
 
-// LSUBS = sub-blocks per lane: 1 = SUBS lanes share a visit; 2 = a lane owns two neighbouring sub-blocks (at pitch 64:
-// the whole 128-byte block), i.e. eight 16-byte loads in flight per lane before the first adder tree runs.  Measured
-// SLOWER (5.2 against 3.8 ms per 100 000 guides: 64 registers, 8 CTAs per SM) -- the kernel is bound by instruction
-// issue and latency across warps, not by bytes in flight per lane; kept selectable (ISSL_TRIPLE_LSUBS) as evidence.
+// One 64-byte sub-block of the blocked copy: four 16-byte words = 16 bit planes of 32 slots; all 31 residuals at once --
+//   mismatch flag of base b (one bit per slot):  x_b = (plane[2b] ^ G[2b]) | (plane[2b+1] ^ G[2b+1])
+//   count of the 8 flags per slot with a carry-save adder (4 full + 3 half adders), compared with the budget,
+// 30 LOP3 for 31 (guide, site) pairs instead of ~7 instructions per pair; no POPC, no offset lookup.
+// Hits are recorded in hits[0 .. cap) through one reservation on *nHits.  `allowed`: the slots still to be reported.
+// A record list found full: kFullSpill = the hit goes to the general pipeline's buffer on its own; kFullRetry / kFullDrop =
+// the slots that did not fit are returned (the flush variant tries them again after emptying the list; the warp-per-guide
+// kernel hands the whole guide to the CTA-per-guide kernel).
+enum { kFullSpill = 0, kFullRetry = 1, kFullDrop = 2 };
+
+template <int FULL>
+__device__ __forceinline__ uint32_t triple_sub_block(const TripleArgs &a, const uint32_t *guide, const uint4 *mask, uint32_t *nHits, uint2 *hits,
+                                                     const uint32_t cap, const uint2 v, const uint32_t key, const uint32_t sub, const uint4 q0,
+                                                     const uint4 q1, const uint4 q2, const uint4 q3, const uint32_t allowed, uint32_t &cnt,
+                                                     const uint32_t gated = 31u)
+{
+    cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
+    if (cnt == 0) return 0;
+    const uint4 m0 = mask[0], m1 = mask[1], m2 = mask[2], m3 = mask[3];
+    const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
+    const uint32_t x2 = (q1.x ^ m1.x) | (q1.y ^ m1.y), x3 = (q1.z ^ m1.z) | (q1.w ^ m1.w);
+    const uint32_t x4 = (q2.x ^ m2.x) | (q2.y ^ m2.y), x5 = (q2.z ^ m2.z) | (q2.w ^ m2.w);
+    const uint32_t x6 = (q3.x ^ m3.x) | (q3.y ^ m3.y), x7 = (q3.z ^ m3.z) | (q3.w ^ m3.w);
+    uint32_t sa, ca, sb, cb, sc, cc, t1, u1;
+    bs_full_add(x0, x1, x2, sa, ca);
+    bs_full_add(x3, x4, x5, sb, cb);
+    bs_full_add(x6, x7, sa, sc, cc);
+    const uint32_t s0 = sb ^ sc, cd = sb & sc;          // count bit 0
+    bs_full_add(ca, cb, cc, t1, u1);
+    const uint32_t s1 = t1 ^ cd, u2 = t1 & cd;          // count bit 1
+    const uint32_t s2 = u1 ^ u2, s3 = u1 & u2;          // count bits 2, 3
+    // slots whose count exceeds the budget: a bit-sliced comparator, most significant bit last (lanes of a warp hold
+    // visits with different budgets -- no branches)
+    const uint32_t bud = v.x >> 28;
+    const uint32_t b0 = 0u - (bud & 1u), b1 = 0u - ((bud >> 1) & 1u), b2 = 0u - ((bud >> 2) & 1u);
+    uint32_t over = s0 & ~b0;
+    over = (s1 & ~b1) | (~(s1 ^ b1) & over);
+    over = (s2 & ~b2) | (~(s2 ^ b2) & over);
+    over |= s3;
+    // ... and of those within budget, the ones this triple is responsible for (the stateless replacement of the
+    // reference's toggle bitset, ref :385-390): a function of the visit and of "the residual matches exactly on slice
+    // p / on slice q", tabulated per visit.  Nearly all visits keep only entries that match on neither.
+    const uint32_t pEx = ~(x0 | x1 | x2 | x3), qEx = ~(x4 | x5 | x6 | x7);
+    const uint32_t kt = v.y >> 16;
+    uint32_t keep = ~(pEx | qEx);
+    if (kt != 1u)
+        keep = ((kt & 1u) ? ~(pEx | qEx) : 0u) | ((kt & 2u) ? (pEx & ~qEx) : 0u) | ((kt & 4u) ? (~pEx & qEx) : 0u) | ((kt & 8u) ? (pEx & qEx) : 0u);
+    uint32_t pass = ~over & keep & ((2u << cnt) - 2u) & allowed;   // slots 1..cnt hold residuals
+    if (pass) {
+        // one reservation for all hits of the sub-block; the sub-block's entries that occur more than once are its first ones
+        uint32_t slot = atomicAdd(nHits, (uint32_t)__popc(pass));
+        const uint32_t multi = (q1.z & 1u) | ((q1.w & 1u) << 1) | ((q2.x & 1u) << 2) | ((q2.y & 1u) << 3) | ((q2.z & 1u) << 4);
+        const uint32_t multiMask = (2u << multi) - 2u;
+        const uint32_t y0 = ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | kRecBlocked;
+        do {
+            if (FULL != kFullSpill && slot >= cap) break;   // list full: these slots are handed back
+            const uint32_t sl = __ffs(pass) - 1;
+            pass &= pass - 1;
+            // the entry's residual, gathered back from the 16 planes (issue slots are cheaper than DRAM lines): every
+            // plane is shifted so that the slot's bit becomes its top bit, which a funnel shift then feeds into r
+            const uint32_t up = 31u - sl;
+            uint32_t r = 0;
+            r = __funnelshift_l(q3.w << up, r, 1); r = __funnelshift_l(q3.z << up, r, 1);
+            r = __funnelshift_l(q3.y << up, r, 1); r = __funnelshift_l(q3.x << up, r, 1);
+            r = __funnelshift_l(q2.w << up, r, 1); r = __funnelshift_l(q2.z << up, r, 1);
+            r = __funnelshift_l(q2.y << up, r, 1); r = __funnelshift_l(q2.x << up, r, 1);
+            r = __funnelshift_l(q1.w << up, r, 1); r = __funnelshift_l(q1.z << up, r, 1);
+            r = __funnelshift_l(q1.y << up, r, 1); r = __funnelshift_l(q1.x << up, r, 1);
+            r = __funnelshift_l(q0.w << up, r, 1); r = __funnelshift_l(q0.z << up, r, 1);
+            r = __funnelshift_l(q0.y << up, r, 1); r = __funnelshift_l(q0.x << up, r, 1);
+            const uint32_t y = y0 | (((pEx >> sl) & 1u) << 9) | (((qEx >> sl) & 1u) << 10) | (((multiMask >> sl) & 1u) << 12) | (r << 16);
+            // entry number sub*31 + sl - 1 of the bucket, recorded as entry + 1
+            const uint2 h = make_uint2(key | ((sub * kSubEntries + sl) << 24), y);
+            if (FULL != kFullSpill || slot < cap) hits[slot] = h; else triple_spill(a, *guide, h, gated);
+            slot++;
+        } while (pass);
+    }
+    return pass;
+}
+
+// SUBS lanes share a visit, each owning one 64-byte sub-block (four 16-byte loads in flight per lane).  A lane owning the
+// whole 128-byte block -- eight loads in flight, one visit-table read and one address per two sub-blocks, 64 registers and
+// 8 CTAs per SM -- measured SLOWER (5.2 against 3.8 ms per 100 000 guides, profiles/r02_ab_lane_subs.jsonl), and so did
+// asynchronous copies into a shared-memory ring (cp.async.bulk 4.99 ms, cp.async 4.29 ms against 2.74 ms for the bare
+// loads, profiles/r02_scan_variants_ring_tma.jsonl): the kernel is bound by instruction issue and by latency across many
+// warps, not by bytes in flight per lane.
+//
+// GATES = sliceWidth 10 (TripleView::perm10): the visit's keep table is narrowed by the guide's open gates, and a visit none
+// of whose entries the guide may keep is not read at all.
 //
 // FLUSH = the variant for guides with more hits than the record list holds (maxDist 5-6, repeat families): one barrier
 // per round of visits; a full list is emptied by all threads -- into the guide's own sort keys (heavy_flush; the guide is
 // then sorted and finished by this CTA, heavy_finish) or, without that buffer, into the general pipeline's -- and a hit
 // that found the list full is tried again afterwards: nothing is ever dropped and nothing leaves the CTA hit by hit.
-template <int SUBS, bool FUSED, bool FLUSH, int LSUBS = 1>
-__global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_triple_blocked(const TripleArgs a)
+template <int SUBS, bool FUSED, bool FLUSH, bool GATES = false>
+__global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(const TripleArgs a)
 {
-    static_assert(SUBS % LSUBS == 0, "a lane owns whole sub-blocks of one visit");
-    const uint32_t guide = blockIdx.x;
+    constexpr int LSUBS = 1;   // sub-blocks per lane
+    const uint32_t guide = a.guideList ? a.guideList[blockIdx.x] : blockIdx.x;   // (the guides the warp-per-guide kernel left)
     if (a.done && a.done[guide]) {
         if (a.fuse && threadIdx.x == 0) {
             a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 1;
@@ -1004,7 +1263,7 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
     __shared__ typename std::conditional<FUSED, TripleSmem, TripleSmemScan>::type sm;
     TripleShared &sh = sm.scan;
     const uint64_t g = a.guides[guide];
-    triple_prologue(a, sh, g);
+    triple_prologue(a, sh, g, guide);
 
     constexpr uint32_t LPV = SUBS / LSUBS;                  // lanes per visit
     constexpr uint32_t V = kTripleThreads / LPV;            // visits in flight per CTA
@@ -1016,77 +1275,19 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
 
     // a full record list is emptied by all threads (FLUSH only)
     auto flush = [&]() {
-        if constexpr (FUSED) { if (heavy) { heavy_flush(a, sh, g); return; } }
-        triple_flush(a, sh, guide);
+        if constexpr (FUSED) { if (heavy) { heavy_flush(a, sh, a.guides[sh.guide]); return; } }
+        triple_flush(a, sh, sh.guide);
     };
 
     // one sub-block: 31 residuals against the guide's, hits recorded.  `allowed`: the slots still to be reported; returns
     // the slots that found the record list full (FLUSH only: 0 otherwise, such hits go to the general pipeline one by one)
     auto sub_block = [&](const uint2 v, const uint32_t t, const uint32_t key, const uint32_t sub, const uint4 q0, const uint4 q1,
                          const uint4 q2, const uint4 q3, const uint32_t allowed, const bool count) -> uint32_t {
-        const uint32_t cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
-        if (cnt == 0) return 0;
+        uint32_t cnt = 0;
+        const uint32_t left = triple_sub_block<FLUSH ? kFullRetry : kFullSpill>(a, &sh.guide, sh.mask[t], &sh.nHits, sh.hits, kTripleHitCap, v, key, sub,
+                                                                                 q0, q1, q2, q3, allowed, cnt, sh.gated);
         if (count) entries += cnt;
-        const uint4 m0 = sh.mask[t][0], m1 = sh.mask[t][1], m2 = sh.mask[t][2], m3 = sh.mask[t][3];
-        const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
-        const uint32_t x2 = (q1.x ^ m1.x) | (q1.y ^ m1.y), x3 = (q1.z ^ m1.z) | (q1.w ^ m1.w);
-        const uint32_t x4 = (q2.x ^ m2.x) | (q2.y ^ m2.y), x5 = (q2.z ^ m2.z) | (q2.w ^ m2.w);
-        const uint32_t x6 = (q3.x ^ m3.x) | (q3.y ^ m3.y), x7 = (q3.z ^ m3.z) | (q3.w ^ m3.w);
-        uint32_t sa, ca, sb, cb, sc, cc, t1, u1;
-        bs_full_add(x0, x1, x2, sa, ca);
-        bs_full_add(x3, x4, x5, sb, cb);
-        bs_full_add(x6, x7, sa, sc, cc);
-        const uint32_t s0 = sb ^ sc, cd = sb & sc;          // count bit 0
-        bs_full_add(ca, cb, cc, t1, u1);
-        const uint32_t s1 = t1 ^ cd, u2 = t1 & cd;          // count bit 1
-        const uint32_t s2 = u1 ^ u2, s3 = u1 & u2;          // count bits 2, 3
-        // slots whose count exceeds the budget: a bit-sliced comparator, most significant bit last (lanes of a warp hold
-        // visits with different budgets -- no branches)
-        const uint32_t bud = v.x >> 28;
-        const uint32_t b0 = 0u - (bud & 1u), b1 = 0u - ((bud >> 1) & 1u), b2 = 0u - ((bud >> 2) & 1u);
-        uint32_t over = s0 & ~b0;
-        over = (s1 & ~b1) | (~(s1 ^ b1) & over);
-        over = (s2 & ~b2) | (~(s2 ^ b2) & over);
-        over |= s3;
-        // ... and of those within budget, the ones this triple is responsible for (the stateless replacement of the
-        // reference's toggle bitset, ref :385-390): a function of the visit and of "the residual matches exactly on slice
-        // p / on slice q", tabulated per visit.  Nearly all visits keep only entries that match on neither.
-        const uint32_t pEx = ~(x0 | x1 | x2 | x3), qEx = ~(x4 | x5 | x6 | x7);
-        const uint32_t kt = v.y >> 16;
-        uint32_t keep = ~(pEx | qEx);
-        if (kt != 1u)
-            keep = ((kt & 1u) ? ~(pEx | qEx) : 0u) | ((kt & 2u) ? (pEx & ~qEx) : 0u) | ((kt & 4u) ? (~pEx & qEx) : 0u) | ((kt & 8u) ? (pEx & qEx) : 0u);
-        uint32_t pass = ~over & keep & ((2u << cnt) - 2u) & allowed;   // slots 1..cnt hold residuals
-        if (pass) {
-            // one reservation for all hits of the sub-block; the sub-block's entries that occur more than once are its first ones
-            uint32_t slot = atomicAdd(&sh.nHits, (uint32_t)__popc(pass));
-            const uint32_t multi = (q1.z & 1u) | ((q1.w & 1u) << 1) | ((q2.x & 1u) << 2) | ((q2.y & 1u) << 3) | ((q2.z & 1u) << 4);
-            const uint32_t multiMask = (2u << multi) - 2u;
-            const uint32_t y0 = ((v.x >> 24) & 15u) | ((v.y & 31u) << 4) | kRecBlocked;
-            do {
-                if (FLUSH && slot >= kTripleHitCap) break;   // list full: these slots again after the flush
-                const uint32_t sl = __ffs(pass) - 1;
-                pass &= pass - 1;
-                // the entry's residual, gathered back from the 16 planes (issue slots are cheaper than DRAM lines): every
-                // plane is shifted so that the slot's bit becomes its top bit, which a funnel shift then feeds into r
-                const uint32_t up = 31u - sl;
-                uint32_t r = 0;
-                r = __funnelshift_l(q3.w << up, r, 1); r = __funnelshift_l(q3.z << up, r, 1);
-                r = __funnelshift_l(q3.y << up, r, 1); r = __funnelshift_l(q3.x << up, r, 1);
-                r = __funnelshift_l(q2.w << up, r, 1); r = __funnelshift_l(q2.z << up, r, 1);
-                r = __funnelshift_l(q2.y << up, r, 1); r = __funnelshift_l(q2.x << up, r, 1);
-                r = __funnelshift_l(q1.w << up, r, 1); r = __funnelshift_l(q1.z << up, r, 1);
-                r = __funnelshift_l(q1.y << up, r, 1); r = __funnelshift_l(q1.x << up, r, 1);
-                r = __funnelshift_l(q0.w << up, r, 1); r = __funnelshift_l(q0.z << up, r, 1);
-                r = __funnelshift_l(q0.y << up, r, 1); r = __funnelshift_l(q0.x << up, r, 1);
-                const uint32_t y = y0 | (((pEx >> sl) & 1u) << 9) | (((qEx >> sl) & 1u) << 10) | (((multiMask >> sl) & 1u) << 12) | (r << 16);
-                // entry number sub*31 + sl - 1 of the bucket, recorded as entry + 1
-                const uint2 h = make_uint2(key | ((sub * kSubEntries + sl) << 24), y);
-                if (FLUSH || slot < kTripleHitCap) sh.hits[slot] = h; else triple_spill(a, guide, h);
-                slot++;
-            } while (pass);
-        }
-        return pass;
+        return left;
     };
 
     // entries [start, end) of the contiguous copy (the rest of a bucket that does not fit its block), shared by `lanes`
@@ -1095,7 +1296,7 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
     auto scan_range = [&](const uint2 v, const uint32_t start, const uint32_t end, const uint32_t gl, const uint32_t lanes) {
         const uint32_t t = (v.x >> 24) & 15u;
         if constexpr (!FLUSH) {
-            if (start < end) triple_bucket(a, sh, guide, v, start, end, gl, lanes);
+            if (start < end) triple_bucket(a, sh, sh.guide, v, start, end, gl, lanes);
         } else {
             const uint32_t gg = sh.res[t];
             const uint4 *__restrict__ base = reinterpret_cast<const uint4 *>(a.tv.res + (uint64_t)t * a.tv.stride);
@@ -1106,8 +1307,8 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
                     const uint4 r = __ldg(base + vi);
                     const uint32_t first = vi << 3;
                     const uint32_t lo = start > first ? start - first : 0u, hi = min(end - first, 8u);
-                    const uint32_t left = triple_vector<true>(a, sh, guide, v, gg, r, ((1u << hi) - 1u) & ~((1u << lo) - 1u) & allowed,
-                                                              [first](uint32_t i) { return first + i; }, 0u);
+                    const uint32_t left = triple_vector<true>(a, sh, 0u, v, gg, r, ((1u << hi) - 1u) & ~((1u << lo) - 1u) & allowed,
+                                                              [first](uint32_t i) { return first + i; }, 0u, &sh.nHits, sh.hits, kTripleHitCap, sh.gated);
                     if (left) allowed = left; else { vi += lanes; allowed = 0xFFu; }
                 }
                 if (__syncthreads_or(sh.nHits > kTripleFlushAt)) flush();
@@ -1126,8 +1327,20 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
         bool ovfPending = false;
 #pragma unroll
         for (int s = 0; s < LSUBS; s++) left[s] = 0;
-        if (e < v1) {
+        bool live = e < v1;
+        if (live) {
             v = __ldg(visits + e);
+            if constexpr (GATES) {
+                // sliceWidth 10: of the four ways the residual's two slices can match exactly, only those that leave the hit
+                // with an exact unit behind an open gate; a visit none of whose entries this guide may keep is not read
+                const uint32_t gate = sh.gated, p = (v.y >> 8) & 15u, q = (v.y >> 12) & 15u;
+                const uint32_t ok = (v.y & gate & 31u) ? 0xFu : ((((gate >> p) & 1u) ? 0xAu : 0u) | (((gate >> q) & 1u) ? 0xCu : 0u));
+                const uint32_t kt = (v.y >> 16) & ok;
+                v.y = (v.y & 0xFFFFu) | (kt << 16);
+                live = kt != 0;
+            }
+        }
+        if (live) {
             t = (v.x >> 24) & 15u; key = sh.key[t] ^ (v.x & 0xFFFFFFu);
             const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub0) * 4;
             // read once: streaming loads, so that the visit table and the offsets keep their place in L1
@@ -1135,10 +1348,10 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
             for (int s = 0; s < LSUBS; s++) {
                 q[s][0] = __ldcs(p + 4 * s); q[s][1] = __ldcs(p + 4 * s + 1); q[s][2] = __ldcs(p + 4 * s + 2); q[s][3] = __ldcs(p + 4 * s + 3);
             }
-            if (sub0 == 0) visited++;
+            if constexpr (GATES) { if (sub0 == 0) visited++; }   // (without gates every visit is read: counted after the loop)
             if ((q[0][1].y & 1u) && sub0 == 0) {   // more entries than the block holds: noted for after the loop
                 const uint32_t slot = atomicAdd(&sh.nOvf, 1u);
-                if (slot < kTripleOvfCap) sh.ovf[slot] = (uint16_t)(e - v0);   // visit tables have fewer than 2^16 entries
+                if (slot < kTripleOvfCap) sh.ovf[slot] = (uint16_t)e;   // visit tables have fewer than 2^16 entries
                 else if constexpr (FLUSH) ovfPending = true;
                 else {   // list full (dense repeat families): this lane reads the rest alone
                     const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
@@ -1161,7 +1374,7 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
                 __syncthreads();
                 if (threadIdx.x == 0) sh.nOvf = 0;
                 for (uint32_t j = 0; j < kTripleOvfCap; j++) {
-                    const uint2 vo = __ldg(visits + v0 + sh.ovf[j]);
+                    const uint2 vo = __ldg(visits + sh.ovf[j]);
                     const uint32_t to = (vo.x >> 24) & 15u;
                     const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
                     scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
@@ -1169,11 +1382,12 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
                 __syncthreads();
                 if (ovfPending) {   // buckets that found the list full
                     const uint32_t slot = atomicAdd(&sh.nOvf, 1u);
-                    if (slot < kTripleOvfCap) { sh.ovf[slot] = (uint16_t)(e - v0); ovfPending = false; }
+                    if (slot < kTripleOvfCap) { sh.ovf[slot] = (uint16_t)e; ovfPending = false; }
                 }
             }
         }
     }
+    if constexpr (!GATES) { if (sub0 == 0 && v0 + vslot < v1) visited = (v1 - v0 - vslot + V - 1) / V; }
     __syncthreads();
     if (sh.nOvf) {   // CTA-uniform: the buckets noted during the scan
         const uint32_t nOvf = min(sh.nOvf, kTripleOvfCap);
@@ -1183,7 +1397,7 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
             uint2 vo = make_uint2(0, 0);
             uint32_t start = 0, end = 0;
             if (j < nOvf) {
-                vo = __ldg(visits + v0 + sh.ovf[j]);
+                vo = __ldg(visits + sh.ovf[j]);
                 const uint32_t to = (vo.x >> 24) & 15u;
                 const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
                 start = __ldg(o) + SUBS * kSubEntries; end = __ldg(o + 1);
@@ -1200,13 +1414,131 @@ __global__ void __launch_bounds__(kTripleThreads, LSUBS == 1 ? 10 : 8) k_scan_tr
         __syncthreads();
         const uint32_t nLong = min(sh.nLong, kTripleLongCap);
         for (uint32_t j = 0; j < nLong; j++) {   // one bucket at a time, all threads
-            const uint2 vo = __ldg(visits + v0 + sh.longList[j]);
+            const uint2 vo = __ldg(visits + sh.longList[j]);
             const uint32_t to = (vo.x >> 24) & 15u;
             const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
             scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
         }
     }
-    triple_epilogue<FUSED, FLUSH>(a, sm, guide, g, entries, visited);
+    triple_epilogue<FUSED, FLUSH>(a, sm, sh.guide, a.guides[sh.guide], entries, visited);   // (the guide is read again: two registers the loop needs)
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1s: warp per guide, for visit tables of a few dozen buckets (maxDist <= 3: 10 / 130 visits per guide, about one hit).
+// A CTA per guide leaves most of its 128 lanes idle there and pays a prologue, barriers and a 512-entry tail for one
+// round of loads; here a CTA holds four guides, each warp builds its guide's masks, reads the guide's blocks (a lane per
+// sub-block), records the hits in a list of its own and finishes the guide: sites from the records, scores (ref :392-461),
+// rank by (slice, site text) among the warp's hits, ordered accumulation with the early exit (ref :466-502).  No
+// barriers.  A guide that does not fit (a bucket larger than its block, more than 32 hits: repeat families) is flagged and
+// taken by the CTA-per-guide kernel afterwards.  Needs the blocked copy and an index in text order.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSmallHitCap = 32;
+constexpr uint32_t kSmallMaxVisits = 256;
+
+struct SmallWarp {
+    uint4 mask[kTripleCount][4];
+    uint2 hits[kSmallHitCap];
+    uint64_t order[kSmallHitCap];
+    double mit[kSmallHitCap], cfd[kSmallHitCap];
+    uint32_t key[kTripleCount];
+    uint32_t nHits, pad;
+};
+
+template <int SUBS>
+__global__ void __launch_bounds__(kTripleThreads) k_scan_triple_small(const TripleArgs a)
+{
+    __shared__ SmallWarp sw[kTripleThreads / 32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t guide = blockIdx.x * (kTripleThreads / 32) + warp;
+    if (guide >= a.nGuides) return;
+    if (a.done && a.done[guide]) {
+        if (lane == 0) { a.totMitOut[guide] = a.sp.totMit[guide]; a.totCfdOut[guide] = a.sp.totCfd[guide]; a.doneOut[guide] = 1; }
+        return;
+    }
+    SmallWarp &w = sw[warp];
+    const uint64_t g = a.guides[guide];
+    if (lane < kTripleCount) w.key[lane] = triple_key(g, c_tripleSlices[lane][0], c_tripleSlices[lane][1], c_tripleSlices[lane][2]);
+    for (uint32_t i = lane; i < kTripleCount * 16; i += 32) {
+        const uint32_t t = i >> 4, r = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]);
+        reinterpret_cast<uint32_t *>(w.mask)[i] = 0u - ((r >> (i & 15u)) & 1u);
+    }
+    if (lane == 0) w.nHits = 0;
+    __syncwarp();
+    const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
+    uint32_t entries = 0, visited = 0;
+    bool bad = false;
+    for (uint32_t i = lane; i < a.nVisits * SUBS; i += 32) {
+        const uint32_t e = i / SUBS, sub = i % SUBS;
+        const uint2 v = __ldg(visits + e);
+        const uint32_t t = (v.x >> 24) & 15u, key = w.key[t] ^ (v.x & 0xFFFFFFu);
+        const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
+        const uint4 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2), q3 = __ldcs(p + 3);
+        if (sub == 0) visited++;
+        if ((q1.y & 1u) && sub == 0) {   // more entries than the block holds: this lane reads the rest from the contiguous copy
+            const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
+            const uint32_t start = __ldg(o) + SUBS * kSubEntries, end = __ldg(o + 1);
+            if (end - start > 64u) bad = true;   // a repeat family's bucket: the CTA-per-guide kernel shares it among its threads
+            else {
+                const uint32_t gg = triple_res(g, c_tripleSlices[t][3], c_tripleSlices[t][4]) * 0x10001u;
+                const uint4 *__restrict__ base = reinterpret_cast<const uint4 *>(a.tv.res + (uint64_t)t * a.tv.stride);
+                for (uint32_t vi = start >> 3; vi <= (end - 1) >> 3; vi++) {
+                    const uint4 r = __ldg(base + vi);
+                    const uint32_t first = vi << 3, lo = start > first ? start - first : 0u, hi = min(end - first, 8u);
+                    if (triple_vector<true>(a, *reinterpret_cast<TripleShared *>(&w), guide, v, gg, r, ((1u << hi) - 1u) & ~((1u << lo) - 1u),
+                                            [first](uint32_t i) { return first + i; }, 0u, &w.nHits, w.hits, kSmallHitCap, 31u)) bad = true;
+                }
+                entries += end - start;
+            }
+        }
+        uint32_t cnt;
+        if (triple_sub_block<kFullDrop>(a, nullptr, w.mask[t], &w.nHits, w.hits, kSmallHitCap, v, key, sub, q0, q1, q2, q3, ~0u, cnt)) bad = true;
+        entries += cnt;
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, bad)) {
+        if (lane == 0) a.redo[atomicAdd(a.redoCount, 1ull)] = guide;
+        return;
+    }
+    if (a.streamed) {
+        for (int o = 16; o > 0; o >>= 1) {
+            entries += __shfl_down_sync(0xffffffffu, entries, o);
+            visited += __shfl_down_sync(0xffffffffu, visited, o);
+        }
+        if (lane == 0) { atomicAdd(a.streamed, (unsigned long long)entries); atomicAdd(a.streamed + 1, (unsigned long long)visited); }
+    }
+    const uint32_t n = w.nHits;
+    double mit = 0.0, cfd = 0.0;
+    if (lane == 0) { mit = a.sp.totMit[guide]; cfd = a.sp.totCfd[guide]; }
+    bool stop = false;
+    if (n) {
+        uint64_t okey = 0;
+        double cm = 0.0, cc = 0.0;
+        if (lane < n) {
+            uint32_t slice, occ;
+            uint64_t site;
+            record_resolve(a, w.hits[lane], g, 31u, slice, site, occ);
+            int dist;
+            hit_contrib(a.sp.tb, g, site, occ, a.sp.calcMit, a.sp.calcCfd, cm, cc, dist);
+            okey = ((uint64_t)slice << 60) | site_text_key(site, 20);
+            w.order[lane] = okey;
+        }
+        __syncwarp();
+        if (lane < n) {
+            uint32_t r = 0;
+            for (uint32_t q = 0; q < n; q++) r += (uint32_t)(w.order[q] < okey);
+            w.mit[r] = cm; w.cfd[r] = cc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t i = 0; i < n && !stop; i++) {
+                mit = __dadd_rn(mit, w.mit[i]);
+                cfd = __dadd_rn(cfd, w.cfd[i]);
+                if (a.sp.checkExit) stop = exit_predicate(a.sp.method, mit, cfd, a.sp.maximumSum);
+            }
+            atomicAdd(a.fusedHits, (unsigned long long)n);
+        }
+    }
+    if (lane == 0) { a.totMitOut[guide] = mit; a.totCfdOut[guide] = cfd; a.doneOut[guide] = stop ? 1 : 0; }
 }
 
 // sliceWidth 4: the ordering slice of every general-pipeline key, from the site itself (ref :330-390: a hit is met

@@ -110,6 +110,7 @@ typedef struct issl_stats {
     uint64_t heavy_hits;       /* TRIPLE: hits of guides with more hits than a CTA's record list holds, sorted and
                                   accumulated inside the scan kernel (ABI 4)                          */
     uint64_t sorted_hits;      /* hits that went through the general pipeline's device-wide sort (ABI 4) */
+    double heavy_ms;           /* device time of k_heavy_finish, the per-guide sort + accumulation of those guides (ABI 4) */
 } issl_stats;
 
 typedef struct issl_index issl_index;     /* a parsed .issl image in host memory          */
@@ -307,6 +308,11 @@ size_t issl_mit_table(size_t seqLength, size_t sliceWidth, uint64_t *masks, doub
  * (isslScoreOfftargets.cpp:330-390) -- and waveStart[s] .. waveStart[s+1] delimits slice s.
  * Returns the number of entries (written up to cap); out may be NULL to size the table.  0 <= maxDist <= 7. */
 size_t issl_triple_visits(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6]);
+
+/* ... for sliceWidth 4 (ten 2-base slices): from maxDist 5 on a site can agree with the guide on a 2-base slice without
+ * agreeing on any whole byte; the buckets of triple 0 whose three key bytes all differ from the guide's are added
+ * (1 728 for maxDist 5, 25 056 for maxDist 6), budget = what is left for the residual, both slices of which differ too. */
+size_t issl_triple_visits_w4(int maxDist, uint32_t *out, size_t cap, uint32_t waveStart[6]);
 
 /* The fixed tables behind it: slices_out[t*5 + 0..2] = the slices in key bytes 0..2 of triple t, [t*5 + 3..4] the two
  * residual slices; resp_out[E] = the triple responsible for a site whose exactly matching slices are the set E

@@ -32,7 +32,7 @@ def fmt_stdout(guides_packed, mit, cfd, seq_length=20):
 def layouts_for(case):
     w, L = case.slice_width, case.seq_length
     res32 = w % 2 == 0 and 2 * L - min(w, 8) <= 32
-    triple = w in (8, 4) and L == 20
+    triple = w in (8, 4, 10) and L == 20
     return (["triple"] if triple else []) + (["res32"] if res32 else []) + ["sig64", "gather"]
 
 
@@ -487,8 +487,9 @@ def test_fused_tail_orders_hits_by_site_text_or_by_id(case):
 def test_triple_layout_slice_width_4(fuse, blocks):
     """sliceWidth 4 (ten 2-base slices) under TRIPLE: up to maxDist 4 the same sub-buckets are read, but hits are
     accumulated in the order of the lowest exactly matching 2-base slice, and the early exit takes effect in the
-    ordered accumulation (one wave); above maxDist 4 the ids-only slice lists are scanned.  Large batch, so that the
-    fused tail, the segment kernel and the general pipeline (guides with more than 512 hits) all run."""
+    ordered accumulation (one wave); from maxDist 5 on a hit may match on a 2-base slice without matching on any whole
+    byte, and the buckets whose three key bytes all differ are read as well (issl_triple_visits_w4).  Large batch, so
+    that the fused tail, the segment kernel and the general pipeline (guides with more than 512 hits) all run."""
     text = td.make_offtargets(61, n_random=100_000, n_families=25, family_size=800, max_sub_rate=0.12)
     img = oracle.create_index(text, 20, 4)
     rng = np.random.default_rng(62)
@@ -519,6 +520,54 @@ def test_triple_layout_slice_width_4(fuse, blocks):
         if thr == 0:
             assert st["candidates"] == int(want["candidates"].sum())
         assert (st["bucket_visits"] > 0) == (md <= 4)
+    _, _, hits = dev.score_hits(guides[:600], 4, 0, "and")
+    want = oracle.score(img, guides[:600], 4, 0, "and", threads=1, want_hits=True)["hits"]
+    assert np.array_equal(hits, np.stack([want[k].astype(np.int64) for k in ("guide", "id", "dist", "occ")], axis=1))
+    dev.close()
+
+
+@pytest.mark.parametrize("fuse,blocks,flush", [(2, "64", "0"), (2, "32", "1"), (1, "32", "0"), (0, "0", "0"), (2, "0", "0")])
+def test_triple_layout_slice_width_10(fuse, blocks, flush):
+    """sliceWidth 10 (four 5-base slices) under TRIPLE.  The builder truncates slice values to 8 bits (ref
+    isslCreateIndex.cpp:228): list (i, v) holds the sites that agree with v on the first FOUR bases of slice i, and a guide
+    only finds such a list when the fifth base of its own slice is A.  The sub-bucket copies are built from permuted
+    signatures (the four 4-base units, then the four fifth bases), a guide keeps a hit only behind an open gate, and the
+    hit is accumulated under the lowest such slice -- one wave, the early exit takes effect in the ordered accumulation.
+    Guides are mutated family members with every combination of gates, and plain random ones."""
+    text = td.make_offtargets(71, n_random=100_000, n_families=25, family_size=800, max_sub_rate=0.12)
+    img = oracle.create_index(text, 20, 10)
+    rng = np.random.default_rng(72)
+    roots = td.pack_guides(td.make_guides(73, text, n=400, frac_exact=1.0, frac_mut=0.0))
+    guides = []
+    for r in roots:
+        for k in range(6):
+            g = int(r)
+            for pos in rng.choice(20, size=int(rng.integers(0, 4)), replace=False):
+                g ^= int(rng.integers(1, 4)) << (2 * int(pos))
+            for i in range(4):                      # open (A) or close the gate of every slice at random
+                if rng.random() < 0.6:
+                    g &= ~(3 << (10 * i + 8))
+            guides.append(g)
+    guides = np.concatenate([np.array(guides, dtype=np.uint64), rng.integers(0, 1 << 40, 400, dtype=np.uint64)])
+    os.environ["ISSL_TRIPLE_FUSE"] = str(fuse)
+    os.environ["ISSL_TRIPLE_BLOCKS"] = blocks
+    os.environ["ISSL_TRIPLE_FLUSH"] = flush
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, "auto")
+    finally:
+        del os.environ["ISSL_TRIPLE_FUSE"], os.environ["ISSL_TRIPLE_BLOCKS"], os.environ["ISSL_TRIPLE_FLUSH"]
+    assert dev.info["layout"] == cb.LAYOUTS["triple"]
+    for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("or", 40, 3), ("avg", 55, 5), ("mit", 0, 2), ("cfd", 20, 4), ("and", 30, 6)):
+        want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
+        mit, cfd = dev.score(guides, md, thr, method)
+        if method != "cfd":
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (fuse, blocks, method, thr, md)
+        if method != "mit":
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (fuse, blocks, method, thr, md)
+        st = dev.stats
+        if thr == 0:
+            assert st["candidates"] == int(want["candidates"].sum())
+        assert st["bucket_visits"] > 0
     _, _, hits = dev.score_hits(guides[:600], 4, 0, "and")
     want = oracle.score(img, guides[:600], 4, 0, "and", threads=1, want_hits=True)["hits"]
     assert np.array_equal(hits, np.stack([want[k].astype(np.int64) for k in ("guide", "id", "dist", "occ")], axis=1))
