@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
             "issl_local_mit_score": ([u64, sz], d),
             "issl_mit_table": ([sz, sz, vp, vp, sz, C.POINTER(u64)], sz),
             "issl_triple_visits": ([C.c_int, vp, sz, vp], sz),
+            "issl_triple_visits_w4": ([C.c_int, vp, sz, vp], sz),
             "issl_triple_layout": ([vp, vp], None),
             "issl_last_error": ([], C.c_char_p),
             "issl_abi_version": ([], i),
