@@ -84,6 +84,10 @@ def parse_args():
     ap.add_argument("--threshold", type=float, default=THRESHOLD)
     ap.add_argument("--families", type=int, default=0)
     ap.add_argument("--family-size", type=int, default=0)
+    ap.add_argument("--family-size-max", type=int, default=0,
+                    help="> --family-size: family sizes are log-uniform in [--family-size, this] (config 4 as SURVEY.md 8d states it)")
+    ap.add_argument("--low-complexity", type=float, default=0.0,
+                    help="fraction of further sites overlapping poly-A/T and dinucleotide tracts (config 4: 0.01)")
     ap.add_argument("--family-guides", type=float, default=0.0,
                     help="fraction of guides drawn from the planted families' roots (0-2 substitutions), config 4")
     ap.add_argument("--cpu-guides", type=int, default=0, help="guides in the CPU baseline sample (0 = auto)")
@@ -483,8 +487,14 @@ def main() -> int:
 
     os.environ["ISSL_MAX_GROUP"] = str(args.max_group)
     t_build = time.perf_counter()
-    dev = cb.Device.synthetic(local_rank, args.layout, seed=1, uniform_sites=args.sites, families=args.families,
-                              family_size=args.family_size, max_sub_rate=0.15, seq_length=20, slice_width=args.slice_width)
+    if args.family_size_max > args.family_size or args.low_complexity > 0:
+        dev = cb.Device.synthetic_ex(local_rank, args.layout, seed=1, uniform_sites=args.sites, families=args.families,
+                                     family_size_min=args.family_size, family_size_max=max(args.family_size_max, args.family_size),
+                                     max_sub_rate=0.15, low_complexity_fraction=args.low_complexity, seq_length=20,
+                                     slice_width=args.slice_width)
+    else:
+        dev = cb.Device.synthetic(local_rank, args.layout, seed=1, uniform_sites=args.sites, families=args.families,
+                                  family_size=args.family_size, max_sub_rate=0.15, seq_length=20, slice_width=args.slice_width)
     t_build = time.perf_counter() - t_build
     info = dev.info
     layout_name = {1: "res32", 2: "sig64", 3: "gather", 4: "triple"}[info["layout"]]
@@ -499,7 +509,14 @@ def main() -> int:
         all_guides = None
         guides = make_guides(dev, args.guides, seed=2 + rank, families=args.families, family_frac=args.family_guides)
         lo, hi = rank * args.guides, (rank + 1) * args.guides
-    workload = (f"synthetic human-scale index: {args.sites} uniform NGG sites -> {info['offtargetsCount']} distinct, "
+    repeats = ""
+    if args.families:
+        sizes = (f"{args.family_size}-{args.family_size_max} copies (log-uniform)" if args.family_size_max > args.family_size
+                 else f"{args.family_size} copies")
+        repeats = f" + {args.families} near-repeat families of {sizes}, per-base substitution rate 0-15 %"
+    if args.low_complexity > 0:
+        repeats += f" + {args.low_complexity:.1%} low-complexity (poly-A/T, dinucleotide) tract sites"
+    workload = (f"synthetic {'human' if args.sites == HUMAN_SITES else 'genome'}-scale index: {args.sites} uniform NGG sites{repeats} -> {info['offtargetsCount']} distinct, "
                 f"l=20 w={args.slice_width}, " +
                 (f"{total} guides in all partitioned over the GPUs (BASELINE.json configs[2])" if strong
                  else f"{args.guides} guides per GPU") +
@@ -507,7 +524,8 @@ def main() -> int:
     config = {"workload": workload, "sites": info["offtargetsCount"], "global_guides": total,
               "method": args.method, "max_dist": args.max_dist,
               "threshold": args.threshold, "slice_width": args.slice_width, "hbm_layout": layout_name,
-              "families": args.families, "family_size": args.family_size, "family_guides": args.family_guides,
+              "families": args.families, "family_size": args.family_size, "family_size_max": args.family_size_max,
+              "low_complexity": args.low_complexity, "family_guides": args.family_guides,
               "max_group": args.max_group, "index_hbm_gb": round(info["hbm_bytes"] / 1e9, 2),
               "parallelism": f"replicated index, guides partitioned x{args.gpus}, no collective while scoring",
               "l2": ("inputs larger than L2 (126 MB): every step reads its sub-buckets (~180 KB per guide, random 128-byte blocks "
@@ -551,7 +569,7 @@ def main() -> int:
     # ------------------------------------------------------------------ our arm
     n = guides.size
     stream = torch.cuda.current_stream()
-    keys = ("scan_ms", "scan_launches", "launches", "candidates", "hits", "streamed", "bucket_visits", "early_exits")
+    keys = ("scan_ms", "scan_launches", "launches", "candidates", "hits", "streamed", "bucket_visits", "early_exits", "heavy_hits", "heavy_ms")
 
     def barrier():
         if dist is not None:
@@ -677,6 +695,17 @@ def main() -> int:
               "hits_per_guide": acc["hits"] / max(args.steps * n, 1), "candidates_per_guide": acc["candidates"] / max(args.steps * n, 1),
               "early_exit_fraction": acc["early_exits"] / max(args.steps * n, 1),
               "roofline": roofline}
+
+    if args.families or args.low_complexity > 0:
+        # the slice-list lengths the repeats produce (the reference streams whole lists)
+        ll = dev.list_lengths.astype(np.float64)
+        ll = ll[ll > 0] if (ll > 0).any() else ll
+        edges = [0, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 26, 1 << 40]
+        hist, _ = np.histogram(ll, bins=edges)
+        result["list_lengths"] = {"lists": int(ll.size), "mean": float(ll.mean()), "max": float(ll.max()), "max_over_mean": float(ll.max() / ll.mean()),
+                                  "p50": float(np.percentile(ll, 50)), "p99": float(np.percentile(ll, 99)),
+                                  "histogram": {f"<{e}": int(c) for e, c in zip(edges[1:], hist)}}
+        result["heavy_hits_per_guide"] = acc.get("heavy_hits", 0) / max(args.steps * n, 1)
 
     if world == 1 and strong and n > CONFIG1_GUIDES:
         # configs[1]: the first 100 000 guides alone, one GPU (round 1's headline workload)

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 import subprocess
 
@@ -9,6 +10,8 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 LIB = ROOT / "crackling_b200" / "lib" / "libissl_cuda.so"
+if os.environ.get("ISSL_CUDA_LIB"):   # A/B timing of kernel variants built into another directory (tools/ab_build.sh); never a fallback
+    LIB = pathlib.Path(os.environ["ISSL_CUDA_LIB"]).resolve()
 CLI = ROOT / "bin" / "isslScoreOfftargets"
 CREATE_CLI = ROOT / "bin" / "isslCreateIndex"
 EXTRACT_CLI = ROOT / "bin" / "extractOfftargets"
@@ -33,6 +36,12 @@ class _DeviceInfo(C.Structure):
     _fields_ = [("cuda_device", C.c_int), ("layout", C.c_int), ("bytes_per_candidate", C.c_uint32),
                 ("hbm_bytes", C.c_uint64), ("list_entries", C.c_uint64), ("info", _Info),
                 ("triple_block_bytes", C.c_uint32), ("triple_hit_bytes", C.c_uint32)]
+
+
+class _SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("uniform_sites", C.c_uint64), ("families", C.c_uint32), ("family_size_min", C.c_uint32),
+                ("family_size_max", C.c_uint32), ("max_sub_rate", C.c_double), ("low_complexity_fraction", C.c_double),
+                ("seqLength", C.c_uint32), ("sliceWidth", C.c_uint32)]
 
 
 class _Stats(C.Structure):
@@ -90,6 +99,8 @@ def lib() -> C.CDLL:
             "issl_device_count": ([], i),
             "issl_device_create": ([vp, i, i, pp], i),
             "issl_device_create_synthetic": ([i, i, u64, u64, C.c_uint32, C.c_uint32, d, C.c_uint32, C.c_uint32, pp], i),
+            "issl_device_create_synthetic_ex": ([i, i, vp, pp], i),
+            "issl_device_list_lengths": ([vp, vp, sz], sz),
             "issl_device_create_from_text": ([C.c_char_p, sz, C.c_uint32, C.c_uint32, i, i, pp], i),
             "issl_sites_create": ([i, pp], i),
             "issl_sites_destroy": ([vp], None),
@@ -112,6 +123,7 @@ def lib() -> C.CDLL:
             "issl_host_alloc": ([sz, pp], i),
             "issl_host_free": ([vp], None),
             "issl_guide_filters": ([vp, C.c_char_p, sz, vp, vp, vp], i),
+            "issl_guide_duplicates": ([vp, C.c_char_p, sz, vp, C.POINTER(u64), C.POINTER(u64)], i),
             "issl_local_mit_score": ([u64, sz], d),
             "issl_mit_table": ([sz, sz, vp, vp, sz, C.POINTER(u64)], sz),
             "issl_triple_visits": ([C.c_int, vp, sz, vp], sz),
@@ -260,6 +272,26 @@ class Device:
         return cls(h)
 
     @classmethod
+    def synthetic_ex(cls, cuda_device: int = 0, layout: str | int = "auto", seed: int = 1, uniform_sites: int = 1 << 20,
+                     families: int = 0, family_size_min: int = 0, family_size_max: int = 0, max_sub_rate: float = 0.15,
+                     low_complexity_fraction: float = 0.0, seq_length: int = 20, slice_width: int = 8) -> "Device":
+        """issl_device_create_synthetic_ex: log-uniform family sizes and low-complexity tracts (BASELINE.json configs[3])."""
+        h = C.c_void_p()
+        lay = LAYOUTS[layout] if isinstance(layout, str) else int(layout)
+        spec = _SynthSpec(seed, uniform_sites, families, family_size_min, family_size_max, float(max_sub_rate),
+                          float(low_complexity_fraction), seq_length, slice_width)
+        _check(lib().issl_device_create_synthetic_ex(cuda_device, lay, C.byref(spec), C.byref(h)))
+        return cls(h)
+
+    @property
+    def list_lengths(self) -> np.ndarray:
+        """Lengths of the slice lists, slice-major (issl_device_list_lengths)."""
+        n = lib().issl_device_list_lengths(self._h, None, 0)
+        out = np.zeros(n, dtype=np.uint64)
+        lib().issl_device_list_lengths(self._h, out.ctypes.data, n)
+        return out
+
+    @classmethod
     def from_text(cls, text: bytes, seq_length: int = 20, slice_width: int = 8, cuda_device: int = 0,
                   layout: str | int = "auto") -> "Device":
         """issl_device_create_from_text: the device-side isslCreateIndex."""
@@ -300,6 +332,14 @@ class Device:
         packed = np.zeros(n, dtype=np.uint64)
         _check(lib().issl_guide_filters(self._h, text23, len(text23), flags.ctypes.data, at.ctypes.data, packed.ctypes.data))
         return flags, at, packed
+
+    def guide_duplicates(self, text23: bytes):
+        """(flags, numDuplicateGuides, len(duplicateGuides)) of n lines of 23 characters + LF (issl_guide_duplicates)."""
+        n = len(text23) // 24
+        flags = np.zeros(max(n, 1), dtype=np.uint8)
+        later, seqs = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().issl_guide_duplicates(self._h, text23, len(text23), flags.ctypes.data, C.byref(later), C.byref(seqs)))
+        return flags[:n], int(later.value), int(seqs.value)
 
     @property
     def stats(self) -> dict:

@@ -233,12 +233,20 @@ static ScoreTables score_tables(const issl_device *d)
 // ISSL_LAYOUT_TRIPLE: ten bucketed copies of the sites (issl_triple.cuh), built from sig[] once the
 // index itself is resident and validated
 // ---------------------------------------------------------------------------------------------
-static int build_triple(issl_device *d)
+// Split in two so that issl_device_create can run it on a second stream while the slice lists are still crossing PCIe:
+// the copies need only sig[] and occ[], which are complete once slice 0 has been re-laid out.
+struct TripleBuild {
+    DBuf keysIn, keysOut, idsIn, tmp;
+    uint32_t pitch = 0, perm10 = 0;
+    uint64_t stride = 0, needBlk = 0;
+    bool occFlag = false;
+};
+
+// allocations and launches on `st`; nothing is waited for.  ISSL_ERR_NOMEM when the copies do not fit.
+static int build_triple_enqueue(issl_device *d, cudaStream_t st, TripleBuild &b)
 {
-    if (d->layout != ISSL_LAYOUT_TRIPLE) return ISSL_OK;
     if (getenv("ISSL_TEST_TRIPLE_NOMEM"))   // test hook: behave as if the copies did not fit
         return issl_set_error(ISSL_ERR_NOMEM, "cudaMalloc: out of memory (simulated by ISSL_TEST_TRIPLE_NOMEM)");
-    cudaStream_t st = d->stream;
     const uint64_t N = d->info.offtargetsCount;
     const uint64_t stride = (N + 64 + 7) / 8 * 8;
     // blocked copy of the residuals (issl_triple.cuh): block size from the mean bucket occupancy, so that all but
@@ -257,7 +265,6 @@ static int build_triple(issl_device *d)
     const uint64_t needBase = kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + N * 16 + (64ull << 20);
     uint64_t needBlk = (uint64_t)kTripleCount * kTripleBuckets * pitch * 2;
     if (needBase + needBlk > freeB) { pitch = 0; needBlk = 0; }
-    const uint64_t need = needBase;
     // bit 31 of the stored ids doubles as "occurs more than once" when ids leave it free (ISSL_TRIPLE_OCCFLAG=0: tests
     // of the path indexes with 2^31 sites or more take)
     bool occFlag = N < (1ull << 31);
@@ -270,12 +277,13 @@ static int build_triple(issl_device *d)
         CKR(d->tripleBlk.exact(needBlk));   // every sub-block is written by k_triple_blocks
     }
     const uint32_t perm10 = d->info.sliceWidth == 10 ? 1u : 0u;   // sliceWidth 10: copies of the permuted signatures (issl_triple.cuh)
-    DBuf keysIn, keysOut, idsIn, tmp;
+    DBuf &keysIn = b.keysIn, &keysOut = b.keysOut, &idsIn = b.idsIn, &tmp = b.tmp;
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
     size_t tb = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keysIn.as<uint32_t>(), keysOut.as<uint32_t>(), idsIn.as<uint32_t>(),
                                        d->tripleIds.as<uint32_t>(), N, 0, 25, st));
     CKR(tmp.ensure(tb));
+    CKR(d->counters.ensure(16 * 8));
     for (uint32_t t = 0; t < kTripleCount; t++) {
         uint32_t *ids = d->tripleIds.as<uint32_t>() + t * stride;
         k_triple_keys<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), d->occ.as<uint32_t>(), N, t, perm10, keysIn.as<uint32_t>(), idsIn.as<uint32_t>());
@@ -291,34 +299,46 @@ static int build_triple(issl_device *d)
                 d->tripleBlk.as<uint4>() + (uint64_t)t * kTripleBuckets * (pitch / 8));
         CK(cudaGetLastError());
     }
-    // are the sites in text order, i.e. are ids text ranks?  (ISSL_SITE_ORDER=0: behave as if they were not)
-    CKR(d->counters.ensure(16 * 8));
-    CK(cudaMemsetAsync(d->counters.p, 0, 8, st));
-    k_check_site_order<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), N, (uint32_t)d->info.seqLength, d->counters.as<unsigned long long>());
-    CK(cudaMemcpyAsync(d->hCounters, d->counters.p, 8, cudaMemcpyDeviceToHost, st));
+    // are the sites in text order, i.e. are ids text ranks?  (read back by build_triple_finish)
+    CK(cudaMemsetAsync(d->counters.as<unsigned long long>() + 15, 0, 8, st));
+    k_check_site_order<<<blocks_for(N, 256), 256, 0, st>>>(d->sig.as<uint64_t>(), N, (uint32_t)d->info.seqLength, d->counters.as<unsigned long long>() + 15);
+    CK(cudaMemcpyAsync(d->hCounters + 15, d->counters.as<unsigned long long>() + 15, 8, cudaMemcpyDeviceToHost, st));
+    b.pitch = pitch; b.perm10 = perm10; b.stride = stride; b.needBlk = needBlk; b.occFlag = occFlag;
+    return ISSL_OK;
+}
+
+static int build_triple_finish(issl_device *d, cudaStream_t st, TripleBuild &b)
+{
     CK(cudaStreamSynchronize(st));
-    bool siteOrdered = d->hCounters[0] == 0;
+    bool siteOrdered = d->hCounters[15] == 0;   // (ISSL_SITE_ORDER=0: behave as if the sites were not in text order)
     if (const char *e = getenv("ISSL_SITE_ORDER")) siteOrdered = siteOrdered && atoi(e) != 0;
-    for (DBuf *b : {&keysIn, &keysOut, &idsIn, &tmp}) b->release();
+    for (DBuf *x : {&b.keysIn, &b.keysOut, &b.idsIn, &b.tmp}) x->release();
     d->tv.siteOrdered = siteOrdered ? 1u : 0u;
     d->tv.res = d->tripleRes.as<uint16_t>();
     d->tv.ids = d->tripleIds.as<uint32_t>();
     d->tv.offs = d->tripleOffs.as<uint32_t>();
-    d->tv.stride = stride;
-    d->tv.occFlag = occFlag ? 1u : 0u;
+    d->tv.stride = b.stride;
+    d->tv.occFlag = b.occFlag ? 1u : 0u;
     d->tv.nibbleOrder = d->info.sliceWidth == 4 ? 1u : 0u;
-    d->tv.perm10 = perm10;
-    d->tv.blk = pitch ? d->tripleBlk.as<uint4>() : nullptr;
-    d->tv.pitch = pitch;
-    d->hbmBytes += kTripleCount * (stride * 6 + (kTripleBuckets + 1ull) * 4) + needBlk;
+    d->tv.perm10 = b.perm10;
+    d->tv.blk = b.pitch ? d->tripleBlk.as<uint4>() : nullptr;
+    d->tv.pitch = b.pitch;
+    d->hbmBytes += kTripleCount * (b.stride * 6 + (kTripleBuckets + 1ull) * 4) + b.needBlk;
     return ISSL_OK;
+}
+
+static int build_triple(issl_device *d)
+{
+    if (d->layout != ISSL_LAYOUT_TRIPLE) return ISSL_OK;
+    TripleBuild b;
+    CKR(build_triple_enqueue(d, d->stream, b));
+    return build_triple_finish(d, d->stream, b);
 }
 
 // ISSL_LAYOUT_AUTO promised TRIPLE only "when it fits": when the ten copies cannot be allocated (a second human-scale
 // index next to a resident one, a smaller GPU), the index stays usable through its slice lists.
-static int build_triple_or_fall_back(issl_device *d)
+static int triple_fall_back(issl_device *d, int rc)
 {
-    const int rc = build_triple(d);
     if (rc != ISSL_ERR_NOMEM || !d->layoutAuto || d->layout != ISSL_LAYOUT_TRIPLE) return rc;
     cudaGetLastError();
     for (DBuf *b : {&d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk}) b->release();
@@ -326,6 +346,11 @@ static int build_triple_or_fall_back(issl_device *d)
     d->layout = d->iv.layout;   // RES32 (sliceWidth 8) or the ids-only lists (sliceWidth 4)
     if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] the sub-bucket copies do not fit this GPU's free memory: scanning the slice lists instead\n");
     return ISSL_OK;
+}
+
+static int build_triple_or_fall_back(issl_device *d)
+{
+    return triple_fall_back(d, build_triple(d));
 }
 
 static int new_device(int cuda_device, issl_device **out)
@@ -407,6 +432,9 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
     cudaEvent_t freeEv[2] = {nullptr, nullptr};
     DBuf dstage[2];
     unsigned long long *dErr = nullptr;
+    TripleBuild tbuild;
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t evSlice0 = nullptr;
     auto cleanup = [&]() {
         for (int b = 0; b < 2; b++) {
             if (stage[b]) cudaFreeHost(stage[b]);
@@ -414,6 +442,8 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
             dstage[b].release();
         }
         if (dErr) cudaFree(dErr);
+        if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); st2 = nullptr; }
+        if (evSlice0) { cudaEventDestroy(evSlice0); evSlice0 = nullptr; }
     };
 #define CKF(call)                                                                                         \
     do {                                                                                                  \
@@ -431,6 +461,10 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
     }
     CKF(cudaMalloc(&dErr, 8));
     CKF(cudaMemsetAsync(dErr, 0, 8, d->stream));
+    // TRIPLE: the ten sub-bucket copies are built on a second stream while slices 1.. are still crossing PCIe (they need
+    // sig[] and occ[] only, complete after slice 0); ISSL_TRIPLE_LATE=1 builds them after the upload, as round 1 did
+    int earlyRc = -1;   // -1: not started
+    const bool early = d->layout == ISSL_LAYOUT_TRIPLE && !getenv("ISSL_TRIPLE_LATE");
 
     int buf = 0;
     // 1) signatures: host image -> pinned -> device
@@ -459,17 +493,27 @@ extern "C" int issl_device_create(const issl_index *ix, int cuda_device, int lay
             CKF(cudaEventRecord(freeEv[buf], d->stream));
             buf ^= 1;
         }
+        if (s == 0 && early) {
+            CKF(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+            CKF(cudaEventCreateWithFlags(&evSlice0, cudaEventDisableTiming));
+            CKF(cudaEventRecord(evSlice0, d->stream));
+            CKF(cudaStreamWaitEvent(st2, evSlice0, 0));
+            earlyRc = build_triple_enqueue(d, st2, tbuild);
+        }
     }
     CKF(cudaMemcpyAsync(d->hCounters, dErr, 8, cudaMemcpyDeviceToHost, d->stream));
     CKF(cudaStreamSynchronize(d->stream));
-#undef CKF
     const unsigned long long bad = d->hCounters[0];
+    if (earlyRc == ISSL_OK) earlyRc = build_triple_finish(d, st2, tbuild);
+#undef CKF
     cleanup();
+    for (DBuf *x : {&tbuild.keysIn, &tbuild.keysOut, &tbuild.idsIn, &tbuild.tmp}) x->release();
     if (bad)
         return fail(issl_set_error(ISSL_ERR_UNSUPPORTED,
                                    "Error reading index: %llu list entries violate the isslCreateIndex invariants "
                                    "(id range, list membership, ascending ids or occurrence counts)", bad));
-    if ((rc = build_triple_or_fall_back(d)) != ISSL_OK) return fail(rc);
+    rc = earlyRc >= 0 ? triple_fall_back(d, earlyRc) : build_triple_or_fall_back(d);
+    if (rc != ISSL_OK) return fail(rc);
     *out = d;
     return ISSL_OK;
 }
@@ -596,15 +640,30 @@ static int collapse_and_build(issl_device *d, int layout, const uint64_t *dKeys,
     return build_triple_or_fall_back(d);
 }
 
-extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uint64_t uniform_sites,
-                                            uint32_t families, uint32_t family_size, double max_sub_rate,
-                                            uint32_t seqLength, uint32_t sliceWidth, issl_device **out)
+extern "C" int issl_device_create_synthetic_ex(int cuda_device, int layout, const issl_synth_spec *spec, issl_device **out)
 {
-    if (!out) return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: null argument");
+    if (!out || !spec) return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic_ex: null argument");
     *out = nullptr;
+    const uint32_t seqLength = spec->seqLength, sliceWidth = spec->sliceWidth;
     if (seqLength == 0 || seqLength > 32 || sliceWidth < 2 || sliceWidth > 24 || (2 * seqLength) / sliceWidth == 0)
         return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: bad sequence length / slice width");
-    const uint64_t nRaw = uniform_sites + (uint64_t)families * family_size;
+    if (spec->family_size_max < spec->family_size_min || !(spec->low_complexity_fraction >= 0.0 && spec->low_complexity_fraction <= 1.0))
+        return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: bad family sizes / low-complexity fraction");
+    // family sizes: fixed, or log-uniform in [min, max] from the same counter-based generator as the sites
+    std::vector<uint64_t> start(spec->families + 1ull, 0);
+    for (uint32_t f = 0; f < spec->families; f++) {
+        uint64_t size = spec->family_size_min;
+        if (spec->family_size_max > spec->family_size_min && spec->family_size_min > 0) {
+            const double u = (double)(rng3(spec->seed, 7, f) >> 11) * (1.0 / 9007199254740992.0);
+            size = (uint64_t)std::floor(std::exp(std::log((double)spec->family_size_min) +
+                                                 u * (std::log((double)spec->family_size_max) - std::log((double)spec->family_size_min))));
+            size = std::min<uint64_t>(std::max<uint64_t>(size, spec->family_size_min), spec->family_size_max);
+        }
+        start[f + 1] = start[f] + size;
+    }
+    const uint64_t nFamily = start[spec->families];
+    const uint64_t nLow = (uint64_t)std::floor(spec->low_complexity_fraction * (double)(spec->uniform_sites + nFamily));
+    const uint64_t nRaw = spec->uniform_sites + nFamily + nLow;
     if (nRaw == 0) return issl_set_error(ISSL_ERR_ARG, "issl_device_create_synthetic: no sites");
     issl_info f{};
     f.seqLength = seqLength; f.sliceWidth = sliceWidth; f.sliceCount = (2 * seqLength) / sliceWidth;
@@ -613,22 +672,50 @@ extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_
     issl_device *d = nullptr;
     CKR(new_device(cuda_device, &d));
     d->layoutAuto = (layout == ISSL_LAYOUT_AUTO);
-    DBuf keys, keysAlt;
+    DBuf keys, keysAlt, dStart;
     int rc = keys.ensure(nRaw * 8);
     if (rc == ISSL_OK) rc = keysAlt.ensure(nRaw * 8);
+    if (rc == ISSL_OK) rc = dStart.ensure(start.size() * 8);
+    if (rc == ISSL_OK && cudaMemcpyAsync(dStart.p, start.data(), start.size() * 8, cudaMemcpyHostToDevice, d->stream) != cudaSuccess)
+        rc = issl_set_error(ISSL_ERR_CUDA, "synthetic build: upload of the family table failed");
     if (rc == ISSL_OK) {
-        k_synth_sites<<<blocks_for(nRaw, 256), 256, 0, d->stream>>>(seed, uniform_sites, families, family_size, max_sub_rate,
-                                                                   seqLength, keys.as<uint64_t>());
+        SynthArgs a;
+        a.seed = spec->seed; a.nUniform = spec->uniform_sites; a.nFamilySites = nFamily; a.nLow = nLow;
+        a.families = spec->families; a.familyStart = dStart.as<uint64_t>(); a.maxSubRate = spec->max_sub_rate;
+        a.L = seqLength; a.keys = keys.as<uint64_t>();
+        k_synth_sites<<<blocks_for(nRaw, 256), 256, 0, d->stream>>>(a);
         rc = build_from_sites(d, lay, keys.as<uint64_t>(), nRaw, seqLength, sliceWidth, keysAlt);
     }
-    keys.release(); keysAlt.release();
     if (rc == ISSL_OK) {
         cudaError_t e = cudaStreamSynchronize(d->stream);
         if (e != cudaSuccess) rc = issl_set_error(ISSL_ERR_CUDA, "synthetic build: %s", cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(d->stream);   // `start` is a local the upload may still be reading
     }
+    keys.release(); keysAlt.release(); dStart.release();
     if (rc != ISSL_OK) { issl_device_destroy(d); return rc; }
     *out = d;
     return ISSL_OK;
+}
+
+extern "C" int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uint64_t uniform_sites,
+                                            uint32_t families, uint32_t family_size, double max_sub_rate,
+                                            uint32_t seqLength, uint32_t sliceWidth, issl_device **out)
+{
+    issl_synth_spec spec{};
+    spec.seed = seed; spec.uniform_sites = uniform_sites; spec.families = families;
+    spec.family_size_min = spec.family_size_max = family_size; spec.max_sub_rate = max_sub_rate;
+    spec.low_complexity_fraction = 0.0; spec.seqLength = seqLength; spec.sliceWidth = sliceWidth;
+    return issl_device_create_synthetic_ex(cuda_device, layout, &spec, out);
+}
+
+// ref isslScoreOfftargets.cpp:204-216 (allSlicelistSizes): the length of every slice list, slice-major
+extern "C" size_t issl_device_list_lengths(const issl_device *d, uint64_t *out, size_t cap)
+{
+    if (!d) return 0;
+    const size_t n = (size_t)d->nLists;
+    if (out) for (size_t i = 0; i < std::min(n, cap); i++) out[i] = d->hListLen[i];
+    return n;
 }
 
 // internal (issl_sites.cu): an index from `nRaw` site sort keys already on this device, in any order.  Both key
@@ -1001,8 +1088,8 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         sp.sig = d->iv.sig; sp.occ = d->iv.occ; sp.nSites = d->info.offtargetsCount; sp.occFlag = d->tv.occFlag; sp.tb = score_tables(d);
         // order keys: site text ranks (40 bits) when the index is in text order, site ids otherwise
         uint32_t idShift = 0;
-        while (idShift < 28 && (d->info.offtargetsCount >> idShift) > 16) idShift++;
-        sp.keyShift = d->tv.siteOrdered ? 36u : idShift;
+        while (idShift < 28 && (d->info.offtargetsCount >> idShift) > kKeyBuckets) idShift++;
+        sp.keyShift = d->tv.siteOrdered ? 34u : idShift;   // (text keys have 40 bits)
         sp.calcMit = ws.calcMit; sp.calcCfd = ws.calcCfd; sp.method = ws.method; sp.checkExit = ws.checkExit;
         sp.maximumSum = ws.maximumSum;
         sp.totMit = d->totMit.as<double>(); sp.totCfd = d->totCfd.as<double>(); sp.done = d->done.as<uint8_t>();
@@ -1505,6 +1592,40 @@ extern "C" int issl_guide_filters(issl_device *d, const char *text, size_t bytes
     for (DBuf *b : {&dText, &dFlags, &dAt, &dPacked}) b->release();
     if (rc != ISSL_OK) return rc;
     if (e != cudaSuccess) return issl_set_error(ISSL_ERR_CUDA, "issl_guide_filters: %s", cudaGetErrorString(e));
+    return ISSL_OK;
+}
+
+extern "C" int issl_guide_duplicates(issl_device *d, const char *text, size_t bytes, uint8_t *flags_out, uint64_t *n_later,
+                                     uint64_t *n_sequences)
+{
+    if (!d || !flags_out || (bytes && !text)) return issl_set_error(ISSL_ERR_ARG, "issl_guide_duplicates: null argument");
+    if (bytes % 24 != 0) return issl_set_error(ISSL_ERR_ARG, "issl_guide_duplicates: input is not a multiple of 24 bytes (23 characters + LF)");
+    const uint64_t n = bytes / 24;
+    if (n_later) *n_later = 0;
+    if (n_sequences) *n_sequences = 0;
+    if (n == 0) return ISSL_OK;
+    if (n >= (1ull << 32)) return issl_set_error(ISSL_ERR_ARG, "issl_guide_duplicates: more than 2^32 - 1 targets in one call");
+    CK(cudaSetDevice(d->dev));
+    cudaStream_t st = d->stream;
+    DBuf dText, keys, keysOut, idx, idxOut, tmp, dFlags;
+    CKR(dText.ensure(bytes)); CKR(keys.ensure(n * 8)); CKR(keysOut.ensure(n * 8)); CKR(idx.ensure(n * 4)); CKR(idxOut.ensure(n * 4));
+    CKR(dFlags.ensure(n)); CKR(d->counters.ensure(16 * 8));
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.as<uint64_t>(), keysOut.as<uint64_t>(), idx.as<uint32_t>(), idxOut.as<uint32_t>(), n, 0, 46, st));
+    CKR(tmp.ensure(tb));
+    unsigned long long *dc = d->counters.as<unsigned long long>();
+    CK(cudaMemcpyAsync(dText.p, text, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dc, 0, 16, st));
+    k_pack_targets<<<blocks_for(n, 256), 256, 0, st>>>(dText.as<char>(), n, keys.as<uint64_t>(), idx.as<uint32_t>());
+    // least-significant-digit radix sort: stable, so inside a run of equal keys positions ascend
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.as<uint64_t>(), keysOut.as<uint64_t>(), idx.as<uint32_t>(), idxOut.as<uint32_t>(), n, 0, 46, st));
+    k_mark_duplicates<<<blocks_for(n, 256), 256, 0, st>>>(keysOut.as<uint64_t>(), idxOut.as<uint32_t>(), n, dFlags.as<uint8_t>(), dc);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(flags_out, dFlags.p, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(d->hCounters, dc, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_later) *n_later = d->hCounters[0];
+    if (n_sequences) *n_sequences = d->hCounters[1];
     return ISSL_OK;
 }
 

@@ -822,24 +822,43 @@ __host__ __device__ __forceinline__ uint64_t sig_to_sortkey(uint64_t sig, uint32
     return k;
 }
 
-// uniform sites: i.i.d. bases, first base in {A,C,G}; family members: a per-family random root,
-// each base substituted with the family's rate.
-__global__ void k_synth_sites(uint64_t seed, uint64_t nUniform, uint32_t families, uint32_t familySize,
-                              double maxSubRate, uint32_t L, uint64_t *keys)
+// uniform sites: i.i.d. bases, first base in {A,C,G}; family members: a per-family random root, each base substituted
+// with the family's rate (family f owns members [familyStart[f], familyStart[f + 1]): sizes are the caller's, fixed or
+// log-uniform); low-complexity sites: windows that overlap a poly-A / poly-T / dinucleotide tract on one side (k = 10..20
+// bases of the repeat, 2 % of them substituted, the rest random) -- they skew the slice lists towards a few values and
+// produce sites that occur thousands of times, as the repeats of a real genome do.
+struct SynthArgs {
+    uint64_t seed, nUniform, nFamilySites, nLow;
+    uint32_t families;
+    const uint64_t *familyStart;   // [families + 1]
+    double maxSubRate;
+    uint32_t L;
+    uint64_t *keys;
+};
+
+__global__ void k_synth_sites(const SynthArgs a)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t total = nUniform + (uint64_t)families * familySize;
+    const uint64_t total = a.nUniform + a.nFamilySites + a.nLow;
     if (t >= total) return;
+    const uint64_t seed = a.seed;
+    const uint32_t L = a.L;
     const uint64_t lmask = (L >= 32) ? ~0ull : ((1ull << (2 * L)) - 1ull);
     uint64_t sig;
-    if (t < nUniform) {
+    if (t < a.nUniform) {
         const uint64_t r = rng3(seed, 1, t);
         sig = r & lmask & ~3ull;
         sig |= (rng3(seed, 2, t) % 3ull);
-    } else {
-        const uint64_t m = t - nUniform, f = m / familySize;
+    } else if (t < a.nUniform + a.nFamilySites) {
+        const uint64_t m = t - a.nUniform;
+        uint32_t lo = 0, hi = a.families;   // the family that owns member m
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.familyStart[mid] <= m) lo = mid; else hi = mid;
+        }
+        const uint64_t f = lo;
         const uint64_t root = (rng3(seed, 3, f) & lmask & ~3ull) | (rng3(seed, 4, f) % 3ull);
-        const double rate = maxSubRate * (double)(rng3(seed, 5, f) >> 11) * (1.0 / 9007199254740992.0);
+        const double rate = a.maxSubRate * (double)(rng3(seed, 5, f) >> 11) * (1.0 / 9007199254740992.0);
         sig = root;
         for (uint32_t j = 0; j < L; j++) {
             const uint64_t r = rng3(seed, 6 + j, m);
@@ -849,8 +868,28 @@ __global__ void k_synth_sites(uint64_t seed, uint64_t nUniform, uint32_t familie
                 sig = (sig & ~(3ull << (2 * j))) | (nb << (2 * j));
             }
         }
+    } else {
+        const uint64_t m = t - a.nUniform - a.nFamilySites;
+        const uint64_t r = rng3(seed, 40, m);
+        const uint32_t kind = (uint32_t)(r % 14ull);            // 0 poly-A, 1 poly-T, 2..13 the twelve dinucleotides XY, X != Y
+        const uint32_t side = (uint32_t)(r >> 8) & 1u;          // tract at the start / at the end of the window
+        const uint32_t k = 10u + (uint32_t)((r >> 16) % 11ull); // bases of the window inside the tract
+        const uint32_t phase = (uint32_t)(r >> 32) & 1u;
+        uint32_t x = 0, y = 0;
+        if (kind == 1) { x = 3; y = 3; }
+        else if (kind >= 2) { x = (kind - 2) / 3; y = (kind - 2) % 3; y += (y >= x); }
+        sig = rng3(seed, 41, m) & lmask;
+        for (uint32_t j = 0; j < L; j++) {
+            const bool inTract = side ? (j + k >= L) : (j < k);
+            if (!inTract) continue;
+            uint64_t b = ((j + phase) & 1u) ? y : x;
+            const uint64_t rs = rng3(seed, 42 + j, m);
+            if (rs % 50ull == 0) b = (b + 1 + ((rs >> 8) % 3ull)) & 3ull;
+            sig = (sig & ~(3ull << (2 * j))) | (b << (2 * j));
+        }
+        if ((sig & 3ull) == 3ull) sig = (sig & ~3ull) | (rng3(seed, 39, m) % 3ull);   // no site starts with T
     }
-    keys[t] = sig_to_sortkey(sig, L);
+    a.keys[t] = sig_to_sortkey(sig, L);
 }
 
 // run heads of the sorted key array
@@ -964,6 +1003,45 @@ __global__ void k_guide_filters(const char *text, uint64_t n, uint8_t *flags, do
     if (flags) flags[i] = (uint8_t)f;
     if (at) at[i] = pct;
     if (packed) packed[i] = sig;
+}
+
+// Duplicate candidate guides, ref /root/reference/src/crackling/Crackling.py:211-240 (the first occurrence of a 23-mer is
+// recorded, every later one is dropped and marks the sequence as not unique) and :291-296 (isUnique = rejected).
+// k_pack_targets: 23 bases -> 46-bit key (2 bits per base, base 0 most significant; anything but C, G, T packs as A, as
+// issl_pack_guides does) + the target's index; after a STABLE sort by key, k_mark_duplicates reads runs of equal keys:
+// the head of a run is the occurrence seen first.
+__global__ void k_pack_targets(const char *text, uint64_t n, uint64_t *keys, uint32_t *idx)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const char *t = text + i * 24;
+    uint64_t k = 0;
+    for (int j = 0; j < 23; j++) {
+        const char c = t[j];
+        k = (k << 2) | (uint64_t)(c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0);
+    }
+    keys[i] = k;
+    idx[i] = (uint32_t)i;
+}
+
+__global__ void k_mark_duplicates(const uint64_t *sortedKeys, const uint32_t *sortedIdx, uint64_t n, uint8_t *flags,
+                                  unsigned long long *counters /* [0] later occurrences, [1] sequences seen more than once */)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t later = 0, multiHead = 0;
+    if (j < n) {
+        const uint64_t k = sortedKeys[j];
+        const bool head = j == 0 || sortedKeys[j - 1] != k;
+        const bool more = j + 1 < n && sortedKeys[j + 1] == k;
+        flags[sortedIdx[j]] = (uint8_t)((head ? 0u : ISSL_FILTER_DUPLICATE) | ((!head || more) ? ISSL_FILTER_NOT_UNIQUE : 0u));
+        later = head ? 0u : 1u;
+        multiHead = (head && more) ? 1u : 0u;
+    }
+    const uint32_t nl = __popc(__ballot_sync(0xffffffffu, later)), nm = __popc(__ballot_sync(0xffffffffu, multiHead));
+    if ((threadIdx.x & 31u) == 0) {
+        if (nl) atomicAdd(counters, (unsigned long long)nl);
+        if (nm) atomicAdd(counters + 1, (unsigned long long)nm);
+    }
 }
 
 __global__ void k_gather_sites(const uint64_t *sig, uint64_t N, const uint64_t *siteIds, uint64_t n, uint64_t *out)

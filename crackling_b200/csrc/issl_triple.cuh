@@ -220,6 +220,13 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, const
 // k_score_segments, or as keys  guide << 35 | min(E) << 32 | id  for the general pipeline (radix sort ->
 // k_contrib -> k_accumulate), which sort back into the reference's visiting order.
 // ------------------------------------------------------------------------------------------------
+// how the scan reads a bucket's block: __ldcs (streaming, evict-first; a block is read once per guide) or __ldg
+#ifndef ISSL_BLOCK_LOAD
+#define ISSL_BLOCK_LOAD __ldcs
+#endif
+#ifndef ISSL_TRIPLE_PREFETCH
+#define ISSL_TRIPLE_PREFETCH 0
+#endif
 #ifndef ISSL_TRIPLE_HIT_CAP
 #define ISSL_TRIPLE_HIT_CAP 512
 #endif
@@ -240,7 +247,7 @@ struct ScoreParams {
     const uint32_t *occ;          // [N] occurrences
     uint64_t nSites;              // N
     uint32_t occFlag;             // ids carry "occurs more than once" in bit 31
-    uint32_t keyShift;            // order keys >> keyShift lie in [0, 16): 36 for site text keys, from the site count for ids
+    uint32_t keyShift;            // order keys >> keyShift lie in [0, kKeyBuckets]: 34 for site text keys, from the site count for ids
     ScoreTables tb;
     int calcMit, calcCfd, method, checkExit;
     double maximumSum;
@@ -249,14 +256,17 @@ struct ScoreParams {
 };
 
 // Hits are put into the reference's accumulation order -- slice, then ascending site id inside the slice (ref :330-344) --
-// by a counting pass over (slice, sixteenth of the key range) groups followed by a rank inside the group: a guide's
-// ~275 hits fall into ~60 groups of a few hits each, so the rank is a handful of comparisons.
-constexpr uint32_t kKeyBuckets = 16;
+// by a counting pass over (slice, 1/64 of the key range) groups followed by a rank inside the group: a guide's
+// ~275 hits fall into ~240 groups of one or two hits each, so the rank is a comparison or two (with 16 key ranges per
+// slice this loop was 12.5 % of the kernel's instructions: a warp pays for the largest group among its lanes).
+constexpr uint32_t kKeyBuckets = 64;
 constexpr uint32_t kOrderGroups = kOrderSlices * kKeyBuckets;
 
 struct ScoreShared {
-    double mit[kTripleThreads], cfd[kTripleThreads];   // a window of contributions in accumulation order
-    uint32_t grp[kOrderGroups];                        // per group: count -> first position -> end position
+    union {   // (shared memory per SM is L1 the scan cannot use: the two never live at the same time)
+        struct { double mit[kTripleThreads], cfd[kTripleThreads]; };   // a window of contributions in accumulation order
+        uint32_t grp[kOrderGroups];                                    // per group: count -> first position -> end position
+    };
     uint32_t kept;
 };
 constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one 64-bit order key per hit
@@ -295,18 +305,18 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint64_t *group, ui
     }
     __syncthreads();
     if (threadIdx.x < 32) {   // counts -> first positions (exclusive prefix sum by one warp)
-        constexpr uint32_t kPer = kOrderGroups / 32;
-        uint32_t c[kPer], sum = 0;
-#pragma unroll
-        for (uint32_t i = 0; i < kPer; i++) { c[i] = ss.grp[threadIdx.x * kPer + i]; sum += c[i]; }
+        constexpr uint32_t kPer = kOrderGroups / 32;   // (the counts are read twice rather than kept in kPer registers)
+        uint32_t sum = 0;
+#pragma unroll 4
+        for (uint32_t i = 0; i < kPer; i++) sum += ss.grp[threadIdx.x * kPer + i];
         uint32_t incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)threadIdx.x >= o) incl += up;
         }
         uint32_t run = incl - sum;
-#pragma unroll
-        for (uint32_t i = 0; i < kPer; i++) { ss.grp[threadIdx.x * kPer + i] = run; run += c[i]; }
+#pragma unroll 4
+        for (uint32_t i = 0; i < kPer; i++) { const uint32_t c = ss.grp[threadIdx.x * kPer + i]; ss.grp[threadIdx.x * kPer + i] = run; run += c; }
         if (threadIdx.x == 31) ss.kept = incl;
     }
     __syncthreads();
@@ -327,9 +337,10 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint64_t *group, ui
             myRank[k] = base + r;
         }
     }
+    const uint32_t kept = ss.kept;
+    __syncthreads();   // grp[] is done with: its memory becomes the window
     // ordered accumulation with the reference's early exit (ref :394, :460, :466-502): the contributions pass through
     // a window of shared memory in rank order, kTripleThreads at a time, and one thread adds them up
-    const uint32_t kept = ss.kept;
     double mit = 0.0, cfd = 0.0;
     bool stop = false;
     if (threadIdx.x == 0) { mit = sp.totMit[guide]; cfd = sp.totCfd[guide]; }
@@ -482,7 +493,11 @@ __device__ __forceinline__ void triple_prologue(const TripleArgs &a, TripleShare
 // exactly; id, site and scores are worked out later, for all records of the guide in parallel.
 //   x: blocked scan: bucket key | (entry + 1) << 24;  contiguous scan: position in the triple's copy
 //   y: triple (0..3) | exact slices of the visit's pattern (4..8) | residual matches on slice p (9), on q (10) |
-//      blocked scan (11) | blocked scan: the entry's residual (16..31) -- with the bucket key, the whole site
+//      blocked scan (11) | occurs more than once (12) | blocked scan: the entry's residual (16..31) -- with the bucket key,
+//      the whole site.  (Leaving the residual out of the record and reading it back from the block in the tail, all lanes
+//      busy, was measured: the scan loop loses 16 % of its instructions, yet 3.91 -> 4.12 ms per 100 000 guides at maxDist 4
+//      and 28.5 -> 40.4 ms at maxDist 5 -- the tail's dependent loads stall the CTA while it requests no blocks;
+//      profiles/r02_ab_block_load.jsonl.)
 constexpr uint32_t kRecBlocked = 1u << 11;
 constexpr uint32_t kRecMulti = 1u << 12;     // blocked scan: the site occurs more than once (its count has to be looked up)
 
@@ -1213,8 +1228,9 @@ __device__ __forceinline__ uint32_t triple_sub_block(const TripleArgs &a, const 
             if (FULL != kFullSpill && slot >= cap) break;   // list full: these slots are handed back
             const uint32_t sl = __ffs(pass) - 1;
             pass &= pass - 1;
-            // the entry's residual, gathered back from the 16 planes (issue slots are cheaper than DRAM lines): every
-            // plane is shifted so that the slot's bit becomes its top bit, which a funnel shift then feeds into r
+            // the entry's residual, gathered back from the 16 planes (reading it back later costs more, see the record's
+            // description): every plane is shifted so that the slot's bit becomes its top bit, which a funnel shift then
+            // feeds into r
             const uint32_t up = 31u - sl;
             uint32_t r = 0;
             r = __funnelshift_l(q3.w << up, r, 1); r = __funnelshift_l(q3.z << up, r, 1);
@@ -1340,13 +1356,25 @@ __global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(cons
                 live = kt != 0;
             }
         }
+#if ISSL_TRIPLE_PREFETCH > 0
+        {   // the block of this lane's visit ISSL_TRIPLE_PREFETCH rounds ahead: requested into L2 now, so that the round that
+            // needs it waits for an L2 hit rather than for DRAM (no registers held, unlike a second visit in flight)
+            const uint32_t en = e + ISSL_TRIPLE_PREFETCH * V;
+            if (en < v1) {
+                const uint2 vn = __ldg(visits + en);
+                const uint32_t tn = (vn.x >> 24) & 15u;
+                const uint4 *pn = a.tv.blk + ((((uint64_t)tn << 24) | (sh.key[tn] ^ (vn.x & 0xFFFFFFu))) * SUBS + sub0) * 4;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+            }
+        }
+#endif
         if (live) {
             t = (v.x >> 24) & 15u; key = sh.key[t] ^ (v.x & 0xFFFFFFu);
             const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub0) * 4;
             // read once: streaming loads, so that the visit table and the offsets keep their place in L1
 #pragma unroll
             for (int s = 0; s < LSUBS; s++) {
-                q[s][0] = __ldcs(p + 4 * s); q[s][1] = __ldcs(p + 4 * s + 1); q[s][2] = __ldcs(p + 4 * s + 2); q[s][3] = __ldcs(p + 4 * s + 3);
+                q[s][0] = ISSL_BLOCK_LOAD(p + 4 * s); q[s][1] = ISSL_BLOCK_LOAD(p + 4 * s + 1); q[s][2] = ISSL_BLOCK_LOAD(p + 4 * s + 2); q[s][3] = ISSL_BLOCK_LOAD(p + 4 * s + 3);
             }
             if constexpr (GATES) { if (sub0 == 0) visited++; }   // (without gates every visit is read: counted after the loop)
             if ((q[0][1].y & 1u) && sub0 == 0) {   // more entries than the block holds: noted for after the loop
@@ -1472,7 +1500,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_small(const Trip
         const uint2 v = __ldg(visits + e);
         const uint32_t t = (v.x >> 24) & 15u, key = w.key[t] ^ (v.x & 0xFFFFFFu);
         const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
-        const uint4 q0 = __ldcs(p), q1 = __ldcs(p + 1), q2 = __ldcs(p + 2), q3 = __ldcs(p + 3);
+        const uint4 q0 = ISSL_BLOCK_LOAD(p), q1 = ISSL_BLOCK_LOAD(p + 1), q2 = ISSL_BLOCK_LOAD(p + 2), q3 = ISSL_BLOCK_LOAD(p + 3);
         if (sub == 0) visited++;
         if ((q1.y & 1u) && sub == 0) {   // more entries than the block holds: this lane reads the rest from the contiguous copy
             const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;

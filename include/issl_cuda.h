@@ -169,6 +169,25 @@ int issl_device_create_synthetic(int cuda_device, int layout, uint64_t seed, uin
                                  uint32_t families, uint32_t family_size, double max_sub_rate,
                                  uint32_t seqLength, uint32_t sliceWidth, issl_device **out);
 
+/* The same with the repeat structure BASELINE.json configs[3] / SURVEY.md 8d (C4) asks for: family sizes drawn
+ * log-uniformly from [family_size_min, family_size_max] (equal: fixed), and low_complexity_fraction x (uniform + family
+ * sites) further sites that overlap a poly-A / poly-T / dinucleotide tract (10-20 bases of the repeat on one side of the
+ * window, 2 % of them substituted): they skew the slice-list lengths and give sites that occur thousands of times. */
+typedef struct issl_synth_spec {
+    uint64_t seed;
+    uint64_t uniform_sites;
+    uint32_t families;
+    uint32_t family_size_min, family_size_max;
+    double max_sub_rate;
+    double low_complexity_fraction;
+    uint32_t seqLength, sliceWidth;
+} issl_synth_spec;
+int issl_device_create_synthetic_ex(int cuda_device, int layout, const issl_synth_spec *spec, issl_device **out);
+
+/* Lengths of the index's slice lists, slice-major (ref allSlicelistSizes, isslScoreOfftargets.cpp:204-216): returns the
+ * number of lists (sliceCount << min(sliceWidth, ...)) and fills out[0..min(cap, lists)).  For list-length histograms. */
+size_t issl_device_list_lengths(const issl_device *dev, uint64_t *out, size_t cap);
+
 /* Builds the index on the device from the text file isslCreateIndex reads: fixed-width lines of seqLength
  * bases + LF, sorted, duplicates adjacent.  Replaces isslCreateIndex.cpp:138-252 (record packing :39-47,
  * run-length collapse of identical adjacent lines into occurrence counts :184-207, slice lists with the 8-bit
@@ -287,6 +306,19 @@ void issl_host_free(void *p);
 #define ISSL_FILTER_TTTT 8u       /* mm10db: "TTTT" in target23                                       (:378-384) */
 int issl_guide_filters(issl_device *dev, const char *text, size_t bytes, uint8_t *flags_out, double *at_out,
                        uint64_t *packed_out);
+
+/* Duplicate candidate guides, /root/reference/src/crackling/Crackling.py:211-240 and :291-296, as one device pass over the
+ * same text (n lines of 23 characters + LF, in the order the pipeline discovers them): the 23-mers are packed to 46-bit
+ * keys, sorted stably with their positions, and runs of equal keys are read off.  flags_out[i] (required) gets
+ *   ISSL_FILTER_DUPLICATE  when an equal target23 occurs EARLIER in the text: the pipeline keeps only the first
+ *                          occurrence in candidateGuides and counts this one in numDuplicateGuides (:221-224);
+ *   ISSL_FILTER_NOT_UNIQUE when the target23 occurs more than once at all (it is in duplicateGuides: isUnique = rejected,
+ *                          position fields ambiguous, :291-296) -- set on the first occurrence too.
+ * n_later (optional) = numDuplicateGuides, n_sequences (optional) = len(duplicateGuides) for this text. */
+#define ISSL_FILTER_DUPLICATE 16u
+#define ISSL_FILTER_NOT_UNIQUE 32u
+int issl_guide_duplicates(issl_device *dev, const char *text, size_t bytes, uint8_t *flags_out, uint64_t *n_later,
+                          uint64_t *n_sequences);
 
 /* ---- builder-side arithmetic (used by the synthetic builder; exposed for parity tests) ---- */
 

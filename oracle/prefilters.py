@@ -38,3 +38,26 @@ def encode20(target23: str) -> int:
     """What the scorer packs from the line Crackling.py:750-751 writes (isslScoreOfftargets.cpp:63-71, :99-102)."""
     lut = {'A': 0, 'C': 1, 'G': 2, 'T': 3}
     return sum(lut.get(c, 0) << (2 * j) for j, c in enumerate(target23[0:20]))
+
+
+FILTER_DUPLICATE, FILTER_NOT_UNIQUE = 16, 32
+
+
+def duplicates(targets23):
+    """Crackling.py:211-240 over the targets in discovery order, and what :291-296 later derives from it:
+    (flags per target, numDuplicateGuides, len(duplicateGuides))."""
+    candidateGuides = set()
+    duplicateGuides = set()
+    numDuplicateGuides = 0
+    later = []
+    for guide in targets23:
+        if guide not in candidateGuides:                              # Crackling.py:221
+            candidateGuides.add(guide)
+            later.append(False)
+        else:
+            duplicateGuides.add(guide)                                # Crackling.py:228
+            numDuplicateGuides += 1
+            later.append(True)
+    flags = [(FILTER_DUPLICATE if l else 0) | (FILTER_NOT_UNIQUE if g in duplicateGuides else 0)   # :291 `if row[0] in duplicateGuides`
+             for g, l in zip(targets23, later)]
+    return flags, numDuplicateGuides, len(duplicateGuides)

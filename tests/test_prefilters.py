@@ -57,3 +57,74 @@ def test_device_filters_match_oracle():
     with pytest.raises(cb.IsslError):
         dev.guide_filters(text[:-1])
     dev.close()
+
+
+DUP_GOLDEN = json.loads((pathlib.Path(__file__).parent / "golden" / "duplicates.json").read_text())
+
+
+def test_oracle_duplicates_match_reference_loop():
+    """oracle.prefilters.duplicates against what the reference's own loop (Crackling.py:231-241, executed by
+    tests/golden/make_duplicates_golden.py) recorded, dropped and called not unique."""
+    assert sum(c["numDuplicateGuides"] for c in DUP_GOLDEN) > 2000
+    for c in DUP_GOLDEN:
+        flags, later, seqs = pf.duplicates(c["targets"])
+        assert later == c["numDuplicateGuides"] and seqs == len(c["duplicateGuides"])
+        assert [i for i, f in enumerate(flags) if not f & pf.FILTER_DUPLICATE] == c["recorded"]
+        dup = set(c["duplicateGuides"])
+        assert all(bool(f & pf.FILTER_NOT_UNIQUE) == (t in dup) for f, t in zip(flags, c["targets"]))
+
+
+@pytest.mark.gpu
+def test_device_duplicates_match_oracle():
+    """issl_guide_duplicates (pack, stable sort, run heads) against the oracle: the reference's vectors, and 300 000
+    targets drawn from a pool small enough that most sequences repeat."""
+    from conftest import golden_case
+    case = golden_case("w8_families")
+    dev = cb.Device.from_index(cb.Index(case.issl), 0, "res32")
+    rng = np.random.default_rng(8)
+    pool = ["".join(rng.choice(list("ACGT"), 23)) for _ in range(60_000)]
+    big = [pool[i] for i in rng.integers(0, len(pool), 300_000)]
+    for targets in [c["targets"] for c in DUP_GOLDEN] + [big]:
+        text = ("\n".join(targets) + "\n").encode() if targets else b""
+        flags, later, seqs = dev.guide_duplicates(text)
+        want, wlater, wseqs = pf.duplicates(targets)
+        assert (later, seqs) == (wlater, wseqs)
+        assert np.array_equal(flags, np.array(want, dtype=np.uint8))
+    with pytest.raises(cb.IsslError):
+        dev.guide_duplicates(b"ACGT\n")
+    dev.close()
+
+
+@pytest.mark.gpu
+def test_pipeline_page_without_temp_files(tmp_path):
+    """crackling_b200.pipeline.OfftargetScorer.score_page replaces Crackling.py:737-786 (guide file, subprocess, output
+    file): the dictionary it returns is what the pipeline would have parsed from the reference binary's output."""
+    import subprocess
+    from conftest import golden_case
+    from crackling_b200.pipeline import OfftargetScorer, FILTER_DUPLICATE
+    case = golden_case("w8_families")
+    issl = tmp_path / "index.issl"
+    issl.write_bytes(bytes(case.issl))
+    rng = np.random.default_rng(9)
+    guides20 = [l.decode() for l in case.guides.split(b"\n") if l]
+    targets = [g + "".join(rng.choice(list("ACGT"), 1)) + "GG" for g in guides20]
+    targets += targets[:7]                                    # duplicates: the pipeline would have dropped these
+    with OfftargetScorer(str(issl)) as scorer:
+        flags, at, later, seqs = scorer.candidate_flags(targets)
+        assert later == 7 and seqs == 7 and np.count_nonzero(flags & FILTER_DUPLICATE) == 7
+        page = [t for t, f in zip(targets, flags) if not f & FILTER_DUPLICATE]
+        for method, thr in (("and", 0.0), ("mit", 75.0), ("cfd", 50.0)):
+            got = scorer.score_page(page, 4, thr, method)
+            # what the reference pipeline does: guide file -> binary -> output file -> dict (Crackling.py:747-786)
+            gfile, ofile = tmp_path / "guides.txt", tmp_path / "out.txt"
+            gfile.write_text("".join(t[0:20] + "\n" for t in page))
+            exe = pathlib.Path(__file__).parent.parent / "oracle" / "_ref" / "isslScoreOfftargets"
+            if not exe.exists():
+                exe = cb.cli_path()                           # (GPU box without the reference build: our own drop-in)
+            with open(ofile, "w") as fo:
+                subprocess.run([str(exe), str(issl), str(gfile), "4", str(thr), method], stdout=fo, check=True)
+            want = {}
+            for f in [x.split("\t") for x in ofile.read_text().splitlines(True)]:
+                if len(f) == 3:
+                    want[f[0]] = {"MIT": float(f[1].strip()), "CFD": float(f[2].strip())}
+            assert got == want and len(got) == len(set(t[:20] for t in page))
