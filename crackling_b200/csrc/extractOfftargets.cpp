@@ -108,7 +108,7 @@ int main(int argc, char **argv)
     const double t2 = now_s();
     if (!indexPath.empty()) {
         issl_device *dev = nullptr;
-        if (issl_device_create_from_sites(sites, (uint32_t)sliceWidth, ISSL_LAYOUT_AUTO, &dev) != ISSL_OK ||
+        if (issl_device_create_from_sites(sites, (uint32_t)sliceWidth, ISSL_LAYOUT_GATHER /* ids-only lists: all the .issl writer needs */, &dev) != ISSL_OK ||
             issl_device_write_issl(dev, indexPath.c_str()) != ISSL_OK) {
             fprintf(stderr, "%s\n", issl_last_error());
             return 1;

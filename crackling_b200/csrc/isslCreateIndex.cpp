@@ -76,7 +76,7 @@ int main(int argc, char **argv)
 
     issl_device *dev = nullptr;
     if (issl_device_create_from_text((const char *)text, fileSize, (uint32_t)seqLength, (uint32_t)sliceWidth, device,
-                                     ISSL_LAYOUT_AUTO, &dev) != ISSL_OK) {
+                                     ISSL_LAYOUT_GATHER, &dev) != ISSL_OK) {   // ids-only lists: all the .issl writer needs (no sub-bucket copies)
         fprintf(stderr, "%s\n", issl_last_error());
         return 1;
     }

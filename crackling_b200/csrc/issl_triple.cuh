@@ -224,6 +224,9 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, const
 #ifndef ISSL_BLOCK_LOAD
 #define ISSL_BLOCK_LOAD __ldcs
 #endif
+#ifndef ISSL_TRIPLE_MIN_CTAS
+#define ISSL_TRIPLE_MIN_CTAS 10   // resident CTAs per SM the scan kernel is compiled for (48 registers); 8, 9, 12 measured slower
+#endif
 #ifndef ISSL_TRIPLE_PREFETCH
 #define ISSL_TRIPLE_PREFETCH 0
 #endif
@@ -1266,7 +1269,7 @@ __device__ __forceinline__ uint32_t triple_sub_block(const TripleArgs &a, const 
 // then sorted and finished by this CTA, heavy_finish) or, without that buffer, into the general pipeline's -- and a hit
 // that found the list full is tried again afterwards: nothing is ever dropped and nothing leaves the CTA hit by hit.
 template <int SUBS, bool FUSED, bool FLUSH, bool GATES = false>
-__global__ void __launch_bounds__(kTripleThreads, 10) k_scan_triple_blocked(const TripleArgs a)
+__global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_triple_blocked(const TripleArgs a)
 {
     constexpr int LSUBS = 1;   // sub-blocks per lane
     const uint32_t guide = a.guideList ? a.guideList[blockIdx.x] : blockIdx.x;   // (the guides the warp-per-guide kernel left)

@@ -25,11 +25,15 @@ def main():
     ap.add_argument("--guides", type=int, default=4000, help="batch scored by the GPU (>= 2368 so that every guide owns a CTA)")
     ap.add_argument("--check", type=int, default=320, help="guides of the batch also scored by the oracle, per combination")
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--slice-width", type=int, default=8, help="4 and 10 as well: the oracle walks 31x more list entries per guide at w = 4, so use --check 32")
+    ap.add_argument("--dists", default="2,3,4,5")
+    ap.add_argument("--methods", default="and,or,avg,mit,cfd")
+    ap.add_argument("--thresholds", default="0,50,75,90")
     a = ap.parse_args()
     dev = cb.Device.synthetic(0, "auto", seed=a.seed, uniform_sites=a.sites, families=a.families, family_size=a.family_size,
-                              max_sub_rate=0.12)
+                              max_sub_rate=0.12, slice_width=a.slice_width)
     guides = make_guides(dev, a.guides, seed=11, families=a.families, family_frac=0.3, index_seed=a.seed)
-    out = {"sites": dev.info["offtargetsCount"], "layout": dev.info["layout"], "guides": int(guides.size), "checked_per_combo": a.check,
+    out = {"sites": dev.info["offtargetsCount"], "slice_width": a.slice_width, "layout": dev.info["layout"], "guides": int(guides.size), "checked_per_combo": a.check,
            "combos": [], "mismatches": 0}
     with tempfile.TemporaryDirectory(dir="/dev/shm") as tmp:
         path = os.path.join(tmp, "index.issl")
@@ -38,9 +42,9 @@ def main():
         os.unlink(path)
         rng = np.random.default_rng(3)
         t0 = time.perf_counter()
-        for md in (2, 3, 4, 5):
-            for method in ("and", "or", "avg", "mit", "cfd"):
-                for thr in (0.0, 50.0, 75.0, 90.0):
+        for md in [int(x) for x in a.dists.split(",")]:
+            for method in a.methods.split(","):
+                for thr in [float(x) for x in a.thresholds.split(",")]:
                     mit, cfd = dev.score(guides, md, thr, method)
                     st = dev.stats
                     pick = np.sort(rng.choice(guides.size, a.check, replace=False))
@@ -52,7 +56,7 @@ def main():
                         bad += int((cfd[pick].view(np.uint64) != want["cfd"].view(np.uint64)).sum())
                     out["mismatches"] += bad
                     out["combos"].append({"maxDist": md, "method": method, "threshold": thr, "hits_per_guide": st["hits"] / guides.size,
-                                          "early_exits": st["early_exits"], "bit_mismatches": bad})
+                                          "early_exits": st["early_exits"], "heavy_hits": st["heavy_hits"], "bit_mismatches": bad})
         out["seconds"] = time.perf_counter() - t0
     dev.close()
     print(json.dumps(out))
