@@ -53,6 +53,7 @@ struct issl_device {
     DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites, totMit2, totCfd2, done2;
     uint64_t segCap = 0;
     DBuf redo;                       // guides the warp-per-guide kernel left to the CTA-per-guide kernel
+    DBuf ovfBits;                    // non-flush scan: one bit per (CTA, visit) whose bucket overflows its block beyond the shared-memory list
     int tripleSmall = 1;             // ISSL_TRIPLE_SMALL=0: never use the warp-per-guide kernel
     DBuf heavyDesc, heavyFlat;       // k_heavy_finish: one descriptor per heavy guide; the second half of its sort's ping-pong
     DBuf heavyKeys;                  // sort keys of the guides with more hits than a CTA's record list holds (heavy_finish)
@@ -397,7 +398,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->heavyDesc, &d->heavyFlat, &d->redo, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
+                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->heavyDesc, &d->heavyFlat, &d->redo, &d->ovfBits, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
                     &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
@@ -1114,6 +1115,13 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             }
             CK(cudaMemsetAsync(dc + 1, 0, 8, st));
             CK(cudaMemsetAsync(dc + 4, 0, 72, st));
+            // overflow bitmap of the non-flush scan (issl_triple.cuh): a row per CTA
+            const uint32_t visitsPerCta = (nv + chunks - 1) / chunks, ovfWords = (visitsPerCta + 31) / 32;
+            const bool ovfBitmap = d->tv.pitch && !flush && visitsPerCta <= 65536;
+            if (ovfBitmap) {
+                CKR(d->ovfBits.ensure((size_t)n * chunks * ovfWords * 4));
+                CK(cudaMemsetAsync(d->ovfBits.p, 0, (size_t)n * chunks * ovfWords * 4, st));
+            }
             if (fuse) CK(cudaMemsetAsync(d->segCnt.p, 0, n * 4ull, st));
             TripleArgs a;
             a.tv = d->tv; a.guides = dGuides; a.done = doneMask; a.visits = d->visits.as<TripleVisit>() + v0;
@@ -1127,6 +1135,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             a.fusedHits = dc + 7; a.maxRecords = dc + 2;
             a.heavyKeys = heavy ? d->heavyKeys.as<uint64_t>() : nullptr; a.heavyCount = dc + 8; a.heavyCap = heavy ? d->heavyCap : 0;
             a.heavyHits = dc + 9; a.heavyDesc = heavy ? d->heavyDesc.as<HeavyDesc>() : nullptr; a.heavyGuides = dc + 11;
+            a.ovfBits = ovfBitmap ? d->ovfBits.as<uint32_t>() : nullptr; a.ovfWords = ovfWords;
             a.nGuides = n; a.redo = small ? d->redo.as<uint32_t>() : nullptr; a.redoCount = dc + 10; a.guideList = nullptr;
             cudaEvent_t e0, e1;
             CKR(timer.get(&e0)); CKR(timer.get(&e1));

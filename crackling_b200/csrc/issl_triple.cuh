@@ -428,6 +428,10 @@ struct TripleArgs {
     unsigned long long *heavyGuides;
     // warp-per-guide kernel (k_scan_triple_small): guides it cannot finish (more hits than a warp's list holds, a long
     // bucket remainder: repeat families) are listed in redo[]; the CTA-per-guide kernel then runs for exactly those (guideList)
+    // visits whose bucket overflows its block, beyond the kTripleOvfCap a CTA notes in shared memory: one bit per visit, one
+    // row of ovfWords words per CTA (zeroed before the launch); nullptr: such visits are finished by the lane that met them
+    uint32_t *ovfBits;
+    uint32_t ovfWords;
     uint32_t nGuides;
     uint32_t *redo;
     unsigned long long *redoCount;
@@ -1384,7 +1388,13 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
                 const uint32_t slot = atomicAdd(&sh.nOvf, 1u);
                 if (slot < kTripleOvfCap) sh.ovf[slot] = (uint16_t)e;   // visit tables have fewer than 2^16 entries
                 else if constexpr (FLUSH) ovfPending = true;
-                else {   // list full (dense repeat families): this lane reads the rest alone
+                else if (a.ovfBits) {
+                    // list full: one bit per visit in this CTA's row of a global bitmap (L2), read back after the loop.  Indexes
+                    // whose sites are not uniform need this: the reference's extractor takes the reverse strand's site from
+                    // the wrong end of its match (extractOfftargets.py:97-106), so half of a real index's sites end in AG / GG,
+                    // the buckets keyed on those values are 4.5 x fuller than the mean and most visits of such a guide overflow
+                    atomicOr(a.ovfBits + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * a.ovfWords + ((e - v0) >> 5), 1u << ((e - v0) & 31u));
+                } else {   // (no bitmap: this lane reads the rest alone)
                     const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;
                     scan_range(v, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), 0, 1);
                 }
@@ -1441,6 +1451,32 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
                 if (isLong) end = start;
             }
             scan_range(vo, start, end, gl, 8);
+        }
+        if constexpr (!FLUSH) {
+            if (sh.nOvf > kTripleOvfCap && a.ovfBits) {   // CTA-uniform: the visits noted in the bitmap, a word per group of eight lanes
+                const uint32_t *bits = a.ovfBits + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * a.ovfWords;
+                const uint32_t gl = threadIdx.x & 7u, words = (v1 - v0 + 31u) >> 5;
+                for (uint32_t w = threadIdx.x >> 3; w < words; w += kTripleThreads / 8) {
+                    uint32_t word = __ldcg(bits + w);
+                    while (word) {
+                        const uint32_t e = v0 + (w << 5) + (uint32_t)__ffs(word) - 1u;
+                        word &= word - 1u;
+                        const uint2 vo = __ldg(visits + e);
+                        const uint32_t to = (vo.x >> 24) & 15u;
+                        const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
+                        uint32_t start = __ldg(o) + SUBS * kSubEntries;
+                        const uint32_t end = __ldg(o + 1);
+                        uint32_t isLong = 0;
+                        if (gl == 0 && end - start > kTripleLongBucket) {
+                            const uint32_t slot = atomicAdd(&sh.nLong, 1u);
+                            if (slot < kTripleLongCap) { sh.longList[slot] = (uint16_t)e; isLong = 1; }
+                        }
+                        isLong = __shfl_sync(0xffu << (threadIdx.x & 24u), isLong, 0, 8);
+                        if (isLong) start = end;
+                        scan_range(vo, start, end, gl, 8);
+                    }
+                }
+            }
         }
         __syncthreads();
         const uint32_t nLong = min(sh.nLong, kTripleLongCap);

@@ -848,3 +848,48 @@ def test_resident_server_is_invisible_to_the_caller(tmp_path):
     r = subprocess.run([exe, str(idx), str(ga), "4", "0", "and"], capture_output=True, env=env2, timeout=300)
     run_ = next(r_ for r_ in a.expected["runs"] if r_["method"] == "and" and r_["maxDist"] == 4 and float(r_["threshold"]) == 0)
     assert r.returncode == 0 and r.stdout.decode() == run_["stdout"] and b"scoring in-process" in r.stderr
+
+
+@pytest.mark.parametrize("flush", ["0", None])
+def test_triple_skewed_index_many_overflowing_buckets(flush):
+    """Indexes made by the reference's extractor are not uniform: it takes the reverse strand's site from the wrong end of
+    its match (extractOfftargets.py:97-106), so half of the sites end in AG / GG and the sub-buckets keyed on those values
+    are several times fuller than the mean.  Here: 60 000 uniform sites + 150 000 sites over a two-letter alphabet ending in
+    [AG]G, blocks of 31 slots: a guide of the second kind meets ~130 buckets that overflow their block -- more than the 64
+    a CTA notes in shared memory, so the rest go through the global bitmap (non-flush scan) or are finished whenever the list
+    fills (flush scan).  Scores bit-identical to the oracle either way."""
+    rng = np.random.default_rng(71)
+    F = rng.integers(0, 4, (60_000, 20), dtype=np.uint8)
+    F[:, 0] = rng.integers(0, 3, 60_000)
+    R = rng.integers(0, 2, (150_000, 20), dtype=np.uint8)
+    R[:, 18] = rng.integers(0, 2, 150_000) * 2
+    R[:, 19] = 2
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lines = sorted(bytes(r) for r in letters[np.concatenate([F, R, R[:500]])])      # (some sites occur twice)
+    text = b"".join(l + b"\n" for l in lines)
+    img = oracle.create_index(text, 20, 8)
+    pick = np.concatenate([R[rng.integers(0, len(R), 1700)], F[rng.integers(0, len(F), 500)],
+                           rng.integers(0, 4, (300, 20), dtype=np.uint8)]).copy()
+    for row in pick[: 1200]:
+        for pos in rng.choice(20, size=int(rng.integers(0, 3)), replace=False):
+            row[pos] = (row[pos] + rng.integers(1, 4)) % 4
+    guides = td.pack_guides(b"".join(bytes(r) + b"\n" for r in letters[pick]))
+    os.environ["ISSL_TRIPLE_BLOCKS"] = "32"
+    if flush is not None:
+        os.environ["ISSL_TRIPLE_FLUSH"] = flush
+    try:
+        dev = cb.Device.from_index(cb.Index(img), 0, "triple")
+    finally:
+        del os.environ["ISSL_TRIPLE_BLOCKS"]
+        os.environ.pop("ISSL_TRIPLE_FLUSH", None)
+    assert dev.info["triple_block_bytes"] == 64
+    for method, thr, md in (("and", 0, 4), ("and", 75, 4), ("mit", 0, 3), ("or", 50, 4), ("cfd", 0, 2)):
+        want = oracle.score(img, guides, md, thr, method, threads=0, want_candidates=True)
+        mit, cfd = dev.score(guides, md, thr, method)
+        if method != "cfd":
+            assert np.array_equal(mit.view(np.uint64), want["mit"].view(np.uint64)), (flush, method, thr, md)
+        if method != "mit":
+            assert np.array_equal(cfd.view(np.uint64), want["cfd"].view(np.uint64)), (flush, method, thr, md)
+    st = dev.stats
+    assert st["bucket_visits"] > 0
+    dev.close()
