@@ -119,7 +119,8 @@ def main():
                         # OpenMP region (isslScoreOfftargets.cpp:394, operator[]): with distances the table was not built for
                         # (w = 8: maxDist 5, w = 10: maxDist >= 4) concurrent insertions crash it; one thread is safe
                         line["reference_multithreaded"] = f"exit code {p.returncode} with {cores} OpenMP threads ({p.stderr.decode()[-120:].strip()!r}); rerun with OMP_NUM_THREADS=1"
-                        k, threads = min(k, 24), 1
+                        # ~6 s of single-threaded scoring, so that the noise of the index load time (+-0.5 s of ~15 s) stays small
+                        k, threads = int(max(24, min(400, 6.0 / (per_guide_s * cores)))), 1
                         bench.write_guide_file(gpath, guides[:k])
                         t_all, p = run_reference(exe, issl, gpath, md, dict(env, OMP_NUM_THREADS="1"))
                     t = max(t_all - t_load, 1e-6)
