@@ -1090,7 +1090,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         // order keys: site text ranks (40 bits) when the index is in text order, site ids otherwise
         uint32_t idShift = 0;
         while (idShift < 28 && (d->info.offtargetsCount >> idShift) > kKeyBuckets) idShift++;
-        sp.keyShift = d->tv.siteOrdered ? 34u : idShift;   // (text keys have 40 bits)
+        sp.keyShift = idShift; sp.byFirstMismatch = d->tv.siteOrdered ? 1u : 0u;
         sp.calcMit = ws.calcMit; sp.calcCfd = ws.calcCfd; sp.method = ws.method; sp.checkExit = ws.checkExit;
         sp.maximumSum = ws.maximumSum;
         sp.totMit = d->totMit.as<double>(); sp.totCfd = d->totCfd.as<double>(); sp.done = d->done.as<uint8_t>();
@@ -1201,7 +1201,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             sa.segKeys = d->segKeys.as<uint64_t>(); sa.segSites = d->segSites.as<uint64_t>();
             sa.segOff = d->segOff.as<uint64_t>(); sa.segCnt = d->segCnt.as<uint32_t>();
             sa.guides = dGuides; sa.sp = sp;
-            sa.sp.keyShift = idShift;   // segments are ordered by id
+            sa.sp.keyShift = idShift; sa.sp.byFirstMismatch = 0;   // segments are ordered by id
             k_score_segments<<<n, kTripleThreads, 0, st>>>(sa);
             CK(cudaGetLastError());
             d->stats.launches += 1;

@@ -250,7 +250,8 @@ struct ScoreParams {
     const uint32_t *occ;          // [N] occurrences
     uint64_t nSites;              // N
     uint32_t occFlag;             // ids carry "occurs more than once" in bit 31
-    uint32_t keyShift;            // order keys >> keyShift lie in [0, kKeyBuckets]: 34 for site text keys, from the site count for ids
+    uint32_t keyShift;            // order keys that are ids: id >> keyShift lies in [0, kKeyBuckets]
+    uint32_t byFirstMismatch;     // order keys are site text ranks: groups by the first mismatch with the guide (first_mismatch_group)
     ScoreTables tb;
     int calcMit, calcCfd, method, checkExit;
     double maximumSum;
@@ -259,16 +260,30 @@ struct ScoreParams {
 };
 
 // Hits are put into the reference's accumulation order -- slice, then ascending site id inside the slice (ref :330-344) --
-// by a counting pass over (slice, 1/64 of the key range) groups followed by a rank inside the group: a guide's
-// ~275 hits fall into ~240 groups of one or two hits each, so the rank is a comparison or two (with 16 key ranges per
-// slice this loop was 12.5 % of the kernel's instructions: a warp pays for the largest group among its lanes).
-constexpr uint32_t kKeyBuckets = 64;
+// by a counting pass over (slice, key range) groups followed by a rank inside the group.  The groups have to be small for
+// the rank to be cheap, and leading key bits do not make them small: a guide's hits are its near neighbours, half of them
+// share its first three bases (with 16 or 64 ranges of leading text bits this loop was 11-12 % of the kernel's instructions,
+// profiles/r02_ncu_source_*).  On an index in text order the groups are therefore cut where the hits differ FROM THE GUIDE:
+// f = position of a site's first mismatch, and whether its base there is below or above the guide's.  Sites below the guide
+// sort before it, by ascending f (one that leaves the guide earlier, downwards, precedes one that still follows it); sites
+// above it sort after it, by descending f: group = f | 20 (the guide itself) | 40 - f, monotone in text order, and the
+// largest group holds a fifth of a slice's hits.  Indexes that are not in text order fall back to ranges of the id.
+constexpr uint32_t kKeyBuckets = 41;
 constexpr uint32_t kOrderGroups = kOrderSlices * kKeyBuckets;
+
+__device__ __forceinline__ uint32_t first_mismatch_group(uint64_t site, uint64_t g)
+{
+    const uint64_t x = site ^ g;
+    if (x == 0) return 20u;
+    const uint32_t f = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
+    const uint32_t sb = (uint32_t)(site >> (2 * f)) & 3u, gb = (uint32_t)(g >> (2 * f)) & 3u;
+    return sb < gb ? f : 40u - f;
+}
 
 struct ScoreShared {
     union {   // (shared memory per SM is L1 the scan cannot use: the two never live at the same time)
         struct { double mit[kTripleThreads], cfd[kTripleThreads]; };   // a window of contributions in accumulation order
-        uint32_t grp[kOrderGroups];                                    // per group: count -> first position -> end position
+        uint32_t grp[(kOrderGroups + 31) / 32 * 32];                   // per group: count -> first position -> end position
     };
     uint32_t kept;
 };
@@ -276,14 +291,14 @@ constexpr uint32_t kScoreGroupWords = kTripleHitCap;   // one 64-bit order key p
 
 // load(j, slice, site, occ, orderKey): hit j of the guide -- the slice through which the reference meets it first
 // (kNoSlice: not a hit here), its signature, its occurrences, and a key that ascends as the site id does (the id itself,
-// or the site's text rank).  sp.keyShift: orderKey >> keyShift < 16.  group[] may alias whatever load() reads: it is
+// or the site's text rank).  group[] may alias whatever load() reads: it is
 // first written after a barrier that follows the last load.  Results go to totMitOut/totCfdOut/doneOut[guide].
 template <class Load>
 __device__ __forceinline__ void score_guide(ScoreShared &ss, uint64_t *group, uint32_t n, uint32_t guide, uint64_t g,
                                             const ScoreParams &sp, double *totMitOut, double *totCfdOut, uint8_t *doneOut, Load load)
 {
     constexpr uint32_t kPerThread = kTripleHitCap / kTripleThreads;
-    for (uint32_t i = threadIdx.x; i < kOrderGroups; i += kTripleThreads) ss.grp[i] = 0;
+    for (uint32_t i = threadIdx.x; i < (kOrderGroups + 31) / 32 * 32; i += kTripleThreads) ss.grp[i] = 0;   // (padded for the prefix sum)
     __syncthreads();
     uint32_t myGroup[kPerThread];
     uint64_t myKey[kPerThread];
@@ -298,7 +313,7 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint64_t *group, ui
             load(j, slice, site, occ, key);
             if (slice >= kOrderSlices) continue;   // not a hit in this triple (the triple responsible for it reports it)
             myKey[k] = key;
-            myGroup[k] = slice * kKeyBuckets + min((uint32_t)(key >> sp.keyShift), kKeyBuckets - 1);
+            myGroup[k] = slice * kKeyBuckets + (sp.byFirstMismatch ? first_mismatch_group(site, g) : min((uint32_t)(key >> sp.keyShift), kKeyBuckets - 1));
             atomicAdd(&ss.grp[myGroup[k]], 1u);
             double cm, cc;
             int dist;
@@ -308,7 +323,8 @@ __device__ __forceinline__ void score_guide(ScoreShared &ss, uint64_t *group, ui
     }
     __syncthreads();
     if (threadIdx.x < 32) {   // counts -> first positions (exclusive prefix sum by one warp)
-        constexpr uint32_t kPer = kOrderGroups / 32;   // (the counts are read twice rather than kept in kPer registers)
+        constexpr uint32_t kPer = (kOrderGroups + 31) / 32;   // (the counts are read twice rather than kept in kPer registers)
+        static_assert(kPer * 32 <= sizeof(ss.mit) / 4 + sizeof(ss.cfd) / 4, "grp[] is padded to a multiple of 32 inside the window's memory");
         uint32_t sum = 0;
 #pragma unroll 4
         for (uint32_t i = 0; i < kPer; i++) sum += ss.grp[threadIdx.x * kPer + i];
@@ -1341,6 +1357,42 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
         if (gl == 0 && start < end) entries += end - start;
     };
 
+    // the first n buckets of the noted list (visits whose bucket has more entries than its block holds): their remainders
+    // from the contiguous copy, sixteen buckets at a time, eight lanes each; long remainders (repeat families) are noted once
+    // more and shared by all threads.  One remainder is a chain of dependent loads (offsets, then residuals): what counts is
+    // how many chains are in flight.  Called by all threads of the CTA.
+    auto process_noted = [&](const uint32_t n) {
+        for (uint32_t j0 = 0; j0 < n; j0 += kTripleThreads / 8) {
+            const uint32_t j = j0 + (threadIdx.x >> 3), gl = threadIdx.x & 7u;
+            uint2 vo = make_uint2(0, 0);
+            uint32_t start = 0, end = 0;
+            if (j < n) {
+                vo = __ldg(visits + sh.ovf[j]);
+                const uint32_t to = (vo.x >> 24) & 15u;
+                const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
+                start = __ldg(o) + SUBS * kSubEntries; end = __ldg(o + 1);
+                uint32_t isLong = 0;
+                if (gl == 0 && end - start > kTripleLongBucket) {
+                    const uint32_t slot = atomicAdd(&sh.nLong, 1u);
+                    if (slot < kTripleLongCap) { sh.longList[slot] = sh.ovf[j]; isLong = 1; }
+                }
+                isLong = __shfl_sync(0xffu << (threadIdx.x & 24u), isLong, 0, 8);
+                if (isLong) end = start;
+            }
+            scan_range(vo, start, end, gl, 8);
+        }
+    };
+    auto process_long = [&]() {   // one bucket at a time, all threads
+        __syncthreads();
+        const uint32_t nLong = min(sh.nLong, kTripleLongCap);
+        for (uint32_t j = 0; j < nLong; j++) {
+            const uint2 vo = __ldg(visits + sh.longList[j]);
+            const uint32_t to = (vo.x >> 24) & 15u;
+            const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
+            scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
+        }
+    };
+
     for (uint32_t e0 = v0; e0 < v1; e0 += V) {   // the same number of rounds for every thread of the CTA
         const uint32_t e = e0 + vslot;
         uint2 v = make_uint2(0, 0);
@@ -1410,16 +1462,14 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
                 for (int s = 0; s < LSUBS; s++)
                     if (left[s]) left[s] = sub_block(v, t, key, sub0 + s, q[s][0], q[s][1], q[s][2], q[s][3], left[s], false);
             }
-            // the list of noted buckets is full: finish them now (all threads), so that none is ever skipped
+            // the list of noted buckets is full: finish them now, so that none is ever skipped (sixteen at a time -- one bucket
+            // at a time with all threads, as this was first written, left 116 of 128 threads idle on a 94-entry remainder:
+            // 23.4 ms per 100 000 guides on an index made by the reference's extractor)
             while (__syncthreads_or(sh.nOvf >= kTripleOvfCap)) {
+                process_noted(kTripleOvfCap);
+                process_long();
                 __syncthreads();
-                if (threadIdx.x == 0) sh.nOvf = 0;
-                for (uint32_t j = 0; j < kTripleOvfCap; j++) {
-                    const uint2 vo = __ldg(visits + sh.ovf[j]);
-                    const uint32_t to = (vo.x >> 24) & 15u;
-                    const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
-                    scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
-                }
+                if (threadIdx.x == 0) { sh.nOvf = 0; sh.nLong = 0; }
                 __syncthreads();
                 if (ovfPending) {   // buckets that found the list full
                     const uint32_t slot = atomicAdd(&sh.nOvf, 1u);
@@ -1431,29 +1481,10 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
     if constexpr (!GATES) { if (sub0 == 0 && v0 + vslot < v1) visited = (v1 - v0 - vslot + V - 1) / V; }
     __syncthreads();
     if (sh.nOvf) {   // CTA-uniform: the buckets noted during the scan
-        const uint32_t nOvf = min(sh.nOvf, kTripleOvfCap);
-        // short remainders: sixteen buckets at a time, eight lanes each; long ones (repeat families) are noted once more
-        for (uint32_t j0 = 0; j0 < nOvf; j0 += kTripleThreads / 8) {
-            const uint32_t j = j0 + (threadIdx.x >> 3), gl = threadIdx.x & 7u;
-            uint2 vo = make_uint2(0, 0);
-            uint32_t start = 0, end = 0;
-            if (j < nOvf) {
-                vo = __ldg(visits + sh.ovf[j]);
-                const uint32_t to = (vo.x >> 24) & 15u;
-                const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
-                start = __ldg(o) + SUBS * kSubEntries; end = __ldg(o + 1);
-                uint32_t isLong = 0;
-                if (gl == 0 && end - start > kTripleLongBucket) {
-                    const uint32_t slot = atomicAdd(&sh.nLong, 1u);
-                    if (slot < kTripleLongCap) { sh.longList[slot] = sh.ovf[j]; isLong = 1; }
-                }
-                isLong = __shfl_sync(0xffu << (threadIdx.x & 24u), isLong, 0, 8);
-                if (isLong) end = start;
-            }
-            scan_range(vo, start, end, gl, 8);
-        }
+        process_noted(min(sh.nOvf, kTripleOvfCap));
         if constexpr (!FLUSH) {
             if (sh.nOvf > kTripleOvfCap && a.ovfBits) {   // CTA-uniform: the visits noted in the bitmap, a word per group of eight lanes
+                // (two lanes per bucket, dealt out evenly through a prefix sum over the words, was measured: 12.6 against 9.8 ms)
                 const uint32_t *bits = a.ovfBits + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * a.ovfWords;
                 const uint32_t gl = threadIdx.x & 7u, words = (v1 - v0 + 31u) >> 5;
                 for (uint32_t w = threadIdx.x >> 3; w < words; w += kTripleThreads / 8) {
@@ -1478,14 +1509,7 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
                 }
             }
         }
-        __syncthreads();
-        const uint32_t nLong = min(sh.nLong, kTripleLongCap);
-        for (uint32_t j = 0; j < nLong; j++) {   // one bucket at a time, all threads
-            const uint2 vo = __ldg(visits + sh.longList[j]);
-            const uint32_t to = (vo.x >> 24) & 15u;
-            const uint32_t *o = a.tv.offs + (uint64_t)to * (kTripleBuckets + 1) + (sh.key[to] ^ (vo.x & 0xFFFFFFu));
-            scan_range(vo, __ldg(o) + SUBS * kSubEntries, __ldg(o + 1), threadIdx.x, kTripleThreads);
-        }
+        process_long();
     }
     triple_epilogue<FUSED, FLUSH>(a, sm, sh.guide, a.guides[sh.guide], entries, visited);   // (the guide is read again: two registers the loop needs)
 }

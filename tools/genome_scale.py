@@ -49,11 +49,12 @@ def write_genome(path: str, bp: int, seed: int, line: int = 60) -> float:
 def score_stats(dev, guides, label):
     hg, hm, hc = cb.HostBuffer(guides.size, np.uint64), cb.HostBuffer(guides.size, np.float64), cb.HostBuffer(guides.size, np.float64)
     hg.array[:] = guides
-    best = None
+    best, reps = None, []
     for _ in range(4):
         dev.score_into(hg.array, 4, 0.0, "and", hm.array, hc.array)
         st = dev.stats
-        if best is None or st["total_ms"] < best["total_ms"]:
+        reps.append({"scan_ms": round(st["scan_ms"], 3), "total_ms": round(st["total_ms"], 3), "launches": st["launches"], "sorted_hits": st["sorted_hits"], "heavy_hits": st["heavy_hits"]})
+        if best is None or st["scan_ms"] < best["scan_ms"]:
             best = st
     n = guides.size
     info = dev.info
@@ -61,7 +62,7 @@ def score_stats(dev, guides, label):
            "distinct_fraction": info["offtargetsCount"] / max(info["seqCount"], 1), "index_hbm_gb": round(info["hbm_bytes"] / 1e9, 2),
            "guides": n, "guides_per_s": n / (best["total_ms"] / 1e3), "scan_ms": best["scan_ms"], "hits_per_guide": best["hits"] / n,
            "bucket_visits_per_guide": best["bucket_visits"] / n, "entries_per_visited_bucket": best["streamed"] / max(best["bucket_visits"], 1),
-           "candidates_per_guide": best["candidates"] / n, "checksum": float(hm.array.sum() + hc.array.sum())}
+           "candidates_per_guide": best["candidates"] / n, "reps": reps, "checksum": float(hm.array.sum() + hc.array.sum())}
     ll = dev.list_lengths.astype(np.float64)
     ll = ll[ll > 0]
     out["list_length_max_over_mean"] = float(ll.max() / ll.mean())
@@ -76,6 +77,7 @@ def main():
     ap.add_argument("--guides", type=int, default=100_000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--scratch", default="/dev/shm")
+    ap.add_argument("--skip-iid", action="store_true")
     a = ap.parse_args()
     path = os.path.join(a.scratch, f"genome_{os.getpid()}.fa")
     out = {"genome_bp": a.bp, "records": 2, "line_length": 60}
@@ -104,6 +106,9 @@ def main():
     finally:
         if os.path.exists(path):
             os.unlink(path)
+    if a.skip_iid:
+        print(json.dumps(out))
+        return
     t0 = time.perf_counter()
     dev = cb.Device.synthetic(0, "auto", seed=1, uniform_sites=bench.HUMAN_SITES)
     out["synthetic_build_s"] = round(time.perf_counter() - t0, 3)
