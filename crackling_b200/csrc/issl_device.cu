@@ -53,6 +53,7 @@ struct issl_device {
     DBuf tripleRes, tripleIds, tripleOffs, tripleBlk, visits, segOff, segCnt, segKeys, segSites, totMit2, totCfd2, done2;
     uint64_t segCap = 0;
     DBuf redo;                       // guides the warp-per-guide kernel left to the CTA-per-guide kernel
+    bool listsResident = false;      // the slice lists (ids / res32 / sig64) exist: TRIPLE builds them on demand (ensure_lists)
     DBuf ovfBits;                    // non-flush scan: one bit per (CTA, visit) whose bucket overflows its block beyond the shared-memory list
     int tripleSmall = 1;             // ISSL_TRIPLE_SMALL=0: never use the warp-per-guide kernel
     DBuf heavyDesc, heavyFlat;       // k_heavy_finish: one descriptor per heavy guide; the second half of its sort's ping-pong
@@ -135,6 +136,18 @@ static int choose_layout(const issl_info &f, int requested, int *out)
 }
 
 // common tail of both constructors: header-derived fields, list geometry, storage
+static int alloc_lists(issl_device *d);
+
+// TRIPLE scores from its sub-bucket copies; its slice lists (ids + residuals, 23 GB at human scale) are only needed for
+// maxDist above ISSL_TRIPLE_MAXDIST, for issl_device_write_issl and when the copies do not fit: they are built from sig[] the
+// first time something asks for them (ensure_lists; ISSL_LISTS_EAGER=1: at load, as in round 1)
+static bool lists_are_lazy(int layout)
+{
+    if (layout != ISSL_LAYOUT_TRIPLE) return false;
+    const char *e = getenv("ISSL_LISTS_EAGER");
+    return !(e && atoi(e) != 0);
+}
+
 static int init_geometry(issl_device *d, const issl_info &f, int layout, const uint64_t *listLen /* host, nLists */)
 {
     d->info = f;
@@ -160,13 +173,9 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     const uint64_t N = f.offtargetsCount;
     CKR(d->sig.exact(N * 8));
     CKR(d->occ.exact(N * 4));
-    CKR(d->ids.exact(P * 4));
-    CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
-    // TRIPLE keeps slice lists too (maxDist beyond what the sub-bucket scan serves, .issl export): RES32 for sliceWidth 8,
+    // TRIPLE's slice lists (maxDist beyond what the sub-bucket scan serves, .issl export): RES32 for sliceWidth 8 and 10,
     // ids only (GATHER) for sliceWidth 4
     const bool res32 = layout == ISSL_LAYOUT_RES32 || (layout == ISSL_LAYOUT_TRIPLE && (f.sliceWidth == 8 || f.sliceWidth == 10));
-    if (res32) { CKR(d->res32.exact(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
-    if (layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.exact(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
     CKR(d->listStart.exact(d->nLists * 8));
     CKR(d->listLen.exact(d->nLists * 8));
     CKR(d->filePrefix.exact((d->nLists + 1) * 8));
@@ -177,9 +186,7 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     IndexView &v = d->iv;
     v.sig = d->sig.as<uint64_t>();
     v.occ = d->occ.as<uint32_t>();
-    v.ids = d->ids.as<uint32_t>();
-    v.res32 = d->res32.as<uint32_t>();
-    v.sig64 = d->sig64.as<uint64_t>();
+    v.ids = nullptr; v.res32 = nullptr; v.sig64 = nullptr;   // alloc_lists
     v.listStart = d->listStart.as<uint64_t>();
     v.listLen = d->listLen.as<uint64_t>();
     v.N = N; v.P = P;
@@ -189,9 +196,71 @@ static int init_geometry(issl_device *d, const issl_info &f, int layout, const u
     v.knownBits = std::min<uint32_t>((uint32_t)f.sliceWidth, 8);
     v.layout = res32 ? (int)ISSL_LAYOUT_RES32 : layout == ISSL_LAYOUT_TRIPLE ? (int)ISSL_LAYOUT_GATHER : layout;
 
-    d->hbmBytes = N * 12 + P * 4 + (res32 ? P * 4 : 0) + (layout == ISSL_LAYOUT_SIG64 ? P * 8 : 0) +
-                  d->nLists * 24;
+    d->hbmBytes = N * 12 + d->nLists * 24;
+    d->listsResident = false;
+    if (!lists_are_lazy(layout)) CKR(alloc_lists(d));
     return ISSL_OK;
+}
+
+// storage of the slice lists in position space; whoever calls this fills them (k_relayout / fill_lists)
+static int alloc_lists(issl_device *d)
+{
+    IndexView &v = d->iv;
+    const uint64_t P = v.P;
+    CKR(d->ids.exact(P * 4));
+    CK(cudaMemsetAsync(d->ids.p, 0xFF, P * 4, d->stream));
+    if (v.layout == ISSL_LAYOUT_RES32) { CKR(d->res32.exact(P * 4)); CK(cudaMemsetAsync(d->res32.p, 0, P * 4, d->stream)); }
+    if (v.layout == ISSL_LAYOUT_SIG64) { CKR(d->sig64.exact(P * 8)); CK(cudaMemsetAsync(d->sig64.p, 0, P * 8, d->stream)); }
+    v.ids = d->ids.as<uint32_t>();
+    v.res32 = d->res32.as<uint32_t>();
+    v.sig64 = d->sig64.as<uint64_t>();
+    d->hbmBytes += P * 4 + (v.layout == ISSL_LAYOUT_RES32 ? P * 4 : 0) + (v.layout == ISSL_LAYOUT_SIG64 ? P * 8 : 0);
+    d->listsResident = true;
+    return ISSL_OK;
+}
+
+// the slice lists from sig[]: per slice a stable 8-bit radix sort of (value, id) and placement -- "all sites whose slice i has
+// value v, in id order" (ref isslCreateIndex.cpp:216-234, including the 8-bit truncation), which is exactly what a file that
+// passed k_relayout's validation holds
+static int fill_lists(issl_device *d)
+{
+    cudaStream_t st = d->stream;
+    const uint64_t N = d->info.offtargetsCount, S = d->info.sliceCount, sliceLimit = 1ull << d->info.sliceWidth;
+    const uint32_t w = (uint32_t)d->info.sliceWidth, smask = (uint32_t)(sliceLimit - 1);
+    DBuf values, valuesSorted, idsTmp, idsSorted, hist, valueStart, tmp;
+    CKR(values.ensure(N)); CKR(valuesSorted.ensure(N)); CKR(idsTmp.ensure(N * 4)); CKR(idsSorted.ensure(N * 4));
+    CKR(hist.ensure(256 * 8)); CKR(valueStart.ensure(256 * 8));
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, values.as<uint8_t>(), valuesSorted.as<uint8_t>(), idsTmp.as<uint32_t>(),
+                                       idsSorted.as<uint32_t>(), N, 0, 8, st));
+    CKR(tmp.ensure(tb));
+    for (uint64_t s = 0; s < S; s++) {
+        CK(cudaMemsetAsync(hist.p, 0, 256 * 8, st));
+        k_slice_values<<<148 * 8, 256, 0, st>>>(d->sig.as<uint64_t>(), N, w, smask, (uint32_t)s, values.as<uint8_t>(),
+                                               idsTmp.as<uint32_t>(), hist.as<unsigned long long>());
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, values.as<uint8_t>(), valuesSorted.as<uint8_t>(), idsTmp.as<uint32_t>(),
+                                           idsSorted.as<uint32_t>(), N, 0, 8, st));
+        uint64_t vs[256], acc = 0;
+        for (uint64_t v = 0; v < 256; v++) { vs[v] = acc; acc += v < sliceLimit ? d->hListLen[s * sliceLimit + v] : 0; }
+        CK(cudaMemcpyAsync(valueStart.p, vs, sizeof vs, cudaMemcpyHostToDevice, st));
+        k_place_slice<<<blocks_for(N, 256), 256, 0, st>>>(d->iv, valuesSorted.as<uint8_t>(), idsSorted.as<uint32_t>(), N,
+                                                         (uint32_t)s, valueStart.as<uint64_t>());
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));   // vs[] is a stack buffer
+    }
+    return ISSL_OK;
+}
+
+static int ensure_lists(issl_device *d)
+{
+    if (d->listsResident) return ISSL_OK;
+    CKR(alloc_lists(d));
+    const int rc = fill_lists(d);
+    if (rc != ISSL_OK) {
+        for (DBuf *b : {&d->ids, &d->res32, &d->sig64}) b->release();
+        d->iv.ids = nullptr; d->iv.res32 = nullptr; d->iv.sig64 = nullptr; d->listsResident = false;
+    }
+    return rc;
 }
 
 static int upload_mit_table(issl_device *d)
@@ -345,6 +414,7 @@ static int triple_fall_back(issl_device *d, int rc)
     for (DBuf *b : {&d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk}) b->release();
     d->tv = TripleView{};
     d->layout = d->iv.layout;   // RES32 (sliceWidth 8) or the ids-only lists (sliceWidth 4)
+    CKR(ensure_lists(d));
     if (getenv("ISSL_DEBUG")) fprintf(stderr, "[issl] the sub-bucket copies do not fit this GPU's free memory: scanning the slice lists instead\n");
     return ISSL_OK;
 }
@@ -619,25 +689,9 @@ static int collapse_and_build(issl_device *d, int layout, const uint64_t *dKeys,
     CK(cudaStreamSynchronize(st));
     sigTmp.release(); occTmp.release();
 
-    // pass B: per slice, stable 8-bit radix sort of (value, id) and placement (ref :216-234)
-    size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, values.as<uint8_t>(), valuesSorted.as<uint8_t>(), idsTmp.as<uint32_t>(),
-                                       idsSorted.as<uint32_t>(), N, 0, 8, st));
-    DBuf tmp; CKR(tmp.ensure(tb));
-    for (uint64_t s = 0; s < S; s++) {
-        k_slice_values<<<148 * 8, 256, 0, st>>>(d->sig.as<uint64_t>(), N, w, smask, (uint32_t)s, values.as<uint8_t>(),
-                                               idsTmp.as<uint32_t>(), hist.as<unsigned long long>() + s * 256);
-        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, values.as<uint8_t>(), valuesSorted.as<uint8_t>(), idsTmp.as<uint32_t>(),
-                                           idsSorted.as<uint32_t>(), N, 0, 8, st));
-        uint64_t vs[256], acc = 0;
-        for (int v = 0; v < 256; v++) { vs[v] = acc; acc += hHist[s * 256 + v]; }
-        CK(cudaMemcpyAsync(valueStart.p, vs, sizeof vs, cudaMemcpyHostToDevice, st));
-        k_place_slice<<<blocks_for(N, 256), 256, 0, st>>>(d->iv, valuesSorted.as<uint8_t>(), idsSorted.as<uint32_t>(), N,
-                                                         (uint32_t)s, valueStart.as<uint64_t>());
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));   // vs[] is a stack buffer
-    }
-    for (DBuf *b : {&values, &valuesSorted, &idsTmp, &idsSorted, &hist, &valueStart, &tmp}) b->release();
+    for (DBuf *b : {&values, &valuesSorted, &idsTmp, &idsSorted, &hist, &valueStart}) b->release();
+    // pass B: per slice, stable 8-bit radix sort of (value, id) and placement (ref :216-234) -- unless the lists can wait
+    if (d->listsResident) CKR(fill_lists(d));
     return build_triple_or_fall_back(d);
 }
 
@@ -858,7 +912,7 @@ extern "C" int issl_device_clone(const issl_device *src_, int cuda_device, issl_
     d->info = src->info; d->layout = src->layout; d->nLists = src->nLists; d->hbmBytes = src->hbmBytes; d->pbits = src->pbits;
     d->mitCount = src->mitCount; d->hMitMasks = src->hMitMasks; d->hMitScores = src->hMitScores;
     d->hListLen = src->hListLen; d->hListStart = src->hListStart; d->hFilePrefix = src->hFilePrefix;
-    d->layoutAuto = src->layoutAuto; d->tripleMaxDist = src->tripleMaxDist;
+    d->layoutAuto = src->layoutAuto; d->tripleMaxDist = src->tripleMaxDist; d->listsResident = src->listsResident;
     const std::vector<DBuf *> from = index_buffers(src), to = index_buffers(d);
     for (size_t k = 0; k < from.size(); k++) {
         if (!from[k]->p) continue;
@@ -917,6 +971,7 @@ extern "C" int issl_device_write_issl(issl_device *d, const char *path)
 {
     if (!d || !path) return issl_set_error(ISSL_ERR_ARG, "issl_device_write_issl: null argument");
     CK(cudaSetDevice(d->dev));
+    CKR(ensure_lists(d));
     FILE *fp = fopen(path, "wb");
     if (!fp) return issl_set_error(ISSL_ERR_IO, "cannot create %s", path);
     auto put = [&](const void *p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, fp) == bytes; };
@@ -1340,6 +1395,7 @@ static int score_batch(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
     const bool nibble = d->layout == ISSL_LAYOUT_TRIPLE && d->info.sliceWidth == 4;
     const bool gates = d->layout == ISSL_LAYOUT_TRIPLE && d->info.sliceWidth == 10;
     const bool useTriple = d->layout == ISSL_LAYOUT_TRIPLE && maxDist >= 0 && maxDist <= d->tripleMaxDist;
+    if (!useTriple) CKR(ensure_lists(d));   // (TRIPLE builds its slice lists the first time a call needs them)
     // Waves: one slice at a time pays when many guides leave through the early exit (repeat families: their later slices
     // are never scanned); when few do, every further launch only costs.  So after each single-slice wave the guides that
     // left are counted, and once a wave sends fewer than a tenth of the batch through the exit all remaining slices go in

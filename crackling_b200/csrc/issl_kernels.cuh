@@ -770,12 +770,14 @@ __global__ void __launch_bounds__(256) k_relayout(const RelayoutArgs a)
         }
         uint32_t *occOut = const_cast<uint32_t *>(a.iv.occ);
         if (a.slice == 0) occOut[id] = occ; else bad |= (occOut[id] != occ);
-        const uint64_t p = a.iv.listStart[list] + j;
-        const_cast<uint32_t *>(a.iv.ids)[p] = id;
-        if (a.iv.layout == kRes32)
-            const_cast<uint32_t *>(a.iv.res32)[p] = (uint32_t)remove_bits(s, off, a.iv.knownBits);
-        else if (a.iv.layout == kSig64)
-            const_cast<uint64_t *>(a.iv.sig64)[p] = s;
+        if (a.iv.ids) {   // (nullptr: validation only -- TRIPLE builds its slice lists when something asks for them)
+            const uint64_t p = a.iv.listStart[list] + j;
+            const_cast<uint32_t *>(a.iv.ids)[p] = id;
+            if (a.iv.layout == kRes32)
+                const_cast<uint32_t *>(a.iv.res32)[p] = (uint32_t)remove_bits(s, off, a.iv.knownBits);
+            else if (a.iv.layout == kSig64)
+                const_cast<uint64_t *>(a.iv.sig64)[p] = s;
+        }
     }
     if (bad) atomicAdd(a.errors, 1ull);
 }

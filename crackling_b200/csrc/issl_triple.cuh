@@ -227,6 +227,12 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, const
 #ifndef ISSL_TRIPLE_MIN_CTAS
 #define ISSL_TRIPLE_MIN_CTAS 10   // resident CTAs per SM the scan kernel is compiled for (48 registers); 8, 9, 12 measured slower
 #endif
+#ifndef ISSL_SUB_NOEARLY
+#define ISSL_SUB_NOEARLY 1        // 1: an empty sub-block is compared like any other (no branch; its validity mask is empty)
+#endif
+#ifndef ISSL_TRIPLE_PIPE
+#define ISSL_TRIPLE_PIPE 0        // 1: the next round's visit-table entry is loaded one round ahead
+#endif
 #ifndef ISSL_TRIPLE_PREFETCH
 #define ISSL_TRIPLE_PREFETCH 0
 #endif
@@ -1210,7 +1216,9 @@ __device__ __forceinline__ uint32_t triple_sub_block(const TripleArgs &a, const 
                                                      const uint32_t gated = 31u)
 {
     cnt = (q0.x & 1u) | ((q0.y & 1u) << 1) | ((q0.z & 1u) << 2) | ((q0.w & 1u) << 3) | ((q1.x & 1u) << 4);
+#if !ISSL_SUB_NOEARLY
     if (cnt == 0) return 0;
+#endif
     const uint4 m0 = mask[0], m1 = mask[1], m2 = mask[2], m3 = mask[3];
     const uint32_t x0 = (q0.x ^ m0.x) | (q0.y ^ m0.y), x1 = (q0.z ^ m0.z) | (q0.w ^ m0.w);
     const uint32_t x2 = (q1.x ^ m1.x) | (q1.y ^ m1.y), x3 = (q1.z ^ m1.z) | (q1.w ^ m1.w);
@@ -1393,6 +1401,12 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
         }
     };
 
+#if ISSL_TRIPLE_PIPE
+    // the visit of the NEXT round is requested while this round's blocks are on their way: the visit-table entry (an L1 hit)
+    // heads the chain entry -> bucket key -> address -> block loads, and a warp that waits for it has no block in flight
+    uint2 vNext = make_uint2(0, 0);
+    if (v0 + vslot < v1) vNext = __ldg(visits + v0 + vslot);
+#endif
     for (uint32_t e0 = v0; e0 < v1; e0 += V) {   // the same number of rounds for every thread of the CTA
         const uint32_t e = e0 + vslot;
         uint2 v = make_uint2(0, 0);
@@ -1404,7 +1418,12 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
         for (int s = 0; s < LSUBS; s++) left[s] = 0;
         bool live = e < v1;
         if (live) {
+#if ISSL_TRIPLE_PIPE
+            v = vNext;
+            if (e + V < v1) vNext = __ldg(visits + e + V);
+#else
             v = __ldg(visits + e);
+#endif
             if constexpr (GATES) {
                 // sliceWidth 10: of the four ways the residual's two slices can match exactly, only those that leave the hit
                 // with an exact unit behind an open gate; a visit none of whose entries this guide may keep is not read
