@@ -1041,9 +1041,12 @@ struct EventTimer {
 
 }  // namespace
 
-static int ensure_hit_buffers(issl_device *d, uint32_t n)
+// fusedTail: guides are finished where their hits are (the scan kernel's fused tail / k_heavy_finish): only what spills from a
+// CTA's record list reaches this buffer, so it starts small -- 600 MB of cudaMalloc were most of a first call's time on a
+// fresh handle, and in the executable every call is the first; an overflow re-launches the scan with a larger one, as ever
+static int ensure_hit_buffers(issl_device *d, uint32_t n, bool fusedTail = false)
 {
-    uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, 384ull * n), 1ull << 28);
+    uint64_t wantCap = std::min<uint64_t>(std::max<uint64_t>(1ull << 22, fusedTail ? 0ull : 384ull * n), 1ull << 28);
     if (d->firstHitCap) wantCap = d->firstHitCap;   // ISSL_HIT_CAP: start small, so that tests reach the re-launch after an overflow
     if (d->hitCap < wantCap && d->hitCap == d->hitCapAuto) {   // first sizing for this batch size (uniform genomes: ~275 survivors per guide)
         d->hitCap = d->hitCapAuto = wantCap;
@@ -1162,7 +1165,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
         const bool small = inScan && !flush && d->tripleSmall && nv <= kSmallMaxVisits && d->tv.pitch && d->tv.siteOrdered && !d->tv.perm10;
         if (small) CKR(d->redo.ensure(n * 4ull));
         for (;;) {
-            CKR(ensure_hit_buffers(d, n));
+            CKR(ensure_hit_buffers(d, n, inScan));
             if (heavy) { CKR(d->heavyKeys.ensure(d->heavyCap * 8)); CKR(d->heavyDesc.ensure((size_t)n * sizeof(HeavyDesc))); }
             if (fuse && d->segCap < d->hitCap) {
                 d->segCap = d->hitCap;
@@ -1235,7 +1238,7 @@ static int triple_wave(issl_device *d, cudaStream_t st, const uint64_t *dGuides,
             CKR(d->heavyFlat.ensure(d->hCounters[9] * 8));
             HeavyArgs ha;
             ha.desc = d->heavyDesc.as<HeavyDesc>(); ha.keys = d->heavyKeys.as<uint64_t>(); ha.flat = d->heavyFlat.as<uint64_t>();
-            ha.flatCount = dc + 12; ha.guides = dGuides; ha.sp = sp;
+            ha.flatCount = dc + 12; ha.guides = dGuides; ha.sp = sp; ha.fineGroups = d->tv.nibbleOrder ? 0u : 1u;
             ha.totMitOut = d->totMit2.as<double>(); ha.totCfdOut = d->totCfd2.as<double>(); ha.doneOut = d->done2.as<uint8_t>();
             cudaEvent_t h0, h1;
             CKR(timer.get(&h0)); CKR(timer.get(&h1));

@@ -690,6 +690,7 @@ struct HeavyArgs {
     ScoreParams sp;                   // sp.totMit / totCfd: state before this wave
     double *totMitOut, *totCfdOut;    // state after it
     uint8_t *doneOut;
+    uint32_t fineGroups;              // 161 counting-sort groups per ordering slice (at most six slices) instead of 41
 };
 struct HeavySmem {
     uint32_t radix[4][256];
@@ -786,10 +787,10 @@ __device__ __forceinline__ uint32_t occ_by_text(const ScoreParams &sp, uint64_t 
 // this at the end of the scan CTA itself was measured: 40.3 ms per 100 000 guides at maxDist 5 instead of 30.6 ms for the
 // scan alone -- a chain of dependent L2 round trips during which the CTA requests no blocks; on its own, with a dozen
 // guides per SM in flight, the same work hides behind itself.)
-//   Two sorts.  Keys spread over many (slice, leading text bits) groups -- hits on a genome without dense repeat families --
-// take a counting sort over 16 x 64 groups followed by a rank inside the group (a handful of comparisons per key): three
-// sweeps over the keys.  When a group is large (a family of near-copies shares its leading bases) the rank would be
-// quadratic, and the keys take the radix sort: six stable passes, data-independent.  Either way every sweep requests four
+//   Two sorts.  Keys spread over many (slice, first mismatch with the guide) groups take a counting sort over up to 1 024
+// groups followed by a rank inside the group (a handful of comparisons per key): three sweeps over the keys.  When a group is
+// large (exact copies aside, a family whose members all leave the guide at the same base) the rank would be quadratic, and
+// the keys take the radix sort: six stable passes, data-independent.  Either way every sweep requests four
 // keys per thread before it uses the first: the keys sit in L2, and a sweep is bound by that round trip, not by arithmetic.
 constexpr uint32_t kHeavyRankMax = 48;   // largest group the counting sort finishes by comparisons
 
@@ -807,7 +808,20 @@ __global__ void __launch_bounds__(kTripleThreads, 12) k_heavy_finish(const Heavy
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t *const cnt = &sh.radix[0][0];
     auto load = [&](uint32_t c, uint32_t L) { return c ? flat[L] : chunks[heavy_slot(sh.chunkBase, L)]; };
-    auto group_of = [](uint64_t key) { return (uint32_t)(key >> 60) << 6 | ((uint32_t)(key >> 54) & 63u); };
+    // groups of the counting sort: (slice, where and how the site first leaves the guide) -- monotone in (slice, site text),
+    // like first_mismatch_group but split once more by the site's base at that position: 161 groups per slice, the largest
+    // holding ~7 % of a slice's hits.  (Leading text bits do not spread a guide's hits: they are its near neighbours.)
+    // sliceWidth 4 has ten ordering slices: 41 groups per slice there.
+    const uint32_t fine = a.fineGroups;
+    auto group_of = [&](uint64_t key) -> uint32_t {
+        const uint64_t site = text_key_site((key >> 20) & 0xFFFFFFFFFFull), x = site ^ g;
+        const uint32_t slice = (uint32_t)(key >> 60);
+        if (!fine) return slice * kKeyBuckets + first_mismatch_group(site, g);
+        if (x == 0) return slice * 161u + 80u;
+        const uint32_t f = (uint32_t)(__ffsll((long long)x) - 1) >> 1;
+        const uint32_t sb = (uint32_t)(site >> (2 * f)) & 3u, gb = (uint32_t)(g >> (2 * f)) & 3u;
+        return slice * 161u + (sb < gb ? f * 4u + sb : 81u + (19u - f) * 4u + sb);
+    };
     uint32_t cur = 0;                                                    // 0: the keys are in the chunks, 1: in `flat`
 
     // ---- counting sort over (slice, six leading text bits), if no group is large
