@@ -54,6 +54,7 @@ struct issl_device {
     uint64_t segCap = 0;
     DBuf redo;                       // guides the warp-per-guide kernel left to the CTA-per-guide kernel
     bool listsResident = false;      // the slice lists (ids / res32 / sig64) exist: TRIPLE builds them on demand (ensure_lists)
+    DBuf tripleBits;                 // TripleView::nonEmpty (small indexes)
     DBuf ovfBits;                    // non-flush scan: one bit per (CTA, visit) whose bucket overflows its block beyond the shared-memory list
     int tripleSmall = 1;             // ISSL_TRIPLE_SMALL=0: never use the warp-per-guide kernel
     DBuf heavyDesc, heavyFlat;       // k_heavy_finish: one descriptor per heavy guide; the second half of its sort's ping-pong
@@ -309,7 +310,7 @@ struct TripleBuild {
     DBuf keysIn, keysOut, idsIn, tmp;
     uint32_t pitch = 0, perm10 = 0;
     uint64_t stride = 0, needBlk = 0;
-    bool occFlag = false;
+    bool occFlag = false, bitmap = false;
 };
 
 // allocations and launches on `st`; nothing is waited for.  ISSL_ERR_NOMEM when the copies do not fit.
@@ -346,6 +347,9 @@ static int build_triple_enqueue(issl_device *d, cudaStream_t st, TripleBuild &b)
     if (pitch) {
         CKR(d->tripleBlk.exact(needBlk));   // every sub-block is written by k_triple_blocks
     }
+    // no blocked copy and mostly empty buckets (a bacterial genome): a bitmap of the buckets that hold anything
+    b.bitmap = pitch == 0 && (double)N / kTripleBuckets < 0.5 && !getenv("ISSL_TRIPLE_NO_BITMAP");
+    if (b.bitmap) CKR(d->tripleBits.exact((size_t)kTripleCount * (kTripleBuckets / 32) * 4));
     const uint32_t perm10 = d->info.sliceWidth == 10 ? 1u : 0u;   // sliceWidth 10: copies of the permuted signatures (issl_triple.cuh)
     DBuf &keysIn = b.keysIn, &keysOut = b.keysOut, &idsIn = b.idsIn, &tmp = b.tmp;
     CKR(keysIn.ensure(N * 4)); CKR(keysOut.ensure(N * 4)); CKR(idsIn.ensure(N * 4));
@@ -363,6 +367,9 @@ static int build_triple_enqueue(issl_device *d, cudaStream_t st, TripleBuild &b)
         if (occFlag) k_triple_flag_ids<<<blocks_for(N, 256), 256, 0, st>>>(d->occ.as<uint32_t>(), N, ids);
         k_triple_offsets<<<blocks_for(kTripleBuckets + 1ull, 256), 256, 0, st>>>(keysOut.as<uint32_t>(), N,
                                                                                 d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull));
+        if (b.bitmap)
+            k_triple_nonempty<<<kTripleBuckets / 256, 256, 0, st>>>(d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull),
+                                                                   d->tripleBits.as<uint32_t>() + (size_t)t * (kTripleBuckets / 32));
         if (pitch)
             k_triple_blocks<<<blocks_for((uint64_t)kTripleBuckets * (pitch / 32), 256), 256, 0, st>>>(
                 d->tripleRes.as<uint16_t>() + t * stride, d->tripleOffs.as<uint32_t>() + t * (kTripleBuckets + 1ull), keysOut.as<uint32_t>(), pitch / 32,
@@ -393,7 +400,8 @@ static int build_triple_finish(issl_device *d, cudaStream_t st, TripleBuild &b)
     d->tv.perm10 = b.perm10;
     d->tv.blk = b.pitch ? d->tripleBlk.as<uint4>() : nullptr;
     d->tv.pitch = b.pitch;
-    d->hbmBytes += kTripleCount * (b.stride * 6 + (kTripleBuckets + 1ull) * 4) + b.needBlk;
+    d->tv.nonEmpty = b.bitmap ? d->tripleBits.as<uint32_t>() : nullptr;
+    d->hbmBytes += kTripleCount * (b.stride * 6 + (kTripleBuckets + 1ull) * 4) + b.needBlk + (b.bitmap ? (uint64_t)kTripleCount * (kTripleBuckets / 8) : 0);
     return ISSL_OK;
 }
 
@@ -411,7 +419,7 @@ static int triple_fall_back(issl_device *d, int rc)
 {
     if (rc != ISSL_ERR_NOMEM || !d->layoutAuto || d->layout != ISSL_LAYOUT_TRIPLE) return rc;
     cudaGetLastError();
-    for (DBuf *b : {&d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk}) b->release();
+    for (DBuf *b : {&d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk, &d->tripleBits}) b->release();
     d->tv = TripleView{};
     d->layout = d->iv.layout;   // RES32 (sliceWidth 8) or the ids-only lists (sliceWidth 4)
     CKR(ensure_lists(d));
@@ -468,7 +476,7 @@ extern "C" void issl_device_destroy(issl_device *d)
                     &d->mitMasks, &d->mitScores, &d->guides, &d->totMit, &d->totCfd, &d->done, &d->pairKeys, &d->pairVals, &d->pairKeysSorted, &d->pairValsSorted, &d->pairCounts,
                     &d->pairOffsets, &d->items, &d->keysA, &d->keysB, &d->sortTemp, &d->scanTemp, &d->contribMit,
                     &d->contribCfd, &d->counters, &d->outMit, &d->outCfd, &d->hitId, &d->hitDist, &d->hitOcc,
-                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->heavyDesc, &d->heavyFlat, &d->redo, &d->ovfBits, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
+                    &d->scoredEnd, &d->segBegin, &d->heavyKeys, &d->heavyDesc, &d->heavyFlat, &d->redo, &d->ovfBits, &d->tripleBits, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->visits, &d->segOff, &d->segCnt, &d->tripleBlk, &d->segKeys, &d->segSites, &d->totMit2, &d->totCfd2, &d->done2,
                     &d->mitDense})
         b->release();
     for (cudaEvent_t ev : d->evPool) cudaEventDestroy(ev);
@@ -884,7 +892,7 @@ namespace {
 std::vector<DBuf *> index_buffers(issl_device *d)
 {
     return {&d->sig, &d->occ, &d->ids, &d->res32, &d->sig64, &d->listStart, &d->listLen, &d->filePrefix, &d->mitMasks,
-            &d->mitScores, &d->mitDense, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk};
+            &d->mitScores, &d->mitDense, &d->tripleRes, &d->tripleIds, &d->tripleOffs, &d->tripleBlk, &d->tripleBits};
 }
 template <class T> const T *rebase(const T *p, const DBuf &from, const DBuf &to)
 {
@@ -930,6 +938,7 @@ extern "C" int issl_device_clone(const issl_device *src_, int cuda_device, issl_
     d->tv = src->tv;
     d->tv.res = rebase(src->tv.res, src->tripleRes, d->tripleRes); d->tv.ids = rebase(src->tv.ids, src->tripleIds, d->tripleIds);
     d->tv.offs = rebase(src->tv.offs, src->tripleOffs, d->tripleOffs); d->tv.blk = rebase(src->tv.blk, src->tripleBlk, d->tripleBlk);
+    d->tv.nonEmpty = rebase(src->tv.nonEmpty, src->tripleBits, d->tripleBits);
     const cudaError_t e = cudaStreamSynchronize(d->stream);
     if (e != cudaSuccess) return fail(issl_set_error(ISSL_ERR_CUDA, "peer copy %d -> %d: %s", src->dev, cuda_device, cudaGetErrorString(e)));
     *out = d;

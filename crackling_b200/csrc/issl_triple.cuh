@@ -45,6 +45,10 @@ struct TripleView {
     // lookup in front of it, and 31 residuals are tested with ~30 bitwise instructions.
     const uint4 *blk;
     uint32_t pitch;         // 16-bit slots per bucket: 0 (no blocked copy), 32, 64 or 128
+    // small indexes (a bacterial genome: one site per twenty buckets): one bit per bucket, "holds at least one entry" --
+    // 2 MB per triple, resident in L2 -- so that the contiguous scan only follows the offsets of the ~5 % of its visits
+    // that can find anything.  nullptr on indexes with a blocked copy or with mostly occupied buckets.
+    const uint32_t *nonEmpty;   // [10][2^24 / 32]
     // sliceWidth 4 (ten 2-base slices): with maxDist <= 4 every site within maxDist agrees with the guide on a whole
     // byte, so the same buckets are read; only the order differs -- the reference meets a hit first in the lowest
     // 2-base slice that matches exactly, which may lie below the lowest exact byte
@@ -163,6 +167,14 @@ __global__ void k_triple_offsets(const uint32_t *sortedKeys, uint64_t n, uint32_
         if ((sortedKeys[mid] >> 1) < k) lo = mid + 1; else hi = mid;
     }
     offs[k] = (uint32_t)lo;
+}
+
+// one bit per bucket: it holds at least one entry (TripleView::nonEmpty)
+__global__ void k_triple_nonempty(const uint32_t *offs, uint32_t *bits)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;   // < 2^24
+    const uint32_t b = __ballot_sync(0xffffffffu, offs[k + 1] > offs[k]);
+    if ((threadIdx.x & 31u) == 0) bits[k >> 5] = b;
 }
 
 // blocked copy of one triple: one thread transposes one sub-block.  Column 0 of a sub-block (bit 0 of its 16 words) is
@@ -1173,6 +1185,42 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
     uint32_t entries = 0, visited = 0;
     const uint2 *__restrict__ visits = reinterpret_cast<const uint2 *>(a.visits);
 
+    if (a.tv.nonEmpty) {
+        // small index: every lane looks one visit's bucket up in the bitmap; the warp's four octets then follow the offsets
+        // of the buckets that hold something, four at a time
+        const uint32_t lane = threadIdx.x & 31u, oct = lane >> 3;
+        for (uint32_t e0 = v0; e0 < v1; e0 += kTripleThreads) {
+            const uint32_t e = e0 + threadIdx.x;
+            uint2 v = make_uint2(0, 0);
+            bool some = false;
+            if (e < v1) {
+                v = __ldg(visits + e);
+                const uint32_t t = (v.x >> 24) & 15u, key = sh.key[t] ^ (v.x & 0xFFFFFFu);
+                some = (__ldg(a.tv.nonEmpty + ((size_t)t << 19) + (key >> 5)) >> (key & 31u)) & 1u;
+                visited++;
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, some);
+            while (m) {
+                uint32_t mm = m;
+                for (uint32_t k = 0; k < oct; k++) mm &= mm - 1u;          // this octet's bucket: the oct-th one left
+                const bool has = mm != 0;
+                const int src = has ? __ffs(mm) - 1 : 0;
+                const uint2 vo = make_uint2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+                if (has) {
+                    const uint32_t t = (vo.x >> 24) & 15u;
+                    const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + (sh.key[t] ^ (vo.x & 0xFFFFFFu));
+                    const uint32_t start = __ldg(o), end = __ldg(o + 1);
+                    if (start < end) {
+                        triple_bucket(a, sh, guide, vo, start, end, lane8, 8);
+                        if (lane8 == 0) entries += end - start;
+                    }
+                }
+                for (int k = 0; k < 4 && m; k++) m &= m - 1u;
+            }
+        }
+        triple_epilogue<FUSED>(a, sm, guide, g, entries, visited);
+        return;
+    }
     uint32_t e = v0 + octet;
     uint2 v = make_uint2(0, 0);
     uint32_t start = 0, end = 0;
