@@ -526,10 +526,12 @@ def main() -> int:
               "threshold": args.threshold, "slice_width": args.slice_width, "hbm_layout": layout_name,
               "families": args.families, "family_size": args.family_size, "family_size_max": args.family_size_max,
               "low_complexity": args.low_complexity, "family_guides": args.family_guides,
-              "max_group": args.max_group, "index_hbm_gb": round(info["hbm_bytes"] / 1e9, 2),
+              "max_group": args.max_group,
               "parallelism": f"replicated index, guides partitioned x{args.gpus}, no collective while scoring",
               "l2": ("inputs larger than L2 (126 MB): every step reads its sub-buckets (~180 KB per guide, random 128-byte blocks "
                      "out of a 21 GB copy; ~45 MB of slice lists per guide with the list-scan layouts)")}
+    # measured, not configured (the arms build different copies of the same index): beside config, like index_build_s
+    index_hbm_gb = round(info["hbm_bytes"] / 1e9, 2)
     scaling = "strong" if strong else "weak"
 
     # ------------------------------------------------------------------ reference arm
@@ -559,7 +561,7 @@ def main() -> int:
         emit(({"impl": "reference", "metric": "guides scored/sec (MIT+CFD, <=4 mm)", "value": v, "unit": "guides/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
                "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64 popcount + f64 scores",
-               "data": "synthetic", "config": config, "index_build_s": round(t_build, 2),
+               "data": "synthetic", "config": config, "index_build_s": round(t_build, 2), "index_hbm_gb": index_hbm_gb,
                "host": {"cores": cores, "cpu": cpu_model()},
                "cpu_baseline": {"value": v, "unit": "guides/s", "cores": cores, "kind": kind, "sample": note},
                "e2e": {"value": v, "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -687,7 +689,7 @@ def main() -> int:
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
               "scaling": scaling, "vs_baseline": None,
               "dtype": "u16 bit-sliced compare (LOP3), f64 scores" if triple_scan else "u32/u64 xor+popcount, f64 scores", "data": "synthetic",
-              "config": config, "index_build_s": round(t_build, 2), "clocks": clk,
+              "config": config, "index_build_s": round(t_build, 2), "index_hbm_gb": index_hbm_gb, "clocks": clk,
               "e2e": {"value": e2e_value, "unit": "guides/s", "h2d_bytes_per_step": int(total * 8), "d2h_bytes_per_step": int(total * 16),
                       "how": e2e_how},
               "gpu_launches": int(acc["launches"]), "scan_launches": int(acc["scan_launches"]),
