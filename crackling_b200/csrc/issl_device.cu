@@ -325,7 +325,10 @@ static int build_triple_enqueue(issl_device *d, cudaStream_t st, TripleBuild &b)
     uint32_t pitch = 0;
     {
         const double lambda = (double)N / kTripleBuckets, want = lambda + 4.5 * std::sqrt(lambda);
-        if (lambda >= 2.0) pitch = want <= 31 ? 32 : want <= 62 ? 64 : want <= 124 ? 128 : 0;
+        // from one site per five buckets on (3.4 M sites) a visit is one aligned read of the bucket's block; 64-byte blocks up to
+        // ~14 sites per bucket.  Measured per 100 000 guides, 5 / 10 / 20 M sites: 2.20 ms each, against 3.42 / 5.70 / 6.04 ms
+        // through the offsets (profiles/r02_ab_midsize_blocks.jsonl); at 2 M sites the bitmap below is as fast (2.11 vs 2.19)
+        if (lambda >= 0.2) pitch = want <= 31 ? 32 : want <= 62 ? 64 : want <= 124 ? 128 : 0;
         if (const char *e = getenv("ISSL_TRIPLE_BLOCKS")) {
             const long v = atol(e);
             if (v == 0 || v == 32 || v == 64 || v == 128) pitch = (uint32_t)v;
