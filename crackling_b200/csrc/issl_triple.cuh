@@ -232,10 +232,62 @@ __global__ void k_triple_blocks(const uint16_t *res, const uint32_t *offs, const
 // k_score_segments, or as keys  guide << 35 | min(E) << 32 | id  for the general pipeline (radix sort ->
 // k_contrib -> k_accumulate), which sort back into the reference's visiting order.
 // ------------------------------------------------------------------------------------------------
-// how the scan reads a bucket's block: __ldcs (streaming, evict-first; a block is read once per guide) or __ldg
-#ifndef ISSL_BLOCK_LOAD
-#define ISSL_BLOCK_LOAD __ldcs
+// How the scan reads a 64-byte sub-block (ISSL_BLOCK_POLICY):
+//   0  four 16-byte streaming loads (__ldcs: LDG.E.EF.128)
+//   1  four 16-byte loads with L1::no_allocate
+//   3..6  two 32-byte loads (sm_100 has LDG.256: ld.global.v8.b32) -- a lane then asks for each of its two sectors once, where
+//      four 16-byte loads ask for each twice (the second request waits on the first: ncu's 50 % L1 "hit" rate of the scan)
+//      3 plain, 4 L1::no_allocate + L2::evict_first, 5 L1::evict_first, 6 L1::no_allocate
+// ISSL_VISIT_POLICY: 1 = the visit table is read with L1::evict_last
+// Measured per 100 000 guides (profiles/r02_ab_ld256.jsonl): 0: 3.660 ms, 1: 3.955, 3: 3.579, 5: 3.541, 6: 3.473, 4: 3.457 (default)
+#ifndef ISSL_BLOCK_POLICY
+#define ISSL_BLOCK_POLICY 4
 #endif
+#ifndef ISSL_VISIT_POLICY
+#define ISSL_VISIT_POLICY 0
+#endif
+__device__ __forceinline__ uint4 ld_block_na(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+#if ISSL_BLOCK_POLICY == 3
+#define ISSL_LD256 "ld.global.v8.b32"
+#elif ISSL_BLOCK_POLICY == 4
+#define ISSL_LD256 "ld.global.L1::no_allocate.L2::evict_first.v8.b32"
+#elif ISSL_BLOCK_POLICY == 5
+#define ISSL_LD256 "ld.global.L1::evict_first.v8.b32"
+#else
+#define ISSL_LD256 "ld.global.L1::no_allocate.v8.b32"
+#endif
+__device__ __forceinline__ void ld_block_256(const uint4 *p, uint4 &a, uint4 &b)
+{
+    asm volatile(ISSL_LD256 " {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+// the four 16-byte words of the sub-block at p
+__device__ __forceinline__ void load_sub_block(const uint4 *__restrict__ p, uint4 &q0, uint4 &q1, uint4 &q2, uint4 &q3)
+{
+#if ISSL_BLOCK_POLICY >= 3
+    ld_block_256(p, q0, q1);
+    ld_block_256(p + 2, q2, q3);
+#elif ISSL_BLOCK_POLICY == 1
+    q0 = ld_block_na(p); q1 = ld_block_na(p + 1); q2 = ld_block_na(p + 2); q3 = ld_block_na(p + 3);
+#else
+    q0 = __ldcs(p); q1 = __ldcs(p + 1); q2 = __ldcs(p + 2); q3 = __ldcs(p + 3);
+#endif
+}
+__device__ __forceinline__ uint2 ld_visit(const uint2 *p)
+{
+#if ISSL_VISIT_POLICY == 1
+    uint2 r;
+    asm volatile("ld.global.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
 #ifndef ISSL_TRIPLE_MIN_CTAS
 #define ISSL_TRIPLE_MIN_CTAS 10   // resident CTAs per SM the scan kernel is compiled for (48 registers); 8, 9, 12 measured slower
 #endif
@@ -1520,7 +1572,7 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
             v = vNext;
             if (e + V < v1) vNext = __ldg(visits + e + V);
 #else
-            v = __ldg(visits + e);
+            v = ld_visit(visits + e);
 #endif
             if constexpr (GATES) {
                 // sliceWidth 10: of the four ways the residual's two slices can match exactly, only those that leave the hit
@@ -1550,7 +1602,7 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
             // read once: streaming loads, so that the visit table and the offsets keep their place in L1
 #pragma unroll
             for (int s = 0; s < LSUBS; s++) {
-                q[s][0] = ISSL_BLOCK_LOAD(p + 4 * s); q[s][1] = ISSL_BLOCK_LOAD(p + 4 * s + 1); q[s][2] = ISSL_BLOCK_LOAD(p + 4 * s + 2); q[s][3] = ISSL_BLOCK_LOAD(p + 4 * s + 3);
+                load_sub_block(p + 4 * s, q[s][0], q[s][1], q[s][2], q[s][3]);
             }
             if constexpr (GATES) { if (sub0 == 0) visited++; }   // (without gates every visit is read: counted after the loop)
             if ((q[0][1].y & 1u) && sub0 == 0) {   // more entries than the block holds: noted for after the loop
@@ -1699,7 +1751,8 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple_small(const Trip
         const uint2 v = __ldg(visits + e);
         const uint32_t t = (v.x >> 24) & 15u, key = w.key[t] ^ (v.x & 0xFFFFFFu);
         const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub) * 4;
-        const uint4 q0 = ISSL_BLOCK_LOAD(p), q1 = ISSL_BLOCK_LOAD(p + 1), q2 = ISSL_BLOCK_LOAD(p + 2), q3 = ISSL_BLOCK_LOAD(p + 3);
+        uint4 q0, q1, q2, q3;
+        load_sub_block(p, q0, q1, q2, q3);
         if (sub == 0) visited++;
         if ((q1.y & 1u) && sub == 0) {   // more entries than the block holds: this lane reads the rest from the contiguous copy
             const uint32_t *o = a.tv.offs + (uint64_t)t * (kTripleBuckets + 1) + key;

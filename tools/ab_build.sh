@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds a variant of libissl_cuda.so with extra nvcc flags into crackling_b200/lib_ab/<name>/ for A/B timing:
-#   tools/ab_build.sh ldg -DISSL_BLOCK_LOAD=__ldg
-#   ISSL_CUDA_LIB=crackling_b200/lib_ab/ldg/libissl_cuda.so python tools/score_once.py
+#   tools/ab_build.sh l256 -DISSL_BLOCK_POLICY=3
+#   ISSL_CUDA_LIB=crackling_b200/lib_ab/l256/libissl_cuda.so python tools/score_once.py
 # (the directory is git-ignored; the variants travel to the GPU box with the snapshot)
 set -e
 name=$1; shift
