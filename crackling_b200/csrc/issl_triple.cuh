@@ -1303,7 +1303,7 @@ __global__ void __launch_bounds__(kTripleThreads) k_scan_triple(const TripleArgs
 }
 
 // blocked, bit-sliced copy: ONE aligned read per visit.  SUBS lanes share a visit, each owning a 64-byte
-// sub-block: four 16-byte loads, then all 31 residuals at once --
+// sub-block: two 32-byte loads (load_sub_block), then all 31 residuals at once --
 //   mismatch flag of base b (one bit per slot):  x_b = (plane[2b] ^ G[2b]) | (plane[2b+1] ^ G[2b+1])
 //   count of the 8 flags per slot with a carry-save adder (4 full + 3 half adders), compared with the budget,
 // 30 LOP3 for 31 (guide, site) pairs instead of ~7 instructions per pair; no POPC, no offset lookup.
@@ -1432,7 +1432,7 @@ __device__ __forceinline__ uint32_t triple_sub_block(const TripleArgs &a, const 
     return pass;
 }
 
-// SUBS lanes share a visit, each owning one 64-byte sub-block (four 16-byte loads in flight per lane).  A lane owning the
+// SUBS lanes share a visit, each owning one 64-byte sub-block (two 32-byte loads in flight per lane).  A lane owning the
 // whole 128-byte block -- eight loads in flight, one visit-table read and one address per two sub-blocks, 64 registers and
 // 8 CTAs per SM -- measured SLOWER (5.2 against 3.8 ms per 100 000 guides, profiles/r02_ab_lane_subs.jsonl), and so did
 // asynchronous copies into a shared-memory ring (cp.async.bulk 4.99 ms, cp.async 4.29 ms against 2.74 ms for the bare
@@ -1599,7 +1599,7 @@ __global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_t
         if (live) {
             t = (v.x >> 24) & 15u; key = sh.key[t] ^ (v.x & 0xFFFFFFu);
             const uint4 *__restrict__ p = a.tv.blk + ((((uint64_t)t << 24) | key) * SUBS + sub0) * 4;
-            // read once: streaming loads, so that the visit table and the offsets keep their place in L1
+            // read once: no line left behind in L1 (where the visit table and the offsets live), evict-first in L2
 #pragma unroll
             for (int s = 0; s < LSUBS; s++) {
                 load_sub_block(p + 4 * s, q[s][0], q[s][1], q[s][2], q[s][3]);
