@@ -291,6 +291,9 @@ __device__ __forceinline__ uint2 ld_visit(const uint2 *p)
 #ifndef ISSL_TRIPLE_MIN_CTAS
 #define ISSL_TRIPLE_MIN_CTAS 10   // resident CTAs per SM the scan kernel is compiled for (48 registers); 8, 9, 12 measured slower
 #endif
+#ifndef ISSL_TRIPLE_MIN_CTAS_FLUSH
+#define ISSL_TRIPLE_MIN_CTAS_FLUSH ISSL_TRIPLE_MIN_CTAS   // the flush variant (maxDist 5-6, repeat families) spills 40 bytes at 48 registers
+#endif
 #ifndef ISSL_SUB_NOEARLY
 #define ISSL_SUB_NOEARLY 1        // 1: an empty sub-block is compared like any other (no branch; its validity mask is empty)
 #endif
@@ -1447,7 +1450,7 @@ __device__ __forceinline__ uint32_t triple_sub_block(const TripleArgs &a, const 
 // then sorted and finished by this CTA, heavy_finish) or, without that buffer, into the general pipeline's -- and a hit
 // that found the list full is tried again afterwards: nothing is ever dropped and nothing leaves the CTA hit by hit.
 template <int SUBS, bool FUSED, bool FLUSH, bool GATES = false>
-__global__ void __launch_bounds__(kTripleThreads, ISSL_TRIPLE_MIN_CTAS) k_scan_triple_blocked(const TripleArgs a)
+__global__ void __launch_bounds__(kTripleThreads, FLUSH ? ISSL_TRIPLE_MIN_CTAS_FLUSH : ISSL_TRIPLE_MIN_CTAS) k_scan_triple_blocked(const TripleArgs a)
 {
     constexpr int LSUBS = 1;   // sub-blocks per lane
     const uint32_t guide = a.guideList ? a.guideList[blockIdx.x] : blockIdx.x;   // (the guides the warp-per-guide kernel left)
